@@ -1,0 +1,676 @@
+// b200rt_api.cu -- the C ABI (include/b200rt.h): context, uploads, orchestration of the
+// traversal / influence / solve / brightness kernels.  Host code only.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+#include <new>
+#include <vector>
+#include "common.hpp"
+
+using namespace b200rt;
+
+namespace {
+
+constexpr size_t SCRATCH_BUDGET_BYTES = size_t(1) << 31;   // boundary-list scratch per batch (2 GiB of 180 GB)
+
+struct PhaseTimer {
+  b200rt_ctx *c;
+  int phase;
+  cudaEvent_t a, b;
+  PhaseTimer(b200rt_ctx *ctx, int ph) : c(ctx), phase(ph) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+  }
+  void stop(int launches) {
+    cudaEventRecord(b, c->stream);
+    pending().push_back({phase, launches, a, b});
+  }
+  struct Rec { int phase, launches; cudaEvent_t a, b; };
+  static std::vector<Rec> &pending() { static thread_local std::vector<Rec> v; return v; }
+  static void reset(b200rt_ctx *c) {
+    for (int p = 0; p < PH_COUNT; p++) { c->phase_ms[p] = 0; c->phase_launches[p] = 0; }
+    for (auto &r : pending()) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    pending().clear();
+  }
+  static void collect(b200rt_ctx *c) {   // call after the stream has been synchronised
+    for (auto &r : pending()) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) c->phase_ms[r.phase] += ms;
+      c->phase_launches[r.phase] += r.launches;
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    pending().clear();
+  }
+};
+
+// B200RT_DEBUG_SYNC=1: synchronise after every launch so a fault is attributed to its kernel
+int dbg_sync(b200rt_ctx *c, const char *what) {
+  static const bool on = getenv("B200RT_DEBUG_SYNC") != nullptr;
+  if (!on) return B200RT_OK;
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return fail(c, B200RT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return B200RT_OK;
+}
+#define DBG(c, what) do { if (int rc__ = dbg_sync(c, what)) return rc__; } while (0)
+
+template <class Real>
+GridView<Real> &gv(b200rt_ctx *c) { return *static_cast<GridView<Real> *>(c->grid_view); }
+
+template <class Real>
+EmissionView<Real> em_view(b200rt_ctx *c, int e) {
+  const Emission &E = c->em[e];
+  const int n = c->hg.n_vox;
+  const Real *t = E.tabs.as<Real>();
+  EmissionView<Real> v;
+  v.T_ratio = t + 0 * n; v.density = t + 1 * n; v.dtau_species = t + 2 * n; v.dtau_absorber = t + 3 * n;
+  v.T_ratio_pt = t + 4 * n; v.density_pt = t + 5 * n; v.dtau_species_pt = t + 6 * n; v.dtau_absorber_pt = t + 7 * n;
+  v.phi = E.phi.as<Real>();
+  v.sourcefn = E.S_real.as<Real>();
+  v.branching = (Real) E.branching; v.sigma_ref = (Real) E.sigma_ref; v.g_factor = (Real) E.g_factor;
+  return v;
+}
+
+template <class Real>
+int ensure_lists(b200rt_ctx *c, long long n_rays, ListView<Real> *lv) {
+  const int cap = c->hg.cap;
+  B200RT_CUDA(c, c->list_dist.ensure((size_t) n_rays * cap * sizeof(Real)));
+  B200RT_CUDA(c, c->list_ent.ensure((size_t) n_rays * cap * sizeof(int)));
+  B200RT_CUDA(c, c->list_len.ensure((size_t) n_rays * sizeof(int)));
+  B200RT_CUDA(c, c->list_flag.ensure((size_t) n_rays * sizeof(int)));
+  lv->dist = c->list_dist.as<Real>(); lv->ent = c->list_ent.as<int>();
+  lv->len = c->list_len.as<int>(); lv->flag = c->list_flag.as<int>(); lv->cap = cap;
+  return B200RT_OK;
+}
+
+long long batch_capacity(b200rt_ctx *c, size_t real_bytes) {
+  const size_t per_ray = (size_t) c->hg.cap * (real_bytes + sizeof(int)) + 2 * sizeof(int);
+  long long n = (long long) (SCRATCH_BUDGET_BYTES / per_ray);
+  return std::max<long long>(n, 1);
+}
+
+int check_overflow(b200rt_ctx *c) {
+  int flag = 0;
+  B200RT_CUDA(c, cudaMemcpyAsync(&flag, c->work_counter.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (flag)
+    return fail(c, B200RT_ERR_CAPACITY, "a ray crossed more than 2*n_rb+n_sb boundaries (crossing list capacity)");
+  return B200RT_OK;
+}
+
+// upload a host double array into a device Real array (widening/narrowing on the device)
+template <class Real>
+int upload_real(b200rt_ctx *c, const double *src, Real *dst, size_t n, DevBuf &stage);
+template <>
+int upload_real<double>(b200rt_ctx *c, const double *src, double *dst, size_t n, DevBuf &) {
+  B200RT_CUDA(c, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return B200RT_OK;
+}
+template <>
+int upload_real<float>(b200rt_ctx *c, const double *src, float *dst, size_t n, DevBuf &stage) {
+  B200RT_CUDA(c, stage.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, cudaMemcpyAsync(stage.p, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  B200RT_CUDA(c, launch_convert<float>(stage.as<double>(), dst, (long long) n, c->stream));
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));   // stage is reused by the caller
+  return B200RT_OK;
+}
+
+// ------------------------------------------------------------------ influence
+template <class Real>
+int influence_impl(b200rt_ctx *c, int v_begin, int v_end) {
+  GridView<Real> &g = gv<Real>(c);
+  const int n_vox = g.n_vox;
+  PhaseTimer::reset(c);
+  B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  B200RT_CUDA(c, cudaMemsetAsync(c->step_counter.p, 0, sizeof(unsigned long long), c->stream));
+  for (int e = 0; e < c->n_em; e++) {
+    Emission &E = c->em[e];
+    if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
+    if (v_end > v_begin)
+      B200RT_CUDA(c, cudaMemsetAsync(E.K.as<double>() + (size_t) v_begin * n_vox, 0,
+                                     (size_t) (v_end - v_begin) * n_vox * sizeof(double), c->stream));
+  }
+  const long long cap_rays = batch_capacity(c, sizeof(Real));
+  const int vox_per_batch = (int) std::max<long long>(1, std::min<long long>(cap_rays / g.n_rays, v_end - v_begin));
+  ListView<Real> lv;
+  const long long need = std::max<long long>((long long) vox_per_batch * g.n_rays, n_vox);
+  if (int rc = ensure_lists<Real>(c, need, &lv)) return rc;
+  int *overflow = c->work_counter.as<int>() + 1;
+
+  for (int vb = v_begin; vb < v_end; vb += vox_per_batch) {
+    const int ve = std::min(v_end, vb + vox_per_batch);
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_voxel_rays<Real>(g, vb, ve, lv, overflow, c->stream));
+      t.stop(1);
+      DBG(c, "traverse_voxel_rays");
+    }
+    for (int e = 0; e < c->n_em; e++) {
+      PhaseTimer t(c, PH_INFLUENCE);
+      B200RT_CUDA(c, launch_influence<Real>(g, em_view<Real>(c, e), vb, ve, lv, c->em[e].K.as<double>(),
+                                            c->work_counter.as<int>(),
+                                            e == 0 ? c->step_counter.as<unsigned long long>() : nullptr, c->stream));
+      t.stop(1);
+      DBG(c, "influence march");
+    }
+  }
+  // single scattering: one sun-ward ray per voxel (every rank computes all of them: n_vox rays)
+  {
+    const Real *sp = c->sun_rays.as<Real>();
+    RayList<Real> rl;
+    rl.r = sp + 0 * (size_t) n_vox; rl.z = sp + 1 * (size_t) n_vox; rl.t = sp + 2 * (size_t) n_vox;
+    rl.cost = sp + 3 * (size_t) n_vox; rl.lz = sp + 4 * (size_t) n_vox;
+    const int *ip = reinterpret_cast<const int *>(sp + 5 * (size_t) n_vox);
+    rl.i_voxel = ip;
+    const int *shadow = ip + n_vox;
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, n_vox, lv, overflow, c->stream));
+      t.stop(1);
+      DBG(c, "traverse sun rays");
+    }
+    for (int e = 0; e < c->n_em; e++) {
+      PhaseTimer t(c, PH_INFLUENCE);
+      Emission &E = c->em[e];
+      B200RT_CUDA(c, launch_single_scattering<Real>(g, em_view<Real>(c, e), lv, shadow, E.S0.as<double>(),
+                                                    E.tau_sp.as<double>(), E.tau_abs.as<double>(),
+                                                    c->work_counter.as<int>(), c->stream));
+      t.stop(1);
+      DBG(c, "single scattering march");
+    }
+  }
+  unsigned long long steps = 0;
+  B200RT_CUDA(c, cudaMemcpyAsync(&steps, c->step_counter.p, sizeof(steps), cudaMemcpyDeviceToHost, c->stream));
+  if (int rc = check_overflow(c)) return rc;   // synchronises
+  PhaseTimer::collect(c);
+  c->last_steps = (long long) steps;
+  for (int e = 0; e < c->n_em; e++) { c->em[e].have_K = true; c->em[e].have_S = false; }
+  return B200RT_OK;
+}
+
+int solve_impl(b200rt_ctx *c, bool reset_timer) {
+  const int n = c->hg.n_vox;
+  if (reset_timer) PhaseTimer::reset(c);
+  for (int e = 0; e < c->n_em; e++) {
+    Emission &E = c->em[e];
+    if (!E.have_K) return fail(c, B200RT_ERR_STATE, "b200rt_solve: influence matrix not built");
+    PhaseTimer t(c, PH_SOLVE);
+    SolveResult r = {0, 0, 0};
+    if (int rc = solve_dense(c, n, E.K.as<double>(), E.branching, E.S0.as<double>(), E.S.as<double>(), &r)) return rc;
+    t.stop(r.launches);
+    E.residual = r.residual;
+    if (c->precision == B200RT_F64)
+      B200RT_CUDA(c, launch_convert<double>(E.S.as<double>(), E.S_real.as<double>(), n, c->stream));
+    else
+      B200RT_CUDA(c, launch_convert<float>(E.S.as<double>(), E.S_real.as<float>(), n, c->stream));
+    E.have_S = true;
+  }
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  PhaseTimer::collect(c);
+  return B200RT_OK;
+}
+
+// ------------------------------------------------------------------ brightness
+template <class Real>
+int brightness_impl(b200rt_ctx *c, int n_subsamples) {
+  if (n_subsamples == 1 || n_subsamples < 0)
+    return fail(c, B200RT_ERR_ARG, "n_subsamples must be 0 or > 1 (RT_grid.hpp:237)");
+  if (c->n_los <= 0) return fail(c, B200RT_ERR_STATE, "no lines of sight uploaded");
+  for (int e = 0; e < c->n_em; e++)
+    if (!c->em[e].have_S) return fail(c, B200RT_ERR_STATE, "source function not available (solve or set_sourcefn first)");
+  GridView<Real> &g = gv<Real>(c);
+  PhaseTimer::reset(c);
+  B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  const long long n = c->n_los;
+  const long long per_batch = std::min<long long>(batch_capacity(c, sizeof(Real)), n);
+  ListView<Real> lv;
+  if (int rc = ensure_lists<Real>(c, per_batch, &lv)) return rc;
+  B200RT_CUDA(c, c->los_out.ensure((size_t) c->n_em * 4 * n * sizeof(Real)));
+  const Real *li = c->los_in.as<Real>();
+  EmissionView<Real> ev[MAX_EMISSIONS];
+  for (int e = 0; e < c->n_em; e++) ev[e] = em_view<Real>(c, e);
+  int *overflow = c->work_counter.as<int>() + 1;
+  for (long long first = 0; first < n; first += per_batch) {
+    const long long count = std::min(per_batch, n - first);
+    RayList<Real> rl;
+    rl.r = li + 3 * n + first; rl.z = li + 2 * n + first; rl.t = li + 4 * n + first;
+    rl.cost = li + 8 * n + first; rl.lz = li + 7 * n + first; rl.i_voxel = nullptr;
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, count, lv, overflow, c->stream));
+      t.stop(1);
+    }
+    {
+      PhaseTimer t(c, PH_BRIGHTNESS);
+      B200RT_CUDA(c, launch_brightness<Real>(g, ev, c->n_em, li, n, first, count, lv, n_subsamples,
+                                             c->los_out.as<Real>(), n, c->stream));
+      t.stop(1);
+    }
+  }
+  if (int rc = check_overflow(c)) return rc;
+  PhaseTimer::collect(c);
+  c->los_done = true;
+  return B200RT_OK;
+}
+
+template <class Real>
+int los_upload_impl(b200rt_ctx *c, int n, const double *const src[9]) {
+  B200RT_CUDA(c, c->los_in.ensure((size_t) 9 * n * sizeof(Real)));
+  DevBuf stage;
+  int rc = B200RT_OK;
+  for (int a = 0; a < 9 && rc == B200RT_OK; a++)
+    rc = upload_real<Real>(c, src[a], c->los_in.as<Real>() + (size_t) a * n, n, stage);
+  if (rc == B200RT_OK) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(c, B200RT_ERR_CUDA, cudaGetErrorString(e));
+  }
+  stage.release();
+  c->n_los = n;
+  c->los_done = false;
+  return rc;
+}
+
+template <class Real>
+int los_download_impl(b200rt_ctx *c, double *const dst[4]) {
+  const long long n = c->n_los;
+  const Real *o = c->los_out.as<Real>();
+  DevBuf stage;
+  for (int e = 0; e < c->n_em; e++)
+    for (int q = 0; q < 4; q++) {
+      if (!dst[q]) continue;
+      const Real *src = o + ((size_t) e * 4 + q) * n;
+      double *out = dst[q] + (size_t) e * n;
+      if (sizeof(Real) == sizeof(double)) {
+        B200RT_CUDA(c, cudaMemcpyAsync(out, src, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      } else {
+        std::vector<float> tmp(n);
+        B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (long long i = 0; i < n; i++) out[i] = tmp[i];
+      }
+    }
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  stage.release();
+  return B200RT_OK;
+}
+
+// compact fixed-stride device lists into the caller's concatenated arrays
+template <class Real>
+int fetch_lists(b200rt_ctx *c, const ListView<Real> &lv, long long n_rays, long long capacity, long long *pos,
+                int *len, int *exits_bottom, int *entering, double *distance) {
+  const int cap = lv.cap;
+  std::vector<int> hl(n_rays), hf(n_rays), he((size_t) n_rays * cap);
+  std::vector<Real> hd((size_t) n_rays * cap);
+  B200RT_CUDA(c, cudaMemcpyAsync(hl.data(), lv.len, n_rays * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, cudaMemcpyAsync(hf.data(), lv.flag, n_rays * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, cudaMemcpyAsync(he.data(), lv.ent, (size_t) n_rays * cap * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, cudaMemcpyAsync(hd.data(), lv.dist, (size_t) n_rays * cap * sizeof(Real), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (long long i = 0; i < n_rays; i++) {
+    len[i] = hl[i];
+    exits_bottom[i] = hf[i] & 1;
+    if (*pos + hl[i] > capacity) return fail(c, B200RT_ERR_ARG, "output capacity too small for the boundary lists");
+    for (int k = 0; k < hl[i]; k++) {
+      entering[*pos + k] = he[(size_t) i * cap + k];
+      distance[*pos + k] = (double) hd[(size_t) i * cap + k];
+    }
+    *pos += hl[i];
+  }
+  return B200RT_OK;
+}
+
+template <class Real>
+int traverse_voxel_rays_impl(b200rt_ctx *c, int v_begin, int v_end, long long capacity, int *len, int *exits_bottom,
+                             int *entering, double *distance, long long *n_entries) {
+  GridView<Real> &g = gv<Real>(c);
+  B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  const long long cap_rays = std::min<long long>(batch_capacity(c, sizeof(Real)), 1 << 20);
+  const int vpb = (int) std::max<long long>(1, std::min<long long>(cap_rays / g.n_rays, v_end - v_begin));
+  ListView<Real> lv;
+  if (int rc = ensure_lists<Real>(c, (long long) vpb * g.n_rays, &lv)) return rc;
+  long long pos = 0;
+  for (int vb = v_begin; vb < v_end; vb += vpb) {
+    const int ve = std::min(v_end, vb + vpb);
+    B200RT_CUDA(c, launch_traverse_voxel_rays<Real>(g, vb, ve, lv, c->work_counter.as<int>() + 1, c->stream));
+    const long long nr = (long long) (ve - vb) * g.n_rays;
+    const long long off = (long long) (vb - v_begin) * g.n_rays;
+    if (int rc = fetch_lists<Real>(c, lv, nr, capacity, &pos, len + off, exits_bottom + off, entering, distance)) return rc;
+  }
+  if (n_entries) *n_entries = pos;
+  return check_overflow(c);
+}
+
+template <class Real>
+int traverse_los_impl(b200rt_ctx *c, long long capacity, int *len, int *exits_bottom, int *entering,
+                      double *distance, long long *n_entries) {
+  GridView<Real> &g = gv<Real>(c);
+  if (c->n_los <= 0) return fail(c, B200RT_ERR_STATE, "no lines of sight uploaded");
+  B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  const long long n = c->n_los;
+  const long long per_batch = std::min<long long>(std::min<long long>(batch_capacity(c, sizeof(Real)), 1 << 18), n);
+  ListView<Real> lv;
+  if (int rc = ensure_lists<Real>(c, per_batch, &lv)) return rc;
+  const Real *li = c->los_in.as<Real>();
+  long long pos = 0;
+  for (long long first = 0; first < n; first += per_batch) {
+    const long long count = std::min(per_batch, n - first);
+    RayList<Real> rl;
+    rl.r = li + 3 * n + first; rl.z = li + 2 * n + first; rl.t = li + 4 * n + first;
+    rl.cost = li + 8 * n + first; rl.lz = li + 7 * n + first; rl.i_voxel = nullptr;
+    B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, count, lv, c->work_counter.as<int>() + 1, c->stream));
+    if (int rc = fetch_lists<Real>(c, lv, count, capacity, &pos, len + first, exits_bottom + first, entering, distance)) return rc;
+  }
+  if (n_entries) *n_entries = pos;
+  return check_overflow(c);
+}
+
+template <class Real>
+int set_singlet_impl(b200rt_ctx *c, int e, const double *const arr[8]) {
+  const int n = c->hg.n_vox;
+  Emission &E = c->em[e];
+  B200RT_CUDA(c, E.tabs.ensure((size_t) 8 * n * sizeof(Real)));
+  B200RT_CUDA(c, E.phi.ensure((size_t) n * N_LAMBDA * sizeof(Real)));
+  B200RT_CUDA(c, E.K.ensure((size_t) n * n * sizeof(double)));
+  B200RT_CUDA(c, E.S0.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.tau_sp.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.tau_abs.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.S.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.S_real.ensure(n * sizeof(Real)));
+  DevBuf stage;
+  int rc = B200RT_OK;
+  for (int a = 0; a < 8 && rc == B200RT_OK; a++)
+    rc = upload_real<Real>(c, arr[a], E.tabs.as<Real>() + (size_t) a * n, n, stage);
+  if (rc == B200RT_OK) {
+    cudaError_t er = launch_phi_table<Real>(E.tabs.as<Real>(), n, E.phi.as<Real>(), c->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(c->stream);
+    if (er != cudaSuccess) rc = fail(c, B200RT_ERR_CUDA, cudaGetErrorString(er));
+  }
+  stage.release();
+  return rc;
+}
+
+bool is64(const b200rt_ctx *c) { return c->precision == B200RT_F64; }
+
+} // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int b200rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int b200rt_create(int device, int precision, b200rt_ctx **out) {
+  if (!out || (precision != B200RT_F64 && precision != B200RT_F32)) return B200RT_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return B200RT_ERR_CUDA;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return B200RT_ERR_CUDA;
+  b200rt_ctx *c = new (std::nothrow) b200rt_ctx;
+  if (!c) return B200RT_ERR_NOMEM;
+  c->device = device;
+  c->precision = precision;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return B200RT_ERR_CUDA; }
+  if (c->work_counter.ensure(4 * sizeof(int)) != cudaSuccess || c->step_counter.ensure(sizeof(unsigned long long)) != cudaSuccess) {
+    delete c;
+    return B200RT_ERR_CUDA;
+  }
+  *out = c;
+  return B200RT_OK;
+}
+
+int b200rt_destroy(b200rt_ctx *c) {
+  if (!c) return B200RT_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  DevBuf *bufs[] = {&c->grid_tables, &c->sun_rays, &c->list_dist, &c->list_ent, &c->list_len, &c->list_flag,
+                    &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->lu, &c->lu_dinv, &c->lu_flag};
+  for (DevBuf *b : bufs) b->release();
+  for (int e = 0; e < MAX_EMISSIONS; e++) {
+    Emission &E = c->em[e];
+    DevBuf *eb[] = {&E.tabs, &E.phi, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real};
+    for (DevBuf *b : eb) b->release();
+  }
+  if (c->grid_view) ::operator delete(c->grid_view);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return B200RT_OK;
+}
+
+const char *b200rt_last_error(const b200rt_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int b200rt_synchronize(b200rt_ctx *c) {
+  if (!c) return B200RT_ERR_ARG;
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return B200RT_OK;
+}
+
+int b200rt_make_grid_sph(int precision, int n_rb, int n_sb, int n_theta, int n_phi, const double *rb, int szamethod,
+                         int raymethod, double *sb, double *pts_r, double *pts_s, double *ray_t, double *ray_p,
+                         double *ray_domega) {
+  if (n_rb < 2 || n_sb < 3 || n_theta < 2 || n_phi < 1 || !rb) return B200RT_ERR_ARG;
+  if (precision == B200RT_F64) make_grid_sph<double>(n_rb, n_sb, n_theta, n_phi, rb, szamethod, raymethod, sb, pts_r, pts_s, ray_t, ray_p, ray_domega);
+  else make_grid_sph<float>(n_rb, n_sb, n_theta, n_phi, rb, szamethod, raymethod, sb, pts_r, pts_s, ray_t, ray_p, ray_domega);
+  return B200RT_OK;
+}
+
+int b200rt_set_grid_sph(b200rt_ctx *c, int n_rb, int n_sb, int n_rays, const double *rb, const double *sb,
+                        const double *pts_r, const double *pts_s, const double *ray_t, const double *ray_p,
+                        const double *ray_domega) {
+  if (!c) return B200RT_ERR_ARG;
+  if (n_rb < 2 || n_sb < 3 || n_rays < 1 || !rb || !sb || !pts_r || !pts_s || !ray_t || !ray_p || !ray_domega)
+    return fail(c, B200RT_ERR_ARG, "b200rt_set_grid_sph: bad argument");
+  cudaSetDevice(c->device);
+  HostGrid &h = c->hg;
+  h.n_rb = n_rb; h.n_sb = n_sb; h.n_vox = (n_rb - 1) * (n_sb - 1); h.n_rays = n_rays; h.cap = 2 * n_rb + n_sb;
+  h.rb.assign(rb, rb + n_rb); h.sb.assign(sb, sb + n_sb);
+  h.pts_r.assign(pts_r, pts_r + n_rb - 1); h.pts_s.assign(pts_s, pts_s + n_sb - 1);
+  h.ray_t.assign(ray_t, ray_t + n_rays); h.ray_p.assign(ray_p, ray_p + n_rays);
+  h.ray_domega.assign(ray_domega, ray_domega + n_rays);
+  int rc = is64(c) ? upload_grid<double>(c) : upload_grid<float>(c);
+  if (rc) return rc;
+  c->have_grid = true;
+  c->n_em = 0;
+  for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
+  return B200RT_OK;
+}
+
+int b200rt_set_singlet(b200rt_ctx *c, int e, int n_em, double branching, double T_ref, double sigma_ref, double g,
+                       const double *T_ratio, const double *density, const double *dtau_species,
+                       const double *dtau_absorber, const double *T_ratio_pt, const double *density_pt,
+                       const double *dtau_species_pt, const double *dtau_absorber_pt) {
+  if (!c) return B200RT_ERR_ARG;
+  if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "set the grid before the emissions");
+  if (n_em < 1 || n_em > MAX_EMISSIONS || e < 0 || e >= n_em) return fail(c, B200RT_ERR_ARG, "bad emission index");
+  const double *arr[8] = {T_ratio, density, dtau_species, dtau_absorber, T_ratio_pt, density_pt, dtau_species_pt, dtau_absorber_pt};
+  for (auto p : arr) if (!p) return fail(c, B200RT_ERR_ARG, "null emission table");
+  cudaSetDevice(c->device);
+  c->n_em = n_em;
+  Emission &E = c->em[e];
+  E.branching = branching; E.T_ref = T_ref; E.sigma_ref = sigma_ref; E.g_factor = g;
+  int rc = is64(c) ? set_singlet_impl<double>(c, e, arr) : set_singlet_impl<float>(c, e, arr);
+  if (rc) return rc;
+  E.defined = true; E.have_K = false; E.have_S = false; E.residual = -1;
+  return B200RT_OK;
+}
+
+int b200rt_set_g_factor(b200rt_ctx *c, int e, double g) {
+  if (!c || e < 0 || e >= MAX_EMISSIONS) return B200RT_ERR_ARG;
+  c->em[e].g_factor = g;
+  return B200RT_OK;
+}
+
+int b200rt_influence(b200rt_ctx *c, int v_begin, int v_end) {
+  if (!c) return B200RT_ERR_ARG;
+  if (!c->have_grid || c->n_em < 1) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
+  if (v_begin < 0 || v_end > c->hg.n_vox || v_begin > v_end) return fail(c, B200RT_ERR_ARG, "bad voxel range");
+  cudaSetDevice(c->device);
+  return is64(c) ? influence_impl<double>(c, v_begin, v_end) : influence_impl<float>(c, v_begin, v_end);
+}
+
+int b200rt_solve(b200rt_ctx *c) {
+  if (!c) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  return solve_impl(c, true);
+}
+
+int b200rt_generate_S(b200rt_ctx *c) {
+  if (!c) return B200RT_ERR_ARG;
+  int rc = b200rt_influence(c, 0, c->hg.n_vox);
+  if (rc) return rc;
+  return solve_impl(c, false);
+}
+
+int b200rt_last_step_count(b200rt_ctx *c, long long *n) {
+  if (!c || !n) return B200RT_ERR_ARG;
+  *n = c->last_steps;
+  return B200RT_OK;
+}
+
+int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp, double *tab) {
+  if (!c || e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  Emission &E = c->em[e];
+  const size_t nb = (size_t) c->hg.n_vox * sizeof(double);
+  if (S) {
+    if (!E.have_S) return fail(c, B200RT_ERR_STATE, "source function not solved");
+    B200RT_CUDA(c, cudaMemcpyAsync(S, E.S.p, nb, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if ((S0 || tsp || tab) && !E.have_K) return fail(c, B200RT_ERR_STATE, "influence pass not run");
+  if (S0) B200RT_CUDA(c, cudaMemcpyAsync(S0, E.S0.p, nb, cudaMemcpyDeviceToHost, c->stream));
+  if (tsp) B200RT_CUDA(c, cudaMemcpyAsync(tsp, E.tau_sp.p, nb, cudaMemcpyDeviceToHost, c->stream));
+  if (tab) B200RT_CUDA(c, cudaMemcpyAsync(tab, E.tau_abs.p, nb, cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return B200RT_OK;
+}
+
+int b200rt_get_influence(b200rt_ctx *c, int e, int layout, double *K) {
+  if (!c || e < 0 || e >= c->n_em || !K) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  Emission &E = c->em[e];
+  if (!E.have_K) return fail(c, B200RT_ERR_STATE, "influence matrix not built");
+  const size_t n = c->hg.n_vox;
+  if (layout == B200RT_ROW_MAJOR) {
+    B200RT_CUDA(c, cudaMemcpyAsync(K, E.K.p, n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  } else {
+    std::vector<double> tmp(n * n);
+    B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), E.K.p, n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++) for (size_t j = 0; j < n; j++) K[j * n + i] = tmp[i * n + j];
+  }
+  return B200RT_OK;
+}
+
+int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
+  if (!c || e < 0 || e >= c->n_em || !S) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  Emission &E = c->em[e];
+  if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
+  const int n = c->hg.n_vox;
+  B200RT_CUDA(c, cudaMemcpyAsync(E.S.p, S, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (is64(c)) B200RT_CUDA(c, launch_convert<double>(E.S.as<double>(), E.S_real.as<double>(), n, c->stream));
+  else B200RT_CUDA(c, launch_convert<float>(E.S.as<double>(), E.S_real.as<float>(), n, c->stream));
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  E.have_S = true;
+  return B200RT_OK;
+}
+
+int b200rt_last_residual(b200rt_ctx *c, int e, double *r) {
+  if (!c || e < 0 || e >= c->n_em || !r) return B200RT_ERR_ARG;
+  *r = c->em[e].residual;
+  return B200RT_OK;
+}
+
+int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, void **tab) {
+  if (!c || e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
+  Emission &E = c->em[e];
+  if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
+  if (K) *K = E.K.p;
+  if (S0) *S0 = E.S0.p;
+  if (tsp) *tsp = E.tau_sp.p;
+  if (tab) *tab = E.tau_abs.p;
+  E.have_K = true;   // the caller may fill rows from peers
+  return B200RT_OK;
+}
+
+int b200rt_sourcefn_dev(b200rt_ctx *c, int e, void **S) {
+  if (!c || e < 0 || e >= c->n_em || !S) return B200RT_ERR_ARG;
+  *S = c->em[e].S.p;
+  return B200RT_OK;
+}
+
+int b200rt_los_from_MSO(int precision, int n, const double *loc, const double *dir, double *x, double *y, double *z,
+                        double *r, double *t, double *lx, double *ly, double *lz, double *cost) {
+  if (n < 0 || !loc || !dir || !x || !y || !z || !r || !t || !lx || !ly || !lz || !cost) return B200RT_ERR_ARG;
+  if (precision == B200RT_F64) los_from_MSO<double>(n, loc, dir, x, y, z, r, t, lx, ly, lz, cost);
+  else los_from_MSO<float>(n, loc, dir, x, y, z, r, t, lx, ly, lz, cost);
+  return B200RT_OK;
+}
+
+int b200rt_los_upload(b200rt_ctx *c, int n, const double *x, const double *y, const double *z, const double *r,
+                      const double *t, const double *lx, const double *ly, const double *lz, const double *cost) {
+  if (!c) return B200RT_ERR_ARG;
+  if (n <= 0) return fail(c, B200RT_ERR_ARG, "there must be at least one observation to simulate");
+  const double *src[9] = {x, y, z, r, t, lx, ly, lz, cost};
+  for (auto p : src) if (!p) return fail(c, B200RT_ERR_ARG, "null line-of-sight array");
+  cudaSetDevice(c->device);
+  return is64(c) ? los_upload_impl<double>(c, n, src) : los_upload_impl<float>(c, n, src);
+}
+
+int b200rt_brightness_resident(b200rt_ctx *c, int n_subsamples) {
+  if (!c) return B200RT_ERR_ARG;
+  if (!c->have_grid || c->n_em < 1) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
+  cudaSetDevice(c->device);
+  return is64(c) ? brightness_impl<double>(c, n_subsamples) : brightness_impl<float>(c, n_subsamples);
+}
+
+int b200rt_los_download(b200rt_ctx *c, double *B, double *tsp, double *tab, double *col) {
+  if (!c) return B200RT_ERR_ARG;
+  if (!c->los_done) return fail(c, B200RT_ERR_STATE, "no brightness result to download");
+  cudaSetDevice(c->device);
+  double *dst[4] = {B, tsp, tab, col};
+  return is64(c) ? los_download_impl<double>(c, dst) : los_download_impl<float>(c, dst);
+}
+
+int b200rt_brightness(b200rt_ctx *c, int n, const double *x, const double *y, const double *z, const double *r,
+                      const double *t, const double *lx, const double *ly, const double *lz, const double *cost,
+                      int n_subsamples, double *B, double *tsp, double *tab, double *col) {
+  int rc = b200rt_los_upload(c, n, x, y, z, r, t, lx, ly, lz, cost);
+  if (rc) return rc;
+  rc = b200rt_brightness_resident(c, n_subsamples);
+  if (rc) return rc;
+  return b200rt_los_download(c, B, tsp, tab, col);
+}
+
+int b200rt_traverse_voxel_rays(b200rt_ctx *c, int v_begin, int v_end, long long capacity, int *len, int *eb,
+                               int *entering, double *distance, long long *n_entries) {
+  if (!c || !len || !eb || !entering || !distance) return B200RT_ERR_ARG;
+  if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "grid not set");
+  if (v_begin < 0 || v_end > c->hg.n_vox || v_begin > v_end) return fail(c, B200RT_ERR_ARG, "bad voxel range");
+  cudaSetDevice(c->device);
+  return is64(c) ? traverse_voxel_rays_impl<double>(c, v_begin, v_end, capacity, len, eb, entering, distance, n_entries)
+                 : traverse_voxel_rays_impl<float>(c, v_begin, v_end, capacity, len, eb, entering, distance, n_entries);
+}
+
+int b200rt_traverse_los(b200rt_ctx *c, long long capacity, int *len, int *eb, int *entering, double *distance,
+                        long long *n_entries) {
+  if (!c || !len || !eb || !entering || !distance) return B200RT_ERR_ARG;
+  if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "grid not set");
+  cudaSetDevice(c->device);
+  return is64(c) ? traverse_los_impl<double>(c, capacity, len, eb, entering, distance, n_entries)
+                 : traverse_los_impl<float>(c, capacity, len, eb, entering, distance, n_entries);
+}
+
+int b200rt_last_kernel_ms(b200rt_ctx *c, int phase, float *ms, int *n_launches) {
+  if (!c || phase < 0 || phase >= PH_COUNT) return B200RT_ERR_ARG;
+  if (ms) *ms = c->phase_ms[phase];
+  if (n_launches) *n_launches = c->phase_launches[phase];
+  return B200RT_OK;
+}
+
+} // extern "C"

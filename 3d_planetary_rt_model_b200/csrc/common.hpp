@@ -1,0 +1,205 @@
+// common.hpp -- internal declarations shared by the translation units of
+// lib3d_planetary_rt_b200.so.  Nothing here is part of the C ABI (include/b200rt.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/b200rt.h"
+
+namespace b200rt {
+
+constexpr int N_LAMBDA = 20;        // singlet_CFR_tracker::n_lambda (reference los_tracker.hpp:122)
+constexpr int MAX_EMISSIONS = 2;    // observation_fit drives Ly alpha + Ly beta together
+constexpr int NUM_SMS = 148;        // B200
+
+// ------------------------------------------------------------------ device buffers
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes && p) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    if (need == 0) need = 16;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------ grid tables (device view)
+// Everything the traversal, the interpolation and the ray construction read.
+// All of it is computed on the host (grid_host.cpp) with the libm calls the
+// reference makes, then uploaded once per b200rt_set_grid_sph.
+template <class Real>
+struct GridView {
+  int n_rb, n_sb, n_vox, n_rays, cap;
+  const Real *rb;          // [n_rb]   radial boundaries
+  const Real *sph_R2;      // [n_rb]   (rb/1e9)^2            sphere::set_radius
+  const Real *sb;          // [n_sb]   sza boundaries
+  const Real *cone_cos;    // [n_sb-2] cos(sb[k+1])           cone::set_angle
+  const Real *cone_cos2;   // [n_sb-2]
+  const Real *pts_r;       // [n_rb-1]
+  const Real *log_pts_r;   // [n_rb-1]
+  const Real *pts_s;       // [n_sb-1]
+  const Real *vox_z;       // [n_vox]  r*cos(t) of the voxel point   atmo_point::rtp
+  const double *col_ct;    // [n_sb-1] cos(pt.t) as the double libm call ptray makes
+  const double *col_st;    // [n_sb-1] sin(pt.t)
+  const Real *ray_cost;    // [n_rays] std::cos(ray.t)         atmo_ray::tp
+  const Real *ray_sint;    // [n_rays]
+  const double *ray_cp;    // [n_rays] cos(ray.p) (double call in ptray)
+  const Real *ray_domega;  // [n_rays]
+};
+
+// boundary lists produced by the traversal kernel for a batch of rays: fixed stride
+// `cap` per ray so that no prefix pass is needed; only the used part is ever touched.
+template <class Real>
+struct ListView {
+  Real *dist;      // [n_rays_batch][cap]
+  int *ent;        // [n_rays_batch][cap]   boundary::entering
+  int *len;        // [n_rays_batch]        trimmed length (0 = ray misses the grid)
+  int *flag;       // [n_rays_batch]        bit0 = exits_bottom, bit1 = capacity overflow
+  int cap;
+};
+
+// explicit ray descriptors (sun-ward rays, lines of sight)
+template <class Real>
+struct RayList {
+  const Real *r, *z, *t, *cost, *lz;
+  const int *i_voxel;   // may be null => -1 (search for the origin voxel)
+};
+
+// per-emission tables (device view)
+template <class Real>
+struct EmissionView {
+  const Real *T_ratio, *density, *dtau_species, *dtau_absorber;              // voxel averages
+  const Real *T_ratio_pt, *density_pt, *dtau_species_pt, *dtau_absorber_pt;  // voxel points
+  const Real *phi;        // [n_vox][N_LAMBDA] line shape exp(-lambda_i^2 T_ratio) of the averages
+  const Real *sourcefn;   // [n_vox]
+  Real branching, sigma_ref, g_factor;
+};
+
+// ------------------------------------------------------------------ host-side state
+struct HostGrid {
+  int n_rb = 0, n_sb = 0, n_vox = 0, n_rays = 0, cap = 0;
+  std::vector<double> rb, sb, pts_r, pts_s, ray_t, ray_p, ray_domega;
+};
+
+struct Emission {
+  bool defined = false, have_K = false, have_S = false;
+  double branching = 1, T_ref = 0, sigma_ref = 0, g_factor = 0;
+  double residual = -1;
+  DevBuf tabs;     // 8 * n_vox Real
+  DevBuf phi;      // n_vox * N_LAMBDA Real
+  DevBuf K;        // n_vox^2 double, row major
+  DevBuf S0, tau_sp, tau_abs;  // n_vox double
+  DevBuf S;        // n_vox double (solution)
+  DevBuf S_real;   // n_vox Real   (what the brightness kernel reads)
+};
+
+enum Phase { PH_TRAVERSE = 0, PH_INFLUENCE = 1, PH_SOLVE = 2, PH_BRIGHTNESS = 3, PH_COUNT = 4 };
+
+} // namespace b200rt
+
+struct b200rt_ctx {
+  int device = 0;
+  int precision = B200RT_F64;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  bool have_grid = false;
+  b200rt::HostGrid hg;
+  b200rt::DevBuf grid_tables;       // one slab holding every GridView array
+  void *grid_view = nullptr;        // heap GridView<Real> (host struct of device pointers)
+  b200rt::DevBuf sun_rays;          // RayList arrays for the n_vox sun-ward rays + shadow flags
+  std::vector<int> shadow;          // host copy of the shadow test per voxel
+
+  int n_em = 0;
+  b200rt::Emission em[b200rt::MAX_EMISSIONS];
+
+  // traversal scratch (one batch of rays)
+  b200rt::DevBuf list_dist, list_ent, list_len, list_flag;
+  long long batch_rays = 0;
+  b200rt::DevBuf work_counter;      // 2 ints: dynamic work index, capacity-overflow flag
+  b200rt::DevBuf step_counter;      // unsigned long long
+  long long last_steps = 0;
+
+  // lines of sight
+  int n_los = 0;
+  b200rt::DevBuf los_in;            // 9 * n_los Real: x y z r t lx ly lz cost
+  b200rt::DevBuf los_out;           // n_em * 4 * n_los Real
+  bool los_done = false;
+
+  // dense solve workspace
+  b200rt::DevBuf lu, lu_dinv, lu_flag;
+
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float phase_ms[b200rt::PH_COUNT] = {0, 0, 0, 0};
+  int phase_launches[b200rt::PH_COUNT] = {0, 0, 0, 0};
+};
+
+namespace b200rt {
+
+inline int fail(b200rt_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+#define B200RT_CUDA(ctx, call)                                                              \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return ::b200rt::fail(ctx, B200RT_ERR_CUDA,                                           \
+                            std::string(#call) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+// ---- grid_host.cpp
+template <class Real>
+int upload_grid(b200rt_ctx *c);
+template <class Real>
+void make_grid_sph(int n_rb, int n_sb, int n_theta, int n_phi, const double *rb, int szamethod,
+                   int raymethod, double *sb, double *pts_r, double *pts_s, double *ray_t,
+                   double *ray_p, double *ray_domega);
+template <class Real>
+void los_from_MSO(int n, const double *loc, const double *dir, double *x, double *y, double *z,
+                  double *r, double *t, double *lx, double *ly, double *lz, double *cost);
+
+// ---- traverse.cu  (compiled with -fmad=false: decides voxel indices)
+template <class Real>
+cudaError_t launch_traverse_voxel_rays(const GridView<Real> &g, int v_begin, int v_end,
+                                       ListView<Real> out, int *overflow_flag, cudaStream_t s);
+template <class Real>
+cudaError_t launch_traverse_list(const GridView<Real> &g, RayList<Real> rays, long long n,
+                                 ListView<Real> out, int *overflow_flag, cudaStream_t s);
+
+// ---- influence.cu
+template <class Real>
+cudaError_t launch_influence(const GridView<Real> &g, const EmissionView<Real> &em, int v_begin,
+                             int v_end, ListView<Real> lists, double *K, int *work_counter,
+                             unsigned long long *step_counter, cudaStream_t s);
+template <class Real>
+cudaError_t launch_single_scattering(const GridView<Real> &g, const EmissionView<Real> &em,
+                                     ListView<Real> lists, const int *shadow, double *S0,
+                                     double *tau_sp, double *tau_abs, int *work_counter, cudaStream_t s);
+template <class Real>
+cudaError_t launch_phi_table(const Real *T_ratio, int n_vox, Real *phi, cudaStream_t s);
+
+// ---- brightness.cu
+template <class Real>
+cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em,
+                              const Real *los_in, long long los_stride, long long first,
+                              long long count, ListView<Real> lists, int n_subsamples, Real *out,
+                              long long n_los_total, cudaStream_t s);
+
+// ---- solve.cu
+struct SolveResult { double residual; double min_margin; int launches; };
+int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const double *S0,
+                double *S, SolveResult *res);
+template <class Real>
+cudaError_t launch_convert(const double *src, Real *dst, long long n, cudaStream_t s);
+
+} // namespace b200rt

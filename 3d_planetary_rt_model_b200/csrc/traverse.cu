@@ -1,0 +1,431 @@
+// traverse.cu -- ray / voxel-boundary traversal on the device (sm_100a).
+//
+// COMPILE THIS FILE WITH -fmad=false AND WITHOUT --use_fast_math: the integer
+// voxel sequence it produces must be bit-identical to the reference CPU build
+// (x86-64, no FMA contraction), so every product/sum is rounded separately and
+// sqrt / division are the IEEE-rounded ones.  Transcendentals never appear here:
+// they are tabulated on the host (grid_host.cpp).
+//
+// What it computes (reference src/, restated; nothing is shared with RT_gpu.cu):
+//   spherical_azimuthally_symmetric_grid::ray_voxel_intersections
+//       grid/grid_spherical_azimuthally_symmetric.hpp:459-509
+//   sphere::intersections / cone::intersections      grid/intersections.cpp:58-95, 120-164
+//   boundary_set::add_intersections / sort / propagate_indices /
+//       assign_voxel_indices / trim                  grid/boundaries.hpp:131-232
+//   boundary_intersection_stepper::init_stepper      grid/boundaries.hpp:334-349
+//
+// Mapping: one warp per ray.  The reference builds the full crossing list
+// (<= 2*n_rb+n_sb entries), insertion-sorts it and then trims it to the first
+// contiguous in-grid run.  Here the lanes evaluate the primitives in parallel and
+// the trim is applied BEFORE the sort: a list entry can only be "outside the grid"
+// through its radial index, so the first in-grid entry and the first later exit are
+// found from the sphere crossings alone (two warp min-reductions over
+// (distance, insertion-slot) keys); only crossings between those two keys are
+// compacted into shared memory, ranked (stable order = (distance, slot), which is
+// what a stable insertion sort with strict '<' yields) and forward-filled.
+// The output is the trimmed boundary list of the reference, entry for entry.
+#include <cfloat>
+#include "common.hpp"
+
+namespace b200rt {
+
+namespace {
+
+template <class Real> struct Lim;
+template <> struct Lim<double> {
+  __device__ static double strict_eps() { return 1e-10; }   // Real.hpp:24
+  __device__ static double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+template <> struct Lim<float> {
+  __device__ static float strict_eps() { return 1e-5f; }    // Real.hpp:15
+  __device__ static float inf() { return __int_as_float(0x7f800000); }
+};
+
+// info word: bits 0-11 insertion slot, bit 12 dimension (0 radial, 1 sza), bits 13.. value+1
+constexpr int SLOT_BITS = 12;
+__device__ __forceinline__ int pack_info(int slot, int dim, int val) {
+  return slot | (dim << SLOT_BITS) | ((val + 1) << (SLOT_BITS + 1));
+}
+__device__ __forceinline__ int info_slot(int info) { return info & ((1 << SLOT_BITS) - 1); }
+__device__ __forceinline__ int info_dim(int info) { return (info >> SLOT_BITS) & 1; }
+__device__ __forceinline__ int info_val(int info) { return (info >> (SLOT_BITS + 1)) - 1; }
+
+template <class Real>
+__device__ __forceinline__ bool key_less(Real d1, int s1, Real d2, int s2) {
+  return d1 < d2 || (d1 == d2 && s1 < s2);
+}
+
+template <class Real>
+__device__ __forceinline__ void warp_min_key(Real &d, int &s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Real d2 = __shfl_xor_sync(0xffffffffu, d, o);
+    int s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    if (key_less(d2, s2, d, s)) { d = d2; s = s2; }
+  }
+}
+template <class Real>
+__device__ __forceinline__ void warp_max_key(Real &d, int &s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Real d2 = __shfl_xor_sync(0xffffffffu, d, o);
+    int s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    if (key_less(d, s, d2, s2)) { d = d2; s = s2; }
+  }
+}
+
+__device__ __forceinline__ bool samesign_f(double a, double b) {
+  return (a > 0 && b > 0) || (a < 0 && b < 0) || (a == 0 && b == 0);
+}
+
+// sphere::intersections + the ordering of add_intersections: first <= second, +inf = absent
+template <class Real>
+__device__ __forceinline__ int sphere_hits(Real r, Real cost, Real R2, Real &first, Real &second) {
+  const Real scale = Real(1e9);
+  const Real r_norm = r / scale;
+  const Real B = r_norm * cost;
+  const Real C = r_norm * r_norm - R2;
+  const Real discr = B * B - C;
+  Real dd[2];
+  int nh = 0;
+  if (discr > 0) {
+    const Real sq = sqrt(discr);
+    const Real d0 = (B > 0) ? -B - sq : -B + sq;
+    if (d0 > 0) { dd[nh] = d0 * scale; nh++; }
+    const Real d1 = C / d0;
+    if (d1 > 0) { dd[nh] = d1 * scale; nh++; }
+  }
+  first = second = Lim<Real>::inf();
+  if (nh == 1) first = dd[0];
+  else if (nh == 2) {
+    const bool in_order = dd[1] > dd[0];
+    first = in_order ? dd[0] : dd[1];
+    second = in_order ? dd[1] : dd[0];
+  }
+  return nh;
+}
+
+template <class Real>
+__device__ __forceinline__ int cone_hits(Real r, Real zn, Real lz, Real cost, Real ca, Real ca2, Real &first,
+                                         Real &second) {
+  const Real A = lz * lz - ca2;
+  const Real B = zn * lz - cost * ca2;
+  const Real C = zn * zn - ca2;
+  Real dd[2];
+  int nh = 0;
+  const Real tol = Lim<Real>::strict_eps();
+  if (A > tol || A < -tol) {
+    const Real discr = B * B - A * C;
+    if (discr > 0) {
+      const Real sq = sqrt(discr);
+      const Real q = (B > 0) ? -B - sq : -B + sq;
+      const Real d0 = q / A;
+      if (d0 > 0 && samesign_f(zn + d0 * lz, ca)) { dd[nh] = d0 * r; nh++; }
+      const Real d1 = C / q;
+      if (d1 > 0 && samesign_f(zn + d1 * lz, ca)) { dd[nh] = d1 * r; nh++; }
+    }
+  } else {
+    const Real d = -C / (2 * B);
+    if (d > 0 && samesign_f(zn + d * lz, ca)) { dd[nh] = d * r; nh++; }
+  }
+  first = second = Lim<Real>::inf();
+  if (nh == 1) first = dd[0];
+  else if (nh == 2) {
+    const bool in_order = dd[1] > dd[0];
+    first = in_order ? dd[0] : dd[1];
+    second = in_order ? dd[1] : dd[0];
+  }
+  return nh;
+}
+
+// find_coordinate_index (grid_spherical_azimuthally_symmetric.hpp:433-450): index of the
+// first boundary with c < b[i], minus one (n-1 if none); warp-cooperative.
+template <class Real>
+__device__ __forceinline__ int find_index(Real c, const Real *__restrict__ b, int n, int lane) {
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const bool p = (i < n) && (c < b[i]);
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (m) return base + __ffs(m) - 2;
+  }
+  return n - 1;
+}
+
+template <class Real, bool VOXEL_RAYS>
+__global__ void __launch_bounds__(128)
+traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> rl, ListView<Real> out,
+                int *overflow_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const int cap = g.cap, n_rb = g.n_rb, n_sb = g.n_sb;
+
+  // per-warp scratch
+  const size_t per_warp = ((size_t) (2 * n_rb + 2 * cap) * sizeof(Real) + (size_t) 2 * cap * sizeof(int) + 15) & ~size_t(15);
+  unsigned char *base = smem_raw + per_warp * warp;
+  Real *sph_d = reinterpret_cast<Real *>(base);            // [2*n_rb]  first/second hit per sphere
+  Real *cmp_d = sph_d + 2 * n_rb;                          // [cap]     compacted, unsorted
+  Real *srt_d = cmp_d + cap;                               // [cap]     sorted
+  int *cmp_i = reinterpret_cast<int *>(srt_d + cap);       // [cap]
+  int *srt_i = cmp_i + cap;                                // [cap]
+
+  const Real INF = Lim<Real>::inf();
+
+  for (long long ray = (long long) blockIdx.x * warps_per_block + warp; ray < n_total;
+       ray += (long long) gridDim.x * warps_per_block) {
+    // ---- ray scalars (atmo_vector::ptray for voxel rays; host-prepared otherwise)
+    Real r, z, t, cost, lz;
+    int i_voxel;
+    if (VOXEL_RAYS) {
+      const int iv = v_begin + (int) (ray / g.n_rays);
+      const int ir = (int) (ray % g.n_rays);
+      const int irad = iv / (n_sb - 1), isza = iv % (n_sb - 1);
+      r = g.pts_r[irad];
+      t = g.pts_s[isza];
+      z = g.vox_z[iv];
+      cost = g.ray_cost[ir];
+      // line_z = ray.cost*cos(pt.t) - cos(ray.p)*ray.sint*sin(pt.t)   (atmo_vec.cpp:246), in double
+      const double a = (double) cost * g.col_ct[isza];
+      const double b = (g.ray_cp[ir] * (double) g.ray_sint[ir]) * g.col_st[isza];
+      lz = (Real) (a - b);
+      i_voxel = iv;
+    } else {
+      r = rl.r[ray]; z = rl.z[ray]; t = rl.t[ray]; cost = rl.cost[ray]; lz = rl.lz[ray];
+      i_voxel = rl.i_voxel ? rl.i_voxel[ray] : -1;
+    }
+
+    // ---- origin entry (:467-477)
+    int r0, s0;
+    if (i_voxel == -1) {
+      r0 = find_index(r, g.rb, n_rb, lane);
+      s0 = find_index(t, g.sb, n_sb, lane);
+    } else {
+      r0 = i_voxel / (n_sb - 1);
+      s0 = i_voxel % (n_sb - 1);
+    }
+    const bool origin_in = (r0 >= 0 && r0 <= n_rb - 2 && s0 >= 0 && s0 <= n_sb - 2);
+
+    // ---- pass 1: spheres -> shared, and the keys of the first in-grid entry / first exit
+    for (int ir = lane; ir < n_rb; ir += 32) {
+      Real f, s;
+      sphere_hits(r, cost, g.sph_R2[ir], f, s);
+      sph_d[2 * ir] = f;
+      sph_d[2 * ir + 1] = s;
+    }
+    __syncwarp();
+
+    Real db = INF; int sb_slot = 0x7fffffff;      // key of `begin`
+    int rb_val = r0;                               // radial index at `begin`
+    if (origin_in) { db = 0; sb_slot = 0; }
+    else {
+      for (int ir = lane; ir < n_rb; ir += 32) {
+        const bool above = r > g.rb[ir];
+        const Real f = sph_d[2 * ir], s = sph_d[2 * ir + 1];
+        const int vf = above ? ir - 1 : ir;        // value set by the first hit
+        const int vs = above ? ir : ir - 1;        // value set by the second hit (2 hits only)
+        if (f < INF && vf >= 0 && vf <= n_rb - 2 && key_less(f, 1 + 2 * ir, db, sb_slot)) { db = f; sb_slot = 1 + 2 * ir; }
+        if (s < INF && vs >= 0 && vs <= n_rb - 2 && key_less(s, 2 + 2 * ir, db, sb_slot)) { db = s; sb_slot = 2 + 2 * ir; }
+      }
+      warp_min_key(db, sb_slot);
+      if (db < INF) {
+        const int ir = (sb_slot - 1) >> 1;
+        const bool above = r > g.rb[ir];
+        const bool is_first = ((sb_slot - 1) & 1) == 0;
+        rb_val = is_first ? (above ? ir - 1 : ir) : (above ? ir : ir - 1);
+      }
+    }
+    if (!(db < INF)) {   // never inside the grid
+      if (lane == 0) { out.len[ray] = 0; out.flag[ray] = 0; }
+      continue;
+    }
+    Real de = INF; int se_slot = 0x7fffffff;       // key of `end`
+    for (int ir = lane; ir < n_rb; ir += 32) {
+      const bool above = r > g.rb[ir];
+      const Real f = sph_d[2 * ir], s = sph_d[2 * ir + 1];
+      const int vf = above ? ir - 1 : ir;
+      const int vs = above ? ir : ir - 1;
+      if (f < INF && (vf < 0 || vf > n_rb - 2) && key_less(db, sb_slot, f, 1 + 2 * ir) && key_less(f, 1 + 2 * ir, de, se_slot)) { de = f; se_slot = 1 + 2 * ir; }
+      if (s < INF && (vs < 0 || vs > n_rb - 2) && key_less(db, sb_slot, s, 2 + 2 * ir) && key_less(s, 2 + 2 * ir, de, se_slot)) { de = s; se_slot = 2 + 2 * ir; }
+    }
+    warp_min_key(de, se_slot);
+
+    // ---- pass 2: compact every crossing with  begin < key <= end
+    int count = 0;                                  // warp-uniform
+    Real dsb = -INF; int ssb_slot = -1; int sb_val = s0;   // latest sza crossing before `begin`
+    for (int base_ir = 0; base_ir < n_rb; base_ir += 32) {
+      const int ir = base_ir + lane;
+      Real f = INF, s = INF;
+      bool above = false;
+      if (ir < n_rb) { f = sph_d[2 * ir]; s = sph_d[2 * ir + 1]; above = r > g.rb[ir]; }
+      const bool kf = f < INF && key_less(db, sb_slot, f, 1 + 2 * ir) && !key_less(de, se_slot, f, 1 + 2 * ir);
+      const bool ks = s < INF && key_less(db, sb_slot, s, 2 + 2 * ir) && !key_less(de, se_slot, s, 2 + 2 * ir);
+      const unsigned mf = __ballot_sync(0xffffffffu, kf);
+      const unsigned ms = __ballot_sync(0xffffffffu, ks);
+      const unsigned lt = (1u << lane) - 1u;
+      if (kf) {
+        const int pos = count + __popc(mf & lt);
+        if (pos < cap - 1) { cmp_d[pos] = f; cmp_i[pos] = pack_info(1 + 2 * ir, 0, above ? ir - 1 : ir); }
+      }
+      count += __popc(mf);
+      if (ks) {
+        const int pos = count + __popc(ms & lt);
+        if (pos < cap - 1) { cmp_d[pos] = s; cmp_i[pos] = pack_info(2 + 2 * ir, 0, above ? ir : ir - 1); }
+      }
+      count += __popc(ms);
+    }
+    const Real zn = z / r;
+    for (int base_k = 0; base_k < n_sb - 2; base_k += 32) {
+      const int k = base_k + lane;
+      Real f = INF, s = INF;
+      bool above = false;
+      if (k < n_sb - 2) {
+        cone_hits(r, zn, lz, cost, g.cone_cos[k], g.cone_cos2[k], f, s);
+        above = t > g.sb[k + 1];
+      }
+      const int slot_f = 1 + 2 * n_rb + 2 * k, slot_s = slot_f + 1;
+      const int vf = above ? k : k + 1;            // idx = k+1: above ? idx-1 : idx
+      const int vs = above ? k + 1 : k;
+      const bool kf = f < INF && key_less(db, sb_slot, f, slot_f) && !key_less(de, se_slot, f, slot_f);
+      const bool ks = s < INF && key_less(db, sb_slot, s, slot_s) && !key_less(de, se_slot, s, slot_s);
+      if (!origin_in) {   // remember the latest sza crossing strictly before `begin`
+        if (f < INF && key_less(f, slot_f, db, sb_slot) && key_less(dsb, ssb_slot, f, slot_f)) { dsb = f; ssb_slot = slot_f; sb_val = vf; }
+        if (s < INF && key_less(s, slot_s, db, sb_slot) && key_less(dsb, ssb_slot, s, slot_s)) { dsb = s; ssb_slot = slot_s; sb_val = vs; }
+      }
+      const unsigned mf = __ballot_sync(0xffffffffu, kf);
+      const unsigned ms = __ballot_sync(0xffffffffu, ks);
+      const unsigned lt = (1u << lane) - 1u;
+      if (kf) {
+        const int pos = count + __popc(mf & lt);
+        if (pos < cap - 1) { cmp_d[pos] = f; cmp_i[pos] = pack_info(slot_f, 1, vf); }
+      }
+      count += __popc(mf);
+      if (ks) {
+        const int pos = count + __popc(ms & lt);
+        if (pos < cap - 1) { cmp_d[pos] = s; cmp_i[pos] = pack_info(slot_s, 1, vs); }
+      }
+      count += __popc(ms);
+    }
+    int s_begin = s0;
+    if (!origin_in) {
+      // value carried by the max-key sza crossing before `begin` (warp reduce)
+      Real dmax = dsb; int smax = ssb_slot;
+      warp_max_key(dmax, smax);
+      // the lane owning that key broadcasts its value
+      const unsigned own = __ballot_sync(0xffffffffu, smax >= 0 && ssb_slot == smax && dsb == dmax);
+      if (own) s_begin = __shfl_sync(0xffffffffu, sb_val, __ffs(own) - 1);
+    }
+    if (count + 1 > cap) {   // hard capacity check (the reference only asserts, boundaries.hpp:153-158)
+      if (lane == 0) { out.len[ray] = 0; out.flag[ray] = 2; atomicExch(overflow_flag, 1); }
+      continue;
+    }
+    if (count == 0) {        // `begin` is the last entry of the list: empty (boundaries.hpp:219-220)
+      if (lane == 0) { out.len[ray] = 0; out.flag[ray] = 0; }
+      continue;
+    }
+    __syncwarp();
+
+    // ---- rank by (distance, slot): what the stable insertion sort produces
+    for (int e = lane; e < count; e += 32) {
+      const Real d = cmp_d[e];
+      const int info = cmp_i[e];
+      const int slot = info_slot(info);
+      int rank = 0;
+      for (int j = 0; j < count; j++) {
+        const Real dj = cmp_d[j];
+        const int sj = info_slot(cmp_i[j]);
+        rank += key_less(dj, sj, d, slot) ? 1 : 0;
+      }
+      srt_d[rank] = d;
+      srt_i[rank] = info;
+    }
+    __syncwarp();
+
+    // ---- forward fill (propagate_indices), voxel ids (assign_voxel_indices), write out
+    const int len = count + 1;
+    Real *od = out.dist + (size_t) ray * cap;
+    int *oe = out.ent + (size_t) ray * cap;
+    int carry_r = rb_val, carry_s = s_begin;
+    if (lane == 0) {
+      od[0] = db;
+      oe[0] = carry_r * (n_sb - 1) + carry_s;      // `begin` is inside the grid by construction
+    }
+    int last_r = carry_r;
+    for (int base_e = 0; base_e < count; base_e += 32) {
+      const int e = base_e + lane;
+      int pr = 0, ps = 0;                           // (pos+1)<<16 | (val+1) ; 0 = not set here
+      Real d = 0;
+      if (e < count) {
+        const int info = srt_i[e];
+        d = srt_d[e];
+        const int packed = ((lane + 1) << 16) | (info_val(info) + 1);
+        if (info_dim(info) == 0) pr = packed; else ps = packed;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int qr = __shfl_up_sync(0xffffffffu, pr, o);
+        const int qs = __shfl_up_sync(0xffffffffu, ps, o);
+        if (lane >= o) { pr = max(pr, qr); ps = max(ps, qs); }
+      }
+      const int rv = pr ? (pr & 0xffff) - 1 : carry_r;
+      const int sv = ps ? (ps & 0xffff) - 1 : carry_s;
+      if (e < count) {
+        const bool inside = rv >= 0 && rv <= n_rb - 2 && sv >= 0 && sv <= n_sb - 2;
+        od[e + 1] = d;
+        oe[e + 1] = inside ? rv * (n_sb - 1) + sv : -1;
+      }
+      const int last_lane = min(31, count - base_e - 1);
+      carry_r = __shfl_sync(0xffffffffu, rv, last_lane);
+      carry_s = __shfl_sync(0xffffffffu, sv, last_lane);
+      last_r = carry_r;
+    }
+    if (lane == 0) {
+      out.len[ray] = len;
+      out.flag[ray] = (last_r == -1) ? 1 : 0;       // exits_bottom (boundaries.hpp:340)
+    }
+    __syncwarp();
+  }
+}
+
+template <class Real>
+size_t traverse_smem_bytes(const GridView<Real> &g, int warps) {
+  const size_t per_warp = ((size_t) (2 * g.n_rb + 2 * g.cap) * sizeof(Real) + (size_t) 2 * g.cap * sizeof(int) + 15) & ~size_t(15);
+  return per_warp * warps;
+}
+
+template <class Real, bool VR>
+cudaError_t launch_impl(const GridView<Real> &g, int v_begin, long long n_total, RayList<Real> rl,
+                        ListView<Real> out, int *overflow_flag, cudaStream_t s) {
+  if (n_total <= 0) return cudaSuccess;
+  if (2 * (g.n_rb + g.n_sb) + 2 >= (1 << SLOT_BITS)) return cudaErrorInvalidValue;
+  const int threads = 128, warps = threads / 32;
+  const size_t smem = traverse_smem_bytes(g, warps);
+  cudaError_t e = cudaFuncSetAttribute(traverse_kernel<Real, VR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  long long blocks = (n_total + warps - 1) / warps;
+  const long long max_blocks = (long long) NUM_SMS * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  traverse_kernel<Real, VR><<<(unsigned) blocks, threads, smem, s>>>(g, v_begin, n_total, rl, out, overflow_flag);
+  return cudaGetLastError();
+}
+
+} // namespace
+
+template <class Real>
+cudaError_t launch_traverse_voxel_rays(const GridView<Real> &g, int v_begin, int v_end, ListView<Real> out,
+                                       int *overflow_flag, cudaStream_t s) {
+  RayList<Real> none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return launch_impl<Real, true>(g, v_begin, (long long) (v_end - v_begin) * g.n_rays, none, out, overflow_flag, s);
+}
+template <class Real>
+cudaError_t launch_traverse_list(const GridView<Real> &g, RayList<Real> rays, long long n, ListView<Real> out,
+                                 int *overflow_flag, cudaStream_t s) {
+  return launch_impl<Real, false>(g, 0, n, rays, out, overflow_flag, s);
+}
+
+template cudaError_t launch_traverse_voxel_rays<double>(const GridView<double> &, int, int, ListView<double>, int *, cudaStream_t);
+template cudaError_t launch_traverse_voxel_rays<float>(const GridView<float> &, int, int, ListView<float>, int *, cudaStream_t);
+template cudaError_t launch_traverse_list<double>(const GridView<double> &, RayList<double>, long long, ListView<double>, int *, cudaStream_t);
+template cudaError_t launch_traverse_list<float>(const GridView<float> &, RayList<float>, long long, ListView<float>, int *, cudaStream_t);
+
+} // namespace b200rt

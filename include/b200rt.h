@@ -1,0 +1,164 @@
+/* b200rt.h -- C ABI of the B200-native hot path of planetarymike/3D_planetary_RT_model.
+ *
+ * The reference has no FFI layer: its seam is the set of member functions that
+ * are declared in headers but defined only in src/RT_gpu.cu (pulled in under
+ * __CUDACC__, RT_grid.hpp:328-331).  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference's src/).  A maintainer
+ * binds them from the reference's own host classes as shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array is a caller-owned HOST buffer of
+ *    doubles (a float `Real` build widens losslessly) unless the name ends in _dev;
+ *  - the context owns all device memory persistently (the reference mallocs and
+ *    frees inside every call, RT_gpu.cu:150-191,264-299);
+ *  - every function returns a b200rt_status; b200rt_last_error() gives the text.
+ *    Nothing ever calls exit() (the reference's checkCudaErrors does);
+ *  - a context is not thread-safe: one per host thread / per GPU;
+ *  - there is NO CPU fallback: without a CUDA device b200rt_create fails.
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200rt_ctx b200rt_ctx;
+
+typedef enum {
+  B200RT_OK = 0,
+  B200RT_ERR_CUDA = 1,          /* a CUDA runtime call failed */
+  B200RT_ERR_ARG = 2,           /* bad argument */
+  B200RT_ERR_STATE = 3,         /* call order: grid / emission / source function not set */
+  B200RT_ERR_CAPACITY = 4,      /* a ray produced more boundary crossings than 2*n_rb+n_sb
+                                   (boundary_set::append only asserts, boundaries.hpp:153-158) */
+  B200RT_ERR_NOT_DOMINANT = 5,  /* I - w K is not strictly row diagonally dominant */
+  B200RT_ERR_NOMEM = 6
+} b200rt_status;
+
+enum { B200RT_F64 = 0, B200RT_F32 = 1 };          /* arithmetic of the ray march: Real.hpp:9-27 */
+enum { B200RT_ROW_MAJOR = 0, B200RT_COL_MAJOR = 1 }; /* EIGEN_ROWMAJOR or not, Real.hpp:41-53 */
+
+/* ---- lifetime -------------------------------------------------------------------
+ * replaces cudaSetDevice(0) + per-call cudaMalloc/cudaFree (RT_gpu.cu:143,257,190,299) */
+int b200rt_create(int device, int precision, b200rt_ctx **ctx);
+int b200rt_destroy(b200rt_ctx *ctx);
+const char *b200rt_last_error(const b200rt_ctx *ctx);
+int b200rt_device_count(void);
+
+/* ---- geometry -------------------------------------------------------------------
+ * replaces RT_grid::RT_to_device() for grid_type = spherical_azimuthally_symmetric_grid
+ * (RT_gpu.cu:8-40; members grid_spherical_azimuthally_symmetric.hpp:47-73, grid.hpp:32-45).
+ * Arrays are the members the reference's setup_voxels()/setup_rays() filled:
+ *   radial_boundaries[n_rb], sza_boundaries[n_sb], pts_radii[n_rb-1], pts_sza[n_sb-1],
+ *   rays[i].t, rays[i].p, rays[i].domega  (i < n_rays).
+ * Derived tables (sphere R, R^2: intersections.cpp:53-56; cone cos, cos^2: :103-109;
+ * ray cos/sin: atmo_vec.cpp:172-181; voxel points: :41-49) are rebuilt on the host with
+ * the same libm calls the reference makes, so traversal is bit-exact. */
+int b200rt_set_grid_sph(b200rt_ctx *ctx, int n_rb, int n_sb, int n_rays,
+                        const double *radial_boundaries, const double *sza_boundaries,
+                        const double *pts_radii, const double *pts_sza,
+                        const double *ray_theta, const double *ray_phi, const double *ray_domega);
+
+/* host helper: what setup_voxels()/setup_rays() compute from the radial boundaries
+ * (grid_spherical_azimuthally_symmetric.hpp:302-333,365-406).  szamethod 0 = uniform,
+ * 1 = uniform_cos; raymethod 0 = gauss, 1 = uniform.  Outputs sized as above
+ * (n_rays = n_theta*n_phi). */
+int b200rt_make_grid_sph(int precision, int n_rb, int n_sb, int n_theta, int n_phi,
+                         const double *radial_boundaries, int szamethod, int raymethod,
+                         double *sza_boundaries, double *pts_radii, double *pts_sza,
+                         double *ray_theta, double *ray_phi, double *ray_domega);
+
+/* ---- emissions ------------------------------------------------------------------
+ * replaces singlet_CFR::copy_to_device_influence / copy_to_device_brightness
+ * (singlet_CFR.hpp:565-613) + emission_voxels::copy_to_device_* (emission_voxels.hpp:241-268).
+ * Arrays are the protected per-voxel tables singlet_CFR::define() fills
+ * (singlet_CFR.hpp:62-77,419-492), n_vox = (n_rb-1)*(n_sb-1) each; element order = voxel id. */
+int b200rt_set_singlet(b200rt_ctx *ctx, int i_emission, int n_emissions,
+                       double branching_ratio, double species_T_ref, double species_sigma_T_ref,
+                       double emission_g_factor,
+                       const double *species_T_ratio, const double *species_density,
+                       const double *dtau_species, const double *dtau_absorber,
+                       const double *species_T_ratio_pt, const double *species_density_pt,
+                       const double *dtau_species_pt, const double *dtau_absorber_pt);
+/* singlet_CFR::set_emission_g_factor, singlet_CFR.hpp:282-284 */
+int b200rt_set_g_factor(b200rt_ctx *ctx, int i_emission, double g);
+
+/* ---- source function ------------------------------------------------------------
+ * b200rt_generate_S replaces RT_grid::generate_S_gpu() (RT_gpu.cu:255-309): influence
+ * kernel + single scattering + solve for every emission.  The two halves are exposed
+ * separately so that rows can be sharded over GPUs (rows [v_begin, v_end) only). */
+int b200rt_generate_S(b200rt_ctx *ctx);
+int b200rt_influence(b200rt_ctx *ctx, int v_begin, int v_end);
+int b200rt_solve(b200rt_ctx *ctx);                      /* RT_grid::solve_gpu, emission_voxels::solve_gpu */
+/* ray-voxel steps executed by the last b200rt_influence call (one step = one
+ * RT_grid::influence_update, RT_grid.hpp:90-105, covering all emissions) */
+int b200rt_last_step_count(b200rt_ctx *ctx, long long *n_steps);
+
+/* replaces RT_grid::emissions_solved_to_host / emissions_influence_to_host
+ * (RT_gpu.cu:62-84; emission_voxels.hpp:273-291).  Any pointer may be NULL.
+ * K is the raw influence matrix (before the branching-ratio scaling of pre_solve). */
+int b200rt_get_solution(b200rt_ctx *ctx, int i_emission, double *sourcefn, double *singlescat,
+                        double *tau_species_single_scattering, double *tau_absorber_single_scattering);
+int b200rt_get_influence(b200rt_ctx *ctx, int i_emission, int layout, double *influence_matrix);
+/* sourcefn upload for brightness without a solve (copy_to_device_brightness, emission_voxels.hpp:257-268) */
+int b200rt_set_sourcefn(b200rt_ctx *ctx, int i_emission, const double *sourcefn);
+/* relative residual max|(I-wK)S-S0|/max|S0| of the last solve */
+int b200rt_last_residual(b200rt_ctx *ctx, int i_emission, double *residual);
+
+/* device-resident access for multi-GPU row exchange (pointer into ctx memory,
+ * row-major [n_vox][n_vox] doubles / [n_vox] doubles); valid until destroy or re-grid */
+int b200rt_influence_dev(b200rt_ctx *ctx, int i_emission, void **K_dev, void **S0_dev,
+                         void **tau_species_ss_dev, void **tau_absorber_ss_dev);
+int b200rt_sourcefn_dev(b200rt_ctx *ctx, int i_emission, void **S_dev);
+
+/* ---- observations ---------------------------------------------------------------
+ * host helper: observation::add_MSO_observation (observation.hpp:46-65) + atmo_point::xyz +
+ * atmo_vector::ptxyz (atmo_vec.cpp:51-61,256-290): MSO position / look direction ->
+ * the atmo_vector fields the march needs.  loc, dir: [n][3]; outputs [n] each. */
+int b200rt_los_from_MSO(int precision, int n_los, const double *loc_MSO, const double *dir_MSO,
+                        double *x, double *y, double *z, double *r, double *t,
+                        double *line_x, double *line_y, double *line_z, double *cost);
+
+/* replaces RT_grid::brightness_gpu(obs, n_subsamples) (RT_gpu.cu:138-192) and
+ * observation::to_device/to_host (observation.hpp:211-254).  Inputs are the fields of
+ * obs_vecs[i] (pt.{x,y,z,r,t}, line_{x,y,z}, ray.cost); outputs are the four tracker
+ * members observation_fit reads (observation_fit.cpp:491-559), laid out [n_emissions][n_los].
+ * n_subsamples = 0 -> brightness_nointerp (RT_grid.hpp:320-322); 1 is illegal (:237). */
+int b200rt_brightness(b200rt_ctx *ctx, int n_los,
+                      const double *x, const double *y, const double *z, const double *r, const double *t,
+                      const double *line_x, const double *line_y, const double *line_z, const double *cost,
+                      int n_subsamples,
+                      double *brightness, double *tau_species_final, double *tau_absorber_final,
+                      double *species_col_dens);
+/* the same in three steps, for callers that keep lines of sight resident in HBM */
+int b200rt_los_upload(b200rt_ctx *ctx, int n_los,
+                      const double *x, const double *y, const double *z, const double *r, const double *t,
+                      const double *line_x, const double *line_y, const double *line_z, const double *cost);
+int b200rt_brightness_resident(b200rt_ctx *ctx, int n_subsamples);
+int b200rt_los_download(b200rt_ctx *ctx, double *brightness, double *tau_species_final,
+                        double *tau_absorber_final, double *species_col_dens);
+
+/* ---- traversal (parity surface) -------------------------------------------------
+ * grid.ray_voxel_intersections (grid_spherical_azimuthally_symmetric.hpp:459-509) for the
+ * voxel-origin rays of source voxels [v_begin, v_end) (ray order: voxel major, ray minor)
+ * or for the resident lines of sight: trimmed boundary lists, concatenated.
+ * len[i] entries per ray; entering = boundary::entering, distance = boundary::distance
+ * (boundaries.hpp:15-21); exits_bottom as boundary_intersection_stepper (:334-349). */
+int b200rt_traverse_voxel_rays(b200rt_ctx *ctx, int v_begin, int v_end, long long capacity,
+                               int *len, int *exits_bottom, int *entering, double *distance,
+                               long long *n_entries);
+int b200rt_traverse_los(b200rt_ctx *ctx, long long capacity,
+                        int *len, int *exits_bottom, int *entering, double *distance,
+                        long long *n_entries);
+
+/* ---- timing ---------------------------------------------------------------------
+ * device time (CUDA events on the ctx stream) of the kernels of the last call:
+ * phase 0 = traversal, 1 = influence march, 2 = solve, 3 = brightness march */
+int b200rt_last_kernel_ms(b200rt_ctx *ctx, int phase, float *ms, int *n_launches);
+int b200rt_synchronize(b200rt_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
