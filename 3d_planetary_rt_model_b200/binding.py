@@ -256,8 +256,8 @@ def define_singlet_tables(scn, e, precision=F64):
 
 
 class GpuModel:
-    """Scenario-level convenience with the same method names as oracle.{refbind.RefModel,
-    oraclebind.OracleModel}, so parity tests read alike."""
+    """Scenario-level convenience: one synthetic Scenario (synth.py) on one GPU, with the
+    method vocabulary the parity tests use (grid / traverse / build_rows / solve / brightness)."""
 
     def __init__(self, scn, precision="f64", device=0):
         self.scn = scn

@@ -1,0 +1,63 @@
+"""Golden vectors produced by the reference's own source (tests/golden/make_golden.py):
+the oracle (CPU, always) and the CUDA path (-m gpu) must reproduce them."""
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN, load_golden
+from util import TOL, assert_lists_equal, rel_err, same_bits
+
+
+def check_against_golden(M, scn, z, prec, exact):
+    """exact=True (oracle): bit-identical; exact=False (CUDA): indices/distances bit-identical,
+    floating-point results within the north-star tolerance."""
+    tol = TOL[prec]
+    g = M.grid()
+    for k in ("sza_boundaries", "pts_radii", "pts_sza", "ray_theta", "ray_phi", "ray_domega"):
+        assert same_bits(g[k], z["grid_" + k]), k
+    assert_lists_equal(M.traverse_voxel_rays(), (z["vr_len"], z["vr_eb"], z["vr_ent"], z["vr_dist"]))
+    _, nsteps = M.build_rows()
+    assert nsteps == int(z["n_steps"])
+    for e in range(2):
+        K = M.K(e)
+        if exact:
+            assert same_bits(K, z[f"K{e}"])
+        else:
+            assert np.array_equal(K != 0, z[f"K{e}"] != 0)
+            assert rel_err(K, z[f"K{e}"]) < tol
+        v = M.vectors(e, want_S=False) if not exact else M.vectors(e)
+        for k in ("S0", "tau_species_ss", "tau_absorber_ss"):
+            if exact:
+                assert same_bits(v[k], z[f"vec{e}_{k}"]), k
+            else:
+                assert rel_err(v[k], z[f"vec{e}_{k}"]) < tol, k
+    M.solve()
+    for e in range(2):
+        Sg = z[f"vec{e}_S"]
+        floor = 1e-30 if prec == "f64" else float(np.abs(Sg).max())
+        assert rel_err(M.vectors(e)["S"], Sg, floor=floor) < (1e-7 if prec == "f64" else 1e-3 if exact else tol)
+        M.set_sourcefn(e, Sg)
+    locs, dirs = z["los_loc"], z["los_dir"]
+    lists = M.traverse_los(locs, dirs)
+    assert_lists_equal(lists[:4], (z["los_len"], z["los_eb"], z["los_ent"], z["los_dist"]))
+    for nsub in (10, 0):
+        _, b = M.brightness(locs, dirs, nsub)
+        ref = z[f"brightness_nsub{nsub}"]
+        if exact:
+            assert same_bits(b, ref)
+        else:
+            assert np.array_equal(b[:, 2] == -1, ref[:, 2] == -1)      # lines of sight that hit the planet
+            for q in range(4):
+                assert rel_err(b[:, q], ref[:, q], floor=1e-300) < tol, (nsub, q)
+
+
+@pytest.mark.parametrize("name,prec", GOLDEN)
+def test_oracle_reproduces_golden(synth, oraclebind, name, prec):
+    scn, z = load_golden(synth, name, prec)
+    check_against_golden(oraclebind.OracleModel(scn, prec), scn, z, prec, exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,prec", GOLDEN)
+def test_cuda_reproduces_golden(synth, binding, name, prec):
+    scn, z = load_golden(synth, name, prec)
+    check_against_golden(binding.GpuModel(scn, prec), scn, z, prec, exact=False)

@@ -1,0 +1,143 @@
+"""CUDA path (through the C ABI, libb200rt.so) against the oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): voxel traversal and intersection indices bit-exact;
+influence matrix, source function and brightness within 1e-6 relative (double Real) and
+1e-4 (float Real).  Run on the B200 box: python -m pytest tests -m gpu
+"""
+import numpy as np
+import pytest
+
+from util import TOL, assert_lists_equal, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def compare_models(synth, O, G, scn, prec, los_sets):
+    tol = TOL[prec]
+    assert_lists_equal(O.traverse_voxel_rays(), G.traverse_voxel_rays())
+    _, ns_o = O.build_rows()
+    _, ns_g = G.build_rows()
+    assert ns_o == ns_g
+    for e in range(scn.n_em):
+        Ko, Kg = O.K(e), G.K(e)
+        assert np.array_equal(Ko != 0, Kg != 0)
+        assert rel_err(Ko, Kg) < tol
+        vo, vg = O.vectors(e), G.vectors(e, want_S=False)
+        for k in ("S0", "tau_species_ss", "tau_absorber_ss"):
+            assert rel_err(vo[k], vg[k]) < tol, k
+        assert np.array_equal(vo["S0"] == 0, vg["S0"] == 0)          # shadowed voxels
+    O.solve()
+    res = G.solve()
+    for e in range(scn.n_em):
+        assert res[e] < 1e-12                                          # FP64 solve in both precisions
+        So = O.vectors(e)["S"]
+        floor = 1e-30 if prec == "f64" else float(np.abs(So).max())
+        assert rel_err(So, G.vectors(e)["S"], floor=floor) < tol
+        G.set_sourcefn(e, So)
+    for locs, dirs in los_sets:
+        a, b = O.traverse_los(locs, dirs), G.traverse_los(locs, dirs)
+        assert_lists_equal(a[:4], b[:4])
+        for nsub in (10, 0, 4):
+            _, bo = O.brightness(locs, dirs, nsub)
+            _, bg = G.brightness(locs, dirs, nsub)
+            assert np.array_equal(bo[:, 2] == -1, bg[:, 2] == -1)
+            for q in range(4):
+                assert rel_err(bo[:, q], bg[:, q], floor=1e-300) < tol, (nsub, q)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("shape", [(8, 6, 4, 4), (12, 8, 5, 6), (20, 12, 6, 8)])
+def test_small_grids(synth, binding, oraclebind, prec, shape):
+    scn = synth.make_scenario(*shape, n_em=2, sza_T_contrast=0.1)
+    O = oraclebind.OracleModel(scn, prec)
+    G = binding.GpuModel(scn, prec)
+    compare_models(synth, O, G, scn, prec, [synth.fake_image(30 * synth.rMars, 30, 24), synth.random_los(800)])
+
+
+@pytest.mark.parametrize("szamethod,raymethod", [(0, 0), (0, 1), (1, 0)])
+def test_other_grid_methods(synth, binding, oraclebind, szamethod, raymethod):
+    """szamethod_uniform and Gauss-Legendre ray angles (grid_spherical...hpp:314-319,369-372)"""
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=1, szamethod=szamethod, raymethod=raymethod)
+    O = oraclebind.OracleModel(scn, "f64")
+    G = binding.GpuModel(scn, "f64")
+    compare_models(synth, O, G, scn, "f64", [synth.random_los(300)])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_default_grid_D(synth, binding, oraclebind, prec):
+    """BASELINE.json configs[0]: default 40x20x7x12 grid, Ly alpha + Ly beta"""
+    scn = synth.make_scenario(40, 20, 7, 12, n_em=2)
+    O = oraclebind.OracleModel(scn, prec)
+    G = binding.GpuModel(scn, prec)
+    compare_models(synth, O, G, scn, prec, [synth.fake_image(30 * synth.rMars, 30, 40), synth.random_los(3000)])
+
+
+def test_row_sharding_equals_full(synth, binding):
+    """rows built in ragged pieces (what each rank does under --gpus N) equal one full pass"""
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=2)
+    G = binding.GpuModel(scn, "f64")
+    G.build_rows()
+    Kfull = [G.K(e).copy() for e in range(2)]
+    G2 = binding.GpuModel(scn, "f64")
+    n = G2.n_vox
+    total = 0
+    for a, b in ((0, 1), (1, 30), (30, 30), (30, n)):     # includes an empty range
+        _, ns = G2.build_rows(a, b)
+        total += ns
+    _, ns_full = G.build_rows()
+    assert total == ns_full
+    for e in range(2):
+        assert rel_err(Kfull[e], G2.K(e)) < 1e-13         # fp64 RED ordering only
+
+
+def test_edge_cases(synth, binding, oraclebind):
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=2)
+    G = binding.GpuModel(scn, "f64")
+    O = oraclebind.OracleModel(scn, "f64")
+    O.build_rows(); O.solve()
+    for e in range(2):
+        G.set_sourcefn(e, O.vectors(e)["S"])
+    rM = synth.rMars
+    locs = np.array([[30 * rM, 0, 0],          # looks away from the planet: misses the grid
+                     [30 * rM, 0, 0],          # straight at the planet: exits through the bottom
+                     [0, 0, 2 * rM],           # inside the grid looking up
+                     [0, 0, 2 * rM]])          # inside the grid looking down
+    dirs = np.array([[1.0, 0, 0], [-1.0, 0, 0], [0, 0, 1.0], [0, 0, -1.0]])
+    _, bg = G.brightness(locs, dirs, 10)
+    _, bo = O.brightness(locs, dirs, 10)
+    assert (bg[:, :, 0] == 0).all() and (bg[:, 2, 0] == 0).all()      # miss: brightness 0, tau 0
+    assert (bg[:, 2, 1] == -1).all() and (bg[:, 2, 3] == -1).all()    # planet hits: tau_absorber_final = -1
+    assert (bg[:, 2, 2] >= 0).all()
+    for q in range(4):
+        assert rel_err(bo[:, q], bg[:, q], floor=1e-300) < 1e-6
+    # error behaviour: n_subsamples = 1 is illegal (RT_grid.hpp:237), empty observation (RT_grid.hpp:302)
+    los = G.ctx.los_from_MSO(locs, dirs)
+    with pytest.raises(binding.B200RTError):
+        G.ctx.brightness(los, 1)
+    with pytest.raises(binding.B200RTError):
+        G.ctx.brightness([a[:0] for a in los], 10)
+    # brightness before any source function is a state error, not garbage
+    G3 = binding.GpuModel(scn, "f64")
+    with pytest.raises(binding.B200RTError):
+        G3.ctx.brightness(los, 10)
+    with pytest.raises(binding.B200RTError):
+        G3.ctx.solve()
+
+
+def test_layout_flag(synth, binding):
+    scn = synth.make_scenario(8, 6, 4, 4, n_em=1)
+    G = binding.GpuModel(scn, "f64")
+    G.build_rows()
+    Kr = G.ctx.influence_matrix(0, binding.ROW_MAJOR)
+    Kc = G.ctx.influence_matrix(0, binding.COL_MAJOR)
+    assert np.array_equal(Kr, Kc.T)
+
+
+def test_not_dominant_is_reported(synth, binding):
+    """a branching ratio that breaks row dominance must come back as a status, not a wrong answer"""
+    scn = synth.make_scenario(8, 6, 4, 4, n_em=1)
+    scn.em_scalars[0][0] = 50.0
+    G = binding.GpuModel(scn, "f64")
+    G.build_rows()
+    with pytest.raises(binding.B200RTError, match="dominant"):
+        G.solve()

@@ -1,0 +1,65 @@
+"""Host-side restatements inside libb200rt.so that need no GPU: grid generation
+(b200rt_make_grid_sph) and line-of-sight preparation (b200rt_los_from_MSO), checked
+bit for bit against the oracle (itself pinned to the reference) and the golden vectors."""
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN, load_golden
+from util import same_bits
+
+
+def _make_grid(binding, prec, scn):
+    lib = binding.load()
+    n_rays = scn.n_theta * scn.n_phi
+    sb, pr, ps = np.zeros(scn.n_sb), np.zeros(scn.n_rb - 1), np.zeros(scn.n_sb - 1)
+    rt, rp, rd = np.zeros(n_rays), np.zeros(n_rays), np.zeros(n_rays)
+    rc = lib.b200rt_make_grid_sph(binding.F64 if prec == "f64" else binding.F32, scn.n_rb, scn.n_sb, scn.n_theta,
+                                  scn.n_phi, np.ascontiguousarray(scn.rb), scn.szamethod, scn.raymethod,
+                                  sb, pr, ps, rt, rp, rd)
+    assert rc == 0
+    return dict(sza_boundaries=sb, pts_radii=pr, pts_sza=ps, ray_theta=rt[::scn.n_phi].copy(),
+                ray_phi=rp[:scn.n_phi].copy(), ray_domega=rd)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("szamethod", [0, 1])
+@pytest.mark.parametrize("raymethod", [0, 1])
+def test_make_grid_matches_oracle(synth, binding, oraclebind, prec, szamethod, raymethod):
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=1, szamethod=szamethod, raymethod=raymethod)
+    g = _make_grid(binding, prec, scn)
+    go = oraclebind.OracleModel(scn, prec).grid()
+    for k in go:
+        assert same_bits(g[k], go[k]), k
+    assert abs(g["ray_domega"].sum() - 1.0) < (1e-6 if prec == "f64" else 1e-3)   # RT_grid.hpp:192 invariant
+
+
+@pytest.mark.parametrize("name,prec", GOLDEN)
+def test_make_grid_matches_golden(synth, binding, name, prec):
+    scn, z = load_golden(synth, name, prec)
+    g = _make_grid(binding, prec, scn)
+    for k in g:
+        assert same_bits(g[k], z["grid_" + k]), k
+
+
+@pytest.mark.parametrize("name,prec", GOLDEN)
+def test_los_from_MSO_matches_golden(synth, binding, name, prec):
+    """r, z, t, cost, line_z, line_x of every line of sight, as the reference's
+    observation::add_MSO_observation + atmo_vector::ptxyz produced them"""
+    scn, z = load_golden(synth, name, prec)
+    lib = binding.load()
+    locs, dirs = z["los_loc"], z["los_dir"]
+    n = len(locs)
+    o = [np.zeros(n) for _ in range(9)]
+    rc = lib.b200rt_los_from_MSO(binding.F64 if prec == "f64" else binding.F32, n, np.ascontiguousarray(locs),
+                                 np.ascontiguousarray(dirs), *o)
+    assert rc == 0
+    x, y, zz, r, t, lx, ly, lz, cost = o
+    rs = z["los_rayscal"]
+    assert same_bits(r, rs[:, 0]) and same_bits(zz, rs[:, 1]) and same_bits(t, rs[:, 2])
+    assert same_bits(cost, rs[:, 3]) and same_bits(lz, rs[:, 4]) and same_bits(lx, rs[:, 5])
+
+
+def test_bad_arguments(binding):
+    lib = binding.load()
+    z = np.zeros(4)
+    assert lib.b200rt_make_grid_sph(0, 1, 8, 5, 6, z, 1, 1, z, z, z, z, z, z) == 2      # B200RT_ERR_ARG
