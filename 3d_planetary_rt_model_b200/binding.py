@@ -52,6 +52,7 @@ SIGNATURES = {
     "b200rt_traverse_los": (C.c_int, [_vp, C.c_longlong, _ip, _ip, _ip, _dp, C.POINTER(C.c_longlong)]),
     "b200rt_last_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "b200rt_synchronize": (C.c_int, [_vp]),
+    "b200rt_measure_fp64_peaks": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -238,6 +239,12 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.b200rt_synchronize(self.h))
+
+    def fp64_peaks(self):
+        """-> (DFMA TFLOP/s, DMMA TFLOP/s) measured on this device"""
+        a, b = C.c_double(0), C.c_double(0)
+        self._ck(self.lib.b200rt_measure_fp64_peaks(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 def define_singlet_tables(scn, e, precision=F64):

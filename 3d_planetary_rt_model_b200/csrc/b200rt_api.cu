@@ -673,4 +673,10 @@ int b200rt_last_kernel_ms(b200rt_ctx *c, int phase, float *ms, int *n_launches) 
   return B200RT_OK;
 }
 
+int b200rt_measure_fp64_peaks(b200rt_ctx *c, double *dfma, double *dmma) {
+  if (!c) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  return measure_fp64_peaks(c, dfma, dmma);
+}
+
 } // extern "C"

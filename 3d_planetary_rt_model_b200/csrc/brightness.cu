@@ -26,7 +26,7 @@ template <class Real> struct MathB;
 template <> struct MathB<double> {
   __device__ static double exp_(double x) { return exp(x); }
   __device__ static double log_(double x) { return log(x); }
-  __device__ static double hypot_(double a, double b) { return hypot(a, b); }
+  __device__ static double hypot2_(double a, double b, double c) { return hypot(hypot(a, b), c); }
   __device__ static double acos_(double x) { return acos(x); }
   __device__ static double eps() { return 1e-6; }       // EPS      Real.hpp:23
   __device__ static double coneeps() { return 1e-6; }   // CONEEPS  Real.hpp:25
@@ -34,8 +34,10 @@ template <> struct MathB<double> {
 template <> struct MathB<float> {
   __device__ static float exp_(float x) { return expf(x); }
   __device__ static float log_(float x) { return logf(x); }
-  __device__ static float hypot_(float a, float b) { return hypotf(a, b); }
-  __device__ static float acos_(float x) { return acosf(x); }
+  // atmo_point::xyz calls the unqualified (double) hypot / acos even when Real = float
+  // (atmo_vec.cpp:53-54) and rounds on assignment: do the same
+  __device__ static float hypot2_(float a, float b, float c) { return (float) hypot(hypot((double) a, (double) b), (double) c); }
+  __device__ static float acos_(float x) { return (float) acos((double) x); }
   __device__ static float eps() { return 1e-3f; }       // Real.hpp:14
   __device__ static float coneeps() { return 1e-2f; }   // Real.hpp:16
 };
@@ -137,7 +139,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
           const Real nx = px / scale + (lx * dist) / scale;
           const Real ny = py / scale + (ly * dist) / scale;
           const Real nz = pz / scale + (lz * dist) / scale;
-          const Real rr = MathB<Real>::hypot_(MathB<Real>::hypot_(nx, ny), nz);
+          const Real rr = MathB<Real>::hypot2_(nx, ny, nz);
           Real t = MathB<Real>::acos_(nz / rr);
           Real r = rr * scale;
           // ---- interp_weights

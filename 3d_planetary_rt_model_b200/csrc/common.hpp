@@ -195,6 +195,9 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
                               long long count, ListView<Real> lists, int n_subsamples, Real *out,
                               long long n_los_total, cudaStream_t s);
 
+// ---- peaks.cu
+int measure_fp64_peaks(b200rt_ctx *c, double *dfma_tflops, double *dmma_tflops);
+
 // ---- solve.cu
 struct SolveResult { double residual; double min_margin; int launches; };
 int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const double *S0,

@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json on N B200s of one node.
+
+One "step" = one complete pass of the hot path over one batch of synthetic input:
+    H Ly-alpha influence matrix + single scattering on the 100x60 grid with 24x16 rays
+    (5841 voxels, ~1.2e8 ray-voxel steps; BASELINE.json configs[1]),
+    dense (I - K) S = S0 solve,
+    brightness of --n-los (default 1e6) seeded IUVS-like lines of sight (configs[2] geometry).
+
+value     = ray-voxel steps/s of the influence build, inputs resident in HBM, device time
+            (traversal + march kernels), whole job over all ranks; los_per_s is the second half
+            of the metric; job_ms is the whole step (build + exchange + solve + brightness).
+e2e       = the same two numbers through the reference-facing C-ABI calls with HOST buffers
+            (H2D of the tables / lines of sight and D2H of the results inside the timed region).
+roofline  = dominant kernel against the measured HBM peak (these kernels are FP64-instruction
+            bound, so the fraction is small by construction) + the FP64 picture in "fp64".
+cpu_baseline / --impl reference = the reference's own CPU (OpenMP) source built in place
+            (oracle/_ref), on a bounded sample of the same workload.
+
+N > 1 (torchrun): influence rows are split by source voxel, exchanged with NCCL broadcasts of
+row blocks, rank 0 solves and broadcasts S, lines of sight are split per GPU (no communication).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "3d_planetary_rt_model_b200"
+
+GRID = dict(n_rb=100, n_sb=60, n_theta=24, n_phi=16)
+FLOP_EQ_PER_EMISSION_STEP = 940.0      # 20 x (exp + div + ~14 flop), phi tabulated
+FLOP_EQ_PER_LOS_SUBSTEP = 1520.0       # 20 x (2 exp + div + ~14 flop) + extend/interp, per emission
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nme, val in zip(names, f[3:7]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_workload(synth, n_los):
+    scn = synth.make_scenario(GRID["n_rb"], GRID["n_sb"], GRID["n_theta"], GRID["n_phi"], n_em=1,
+                              rmethod=synth.RMETHOD_ALTITUDE, rmax=synth.rMars + 50000e5)
+    locs, dirs = synth.random_los(n_los)
+    return scn, locs, dirs
+
+
+def partition(n, world, rank):
+    """contiguous block of source voxels / lines of sight for this rank"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """the reference's own CPU implementation (oracle/_ref, built in place from its source) on the
+    host cores of this box, on a bounded sample of the same workload"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    synth = importlib.import_module(PKG + ".synth")
+    from oracle import refbind
+    if not refbind.available("f64"):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_f64.so not built (needs /root/reference at build time)"}))
+        return
+    scn, locs, dirs = make_workload(synth, args.ref_los)
+    R = refbind.RefModel(scn, "f64")
+    stride = args.ref_stride
+    threads = R.omp_threads()
+    # source function for the brightness sample: single scattering only (no CPU solve of 5841^2)
+    times_b, times_l, steps = [], [], 0
+    for it in range(args.warmup + args.steps):
+        tb, ns = R.build_rows(0, scn.n_vox, stride)
+        if it == 0:
+            R.set_sourcefn(0, R.vectors(0)["S0"])
+        tl, _ = R.brightness(locs, dirs, 10)
+        if it >= args.warmup:
+            times_b.append(tb); times_l.append(tl); steps = ns
+    tb, tl = sum(times_b), sum(times_l)
+    K = len(times_b)
+    v = steps * K / tb
+    los = args.ref_los * K / tl
+    sample = (f"every {stride}th source-voxel row of the 5841 ({steps} ray-voxel steps) and "
+              f"{args.ref_los} of the lines of sight per step; S = S0 for the brightness sample")
+    line = {"impl": "reference", "metric": "influence-matrix ray-voxel steps/s + observation LOS/s", "value": v,
+            "unit": "ray-voxel steps/s", "los_per_s": los, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (tb + tl) / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "H Ly-alpha source function on 100x60 grid, 24x16 rays + IUVS-like LOS brightness",
+                       "grid": GRID, "n_emissions": 1, "n_los": args.ref_los, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "ray-voxel steps/s", "los_per_s": los, "cores": threads, "kind": "reference",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": "ray-voxel steps/s", "los_per_s": los, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def cuda_array(ptr, shape, dtype="<f8"):
+    class _A:
+        pass
+    a = _A()
+    a.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": dtype, "data": (int(ptr), False), "version": 2}
+    return a
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+
+    synth = importlib.import_module(PKG + ".synth")
+    binding = importlib.import_module(PKG + ".binding")
+    scn, locs, dirs = make_workload(synth, args.n_los)
+    n_vox, n_los = scn.n_vox, args.n_los
+
+    ctx = binding.Context(local, binding.F64)
+    g = ctx.make_grid(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.rb, scn.szamethod, scn.raymethod)
+    ctx.set_grid(g)
+    tabs = binding.define_singlet_tables(scn, 0)
+    b_, T_, s_, g_ = (float(x) for x in scn.em_scalars[0])
+    ctx.set_singlet(0, 1, b_, T_, s_, g_, tabs)
+
+    v0, v1 = partition(n_vox, world, rank)
+    l0, l1 = partition(n_los, world, rank)
+    los_all = ctx.los_from_MSO(locs, dirs)                      # host preparation (atmo_vector::ptxyz)
+    los_mine = [np.ascontiguousarray(a[l0:l1]) for a in los_all]
+    ctx.los_upload(los_mine)                                    # resident for the device-timed arm
+
+    Kp, S0p, tsp, tab = ctx.influence_dev(0)
+    K_t = torch.as_tensor(cuda_array(Kp, (n_vox, n_vox)), device=dev)
+    S_ptr = binding.C.c_void_p()
+    ctx._ck(ctx.lib.b200rt_sourcefn_dev(ctx.h, 0, binding.C.byref(S_ptr)))
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        """-> dict of device/wall times (s) for this rank"""
+        t = {}
+        w0 = time.perf_counter()
+        ctx.influence(v0, v1)
+        t["traverse"] = ctx.kernel_ms(binding.PH_TRAVERSE)[0] * 1e-3
+        t["march"] = ctx.kernel_ms(binding.PH_INFLUENCE)[0] * 1e-3
+        launches = ctx.kernel_ms(binding.PH_TRAVERSE)[1] + ctx.kernel_ms(binding.PH_INFLUENCE)[1]
+        t["march_launches"] = ctx.kernel_ms(binding.PH_INFLUENCE)[1] - 1      # minus the single-scattering march
+        steps = ctx.last_step_count()
+        w1 = time.perf_counter()
+        if world > 1:                                           # exchange row blocks over NVLink
+            for r in range(world):
+                a, b = partition(n_vox, world, r)
+                if b > a:
+                    dist.broadcast(K_t[a:b], src=r)
+            torch.cuda.synchronize()
+        w2 = time.perf_counter()
+        if rank == 0:
+            ctx.solve()
+            t["solve"] = ctx.kernel_ms(binding.PH_SOLVE)[0] * 1e-3
+            launches += ctx.kernel_ms(binding.PH_SOLVE)[1]
+        if world > 1:
+            S_t = torch.as_tensor(cuda_array(S_ptr.value, (n_vox,)), device=dev)
+            dist.broadcast(S_t, src=0)
+            torch.cuda.synchronize()
+            if rank != 0:
+                S_host = S_t.cpu().numpy()
+                ctx.set_sourcefn(0, S_host)
+        w3 = time.perf_counter()
+        ctx.brightness_resident(10)
+        t["los_traverse"] = ctx.kernel_ms(binding.PH_TRAVERSE)[0] * 1e-3
+        t["brightness"] = ctx.kernel_ms(binding.PH_BRIGHTNESS)[0] * 1e-3
+        t["brightness_launches"] = ctx.kernel_ms(binding.PH_BRIGHTNESS)[1]
+        launches += ctx.kernel_ms(binding.PH_TRAVERSE)[1] + ctx.kernel_ms(binding.PH_BRIGHTNESS)[1]
+        ctx.synchronize()
+        w4 = time.perf_counter()
+        t.update(w_influence=w1 - w0, w_exchange=w2 - w1, w_solve=w3 - w2, w_brightness=w4 - w3, w_total=w4 - w0,
+                 steps=steps, launches=launches)
+        return t
+
+    def e2e_step():
+        """the reference-facing calls with host buffers: uploads and downloads inside the timed region"""
+        w0 = time.perf_counter()
+        ctx.set_singlet(0, 1, b_, T_, s_, g_, tabs)             # H2D: 8 tables
+        ctx.influence(v0, v1)
+        sol = ctx.solution(0, want_S=False)                     # D2H: S0 + optical depths
+        w1 = time.perf_counter()
+        if world > 1:
+            for r in range(world):
+                a, b = partition(n_vox, world, r)
+                if b > a:
+                    dist.broadcast(K_t[a:b], src=r)
+            torch.cuda.synchronize()
+        if rank == 0:
+            ctx.solve()
+            S = ctx.solution(0)["S"]                            # D2H: S
+        if world > 1:
+            S_t = torch.as_tensor(cuda_array(S_ptr.value, (n_vox,)), device=dev)
+            dist.broadcast(S_t, src=0)
+            torch.cuda.synchronize()
+            if rank != 0:
+                ctx.set_sourcefn(0, S_t.cpu().numpy())
+        w2 = time.perf_counter()
+        out = ctx.brightness(los_mine, 10)                      # H2D 9 arrays, kernels, D2H 4 arrays
+        w3 = time.perf_counter()
+        assert np.isfinite(out["brightness"]).all() and sol["S0"].max() <= 1.0
+        return dict(w_influence=w1 - w0, w_solve=w2 - w1, w_brightness=w3 - w2, w_total=w3 - w0)
+
+    # ---- device-timed arm
+    sampler = ClockSampler(local) if rank == 0 else None
+    recs = []
+    for it in range(args.warmup + args.steps):
+        flush.zero_()                                           # L2 flush between iterations (not timed)
+        barrier()
+        if it == args.warmup and sampler:
+            sampler.start()
+        rec = one_step()
+        barrier()
+        if it >= args.warmup:
+            recs.append(rec)
+    if sampler:
+        sampler.stop_flag = True
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def reduce_sum(x):
+        if world == 1:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return float(tt.item())
+
+    K = len(recs)
+    t_infl = reduce_max(sum(r["traverse"] + r["march"] for r in recs))            # device time, max over ranks
+    t_bright = reduce_max(sum(r["los_traverse"] + r["brightness"] for r in recs))
+    t_solve = reduce_max(sum(r.get("solve", 0.0) for r in recs))
+    t_total = reduce_max(sum(r["w_total"] for r in recs))
+    t_exch = reduce_max(sum(r["w_exchange"] for r in recs))
+    steps_total = reduce_sum(float(recs[-1]["steps"]))
+    launches = int(reduce_sum(float(sum(r["launches"] for r in recs))))
+    value = steps_total * K / t_infl
+    los_per_s = n_los * K / t_bright
+
+    # ---- e2e arm (host buffers)
+    erecs = []
+    for it in range(1 + max(1, min(args.steps, 3))):
+        flush.zero_()
+        barrier()
+        r = e2e_step()
+        barrier()
+        if it >= 1:
+            erecs.append(r)
+    Ke = len(erecs)
+    e_infl = reduce_max(sum(r["w_influence"] for r in erecs))
+    e_bright = reduce_max(sum(r["w_brightness"] for r in erecs))
+    e_total = reduce_max(sum(r["w_total"] for r in erecs))
+    h2d = 8 * n_vox * 8 + 9 * (l1 - l0) * 8
+    d2h = 4 * n_vox * 8 + 4 * (l1 - l0) * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (device time from CUDA events on the ctx stream)
+    hbm_peak, peak_kind = load_peaks()
+    dfma, dmma = ctx.fp64_peaks()
+    march_s = sum(r["march"] for r in recs) / K
+    bright_s = sum(r["brightness"] for r in recs) / K
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tj):
+        traffic = json.load(open(tj))
+    if bright_s >= march_s:
+        n_l = max(1, recs[-1]["brightness_launches"])
+        alg = (l1 - l0) * (6 * 8 + 4 * 8) / n_l                 # per LOS: 6 Reals in, 4 Reals out per emission
+        dur = bright_s / n_l
+        roof = {"kernel": "brightness_kernel<double,1>", "bound": "hbm", "achieved": alg / dur / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": alg / dur / 1e9 / hbm_peak, "peak_kind": peak_kind,
+                "traffic": (traffic or {}).get("brightness_kernel")}
+    else:
+        n_l = max(1, recs[-1]["march_launches"])
+        alg = (v1 - v0) * n_vox * 8 / n_l                        # K rows written once
+        dur = (march_s) / n_l
+        roof = {"kernel": "march_kernel<double,0>", "bound": "hbm", "achieved": alg / dur / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": alg / dur / 1e9 / hbm_peak, "peak_kind": peak_kind,
+                "traffic": (traffic or {}).get("march_kernel")}
+    roof["note"] = ("these kernels are FP64-instruction bound (SURVEY.md 8(d)): a small HBM fraction is the expected, "
+                    "healthy reading; see fp64")
+    steps_rank = recs[-1]["steps"]
+    fp64 = {"dfma_peak_tflops": dfma, "dmma_peak_tflops": dmma,
+            "march_flop_eq_tflops": steps_rank * FLOP_EQ_PER_EMISSION_STEP / march_s / 1e12,
+            "march_frac_of_dfma": steps_rank * FLOP_EQ_PER_EMISSION_STEP / march_s / 1e12 / dfma,
+            "solve_tflops": (2.0 / 3.0 * n_vox ** 3) / (t_solve / K) / 1e12 if t_solve > 0 else None,
+            "solve_frac_of_dmma": (2.0 / 3.0 * n_vox ** 3) / (t_solve / K) / 1e12 / dmma if t_solve > 0 else None}
+
+    line = {"metric": "influence-matrix ray-voxel steps/s + observation LOS/s", "value": value,
+            "unit": "ray-voxel steps/s", "los_per_s": los_per_s, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_total / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "H Ly-alpha source function on 100x60 grid, 24x16 rays (5841 voxels) + "
+                                   f"{n_los} IUVS-like LOS brightness, n_subsamples=10",
+                       "grid": GRID, "n_emissions": 1, "n_los": n_los, "ray_voxel_steps": int(steps_total),
+                       "l2": "256 MB buffer written between timed iterations (L2 flush); K is 273 MB > L2",
+                       "partition": "rows by source voxel, LOS by index" if world > 1 else "single GPU"},
+            "phases_ms": {"influence_traverse+march": t_infl / K * 1e3, "row_exchange": t_exch / K * 1e3,
+                          "solve": t_solve / K * 1e3, "brightness_traverse+march": t_bright / K * 1e3},
+            "solve_gflops": fp64["solve_tflops"] * 1e3 if fp64["solve_tflops"] else None,
+            "roofline": roof, "fp64": fp64,
+            "e2e": {"value": steps_total * Ke / e_infl, "unit": "ray-voxel steps/s", "los_per_s": n_los * Ke / e_bright,
+                    "job_ms": e_total / Ke * 1e3, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches,
+            "clocks": sampler.summary() if sampler else None}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own source, bounded sample
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refbind
+            if refbind.available("f64"):
+                R = refbind.RefModel(scn, "f64")
+                tb, ns = R.build_rows(0, n_vox, args.ref_stride)
+                R.set_sourcefn(0, ctx.solution(0)["S"])
+                tl, _ = R.brightness(locs[:args.ref_los], dirs[:args.ref_los], 10)
+                line["cpu_baseline"] = {"value": ns / tb, "unit": "ray-voxel steps/s", "los_per_s": args.ref_los / tl,
+                                        "cores": R.omp_threads(), "kind": "reference",
+                                        "sample": f"every {args.ref_stride}th source-voxel row ({ns} steps, {tb:.1f} s) and "
+                                                  f"{args.ref_los} lines of sight ({tl:.1f} s)"}
+            else:
+                from oracle import oraclebind
+                O = oraclebind.OracleModel(scn, "f64")
+                tb, ns = O.build_rows(0, n_vox, args.ref_stride)
+                O.set_sourcefn(0, ctx.solution(0)["S"])
+                tl, _ = O.brightness(locs[:args.ref_los], dirs[:args.ref_los], 10)
+                line["cpu_baseline"] = {"value": ns / tb, "unit": "ray-voxel steps/s", "los_per_s": args.ref_los / tl,
+                                        "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"every {args.ref_stride}th source-voxel row ({ns} steps) and {args.ref_los} LOS"}
+        except Exception as ex:   # the baseline is a reported number, never a reason to lose the bench line
+            line["cpu_baseline"] = {"error": str(ex)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-los", type=int, default=1000000)
+    ap.add_argument("--ref-stride", type=int, default=8, help="CPU sample: every k-th source-voxel row")
+    ap.add_argument("--ref-los", type=int, default=50000, help="CPU sample: lines of sight per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -157,6 +157,10 @@ int b200rt_traverse_los(b200rt_ctx *ctx, long long capacity,
  * phase 0 = traversal, 1 = influence march, 2 = solve, 3 = brightness march */
 int b200rt_last_kernel_ms(b200rt_ctx *ctx, int phase, float *ms, int *n_launches);
 int b200rt_synchronize(b200rt_ctx *ctx);
+/* measured FP64 peaks of this device (TFLOP/s): plain DFMA and DMMA.8x8x4 (mma.sync m8n8k4.f64).
+ * They are the roofline denominators of the march kernels and of the solve; the reference has
+ * no counterpart (its timing is my_clock, src/my_clock.cpp:5-15). */
+int b200rt_measure_fp64_peaks(b200rt_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
 
 #ifdef __cplusplus
 }
