@@ -69,6 +69,7 @@ EmissionView<Real> em_view(b200rt_ctx *c, int e) {
   v.T_ratio_pt = t + 4 * n; v.density_pt = t + 5 * n; v.dtau_species_pt = t + 6 * n; v.dtau_absorber_pt = t + 7 * n;
   v.phi = E.phi.as<Real>();
   v.sourcefn = E.S_real.as<Real>();
+  v.rec_pt = E.rec_pt.as<Real>(); v.rec_avg = E.rec_avg.as<Real>();
   v.branching = (Real) E.branching; v.sigma_ref = (Real) E.sigma_ref; v.g_factor = (Real) E.g_factor;
   return v;
 }
@@ -206,6 +207,7 @@ int solve_impl(b200rt_ctx *c, bool reset_timer) {
     else
       B200RT_CUDA(c, launch_convert<float>(E.S.as<double>(), E.S_real.as<float>(), n, c->stream));
     E.have_S = true;
+    E.rec_dirty = true;
   }
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
   PhaseTimer::collect(c);
@@ -230,7 +232,14 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
   B200RT_CUDA(c, c->los_out.ensure((size_t) c->n_em * 4 * n * sizeof(Real)));
   const Real *li = c->los_in.as<Real>();
   EmissionView<Real> ev[MAX_EMISSIONS];
-  for (int e = 0; e < c->n_em; e++) ev[e] = em_view<Real>(c, e);
+  for (int e = 0; e < c->n_em; e++) {
+    ev[e] = em_view<Real>(c, e);
+    Emission &E = c->em[e];
+    if (E.rec_dirty) {
+      B200RT_CUDA(c, launch_pack_records<Real>(ev[e], g.n_vox, E.rec_pt.as<Real>(), E.rec_avg.as<Real>(), c->stream));
+      E.rec_dirty = false;
+    }
+  }
   int *overflow = c->work_counter.as<int>() + 1;
   for (long long first = 0; first < n; first += per_batch) {
     const long long count = std::min(per_batch, n - first);
@@ -245,7 +254,7 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
     {
       PhaseTimer t(c, PH_BRIGHTNESS);
       B200RT_CUDA(c, launch_brightness<Real>(g, ev, c->n_em, li, n, first, count, lv, n_subsamples,
-                                             c->los_out.as<Real>(), n, c->stream));
+                                             c->los_out.as<Real>(), n, c->work_counter.as<int>(), c->stream));
       t.stop(1);
     }
   }
@@ -378,6 +387,9 @@ int set_singlet_impl(b200rt_ctx *c, int e, const double *const arr[8]) {
   B200RT_CUDA(c, E.tau_abs.ensure(n * sizeof(double)));
   B200RT_CUDA(c, E.S.ensure(n * sizeof(double)));
   B200RT_CUDA(c, E.S_real.ensure(n * sizeof(Real)));
+  B200RT_CUDA(c, E.rec_pt.ensure((size_t) n * 8 * sizeof(Real)));
+  B200RT_CUDA(c, E.rec_avg.ensure((size_t) n * 8 * sizeof(Real)));
+  E.rec_dirty = true;
   DevBuf stage;
   int rc = B200RT_OK;
   for (int a = 0; a < 8 && rc == B200RT_OK; a++)
@@ -432,7 +444,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   for (DevBuf *b : bufs) b->release();
   for (int e = 0; e < MAX_EMISSIONS; e++) {
     Emission &E = c->em[e];
-    DevBuf *eb[] = {&E.tabs, &E.phi, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real};
+    DevBuf *eb[] = {&E.tabs, &E.phi, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real, &E.rec_pt, &E.rec_avg};
     for (DevBuf *b : eb) b->release();
   }
   if (c->grid_view) ::operator delete(c->grid_view);
@@ -577,6 +589,7 @@ int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
   else B200RT_CUDA(c, launch_convert<float>(E.S.as<double>(), E.S_real.as<float>(), n, c->stream));
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
   E.have_S = true;
+  E.rec_dirty = true;
   return B200RT_OK;
 }
 

@@ -10,12 +10,22 @@
 //                                                           emission/singlet_CFR.hpp:80-260,315-348,262-276
 //   los_tracker::exits_bottom                               emission/los_tracker.hpp:57-62
 //
-// The boundary list of each line of sight comes from traverse.cu.  Mapping: one
-// thread per line of sight (the reference kernel does the same with 32-thread
-// blocks and a 232-byte tracker staged through shared memory; here the tracker is
-// the register file: P[20] per emission, fully unrolled), all emissions marched in
-// the same pass so the geometry (extend, interpolation weights) is done once.
-// Inputs and outputs are SoA so every global access of a warp is coalesced.
+// The boundary list of each line of sight comes from traverse.cu.
+//
+// Mapping (the reference kernel is one LOS per thread, 32-thread blocks, tracker staged through
+// shared memory; RT_gpu.cu:89-135).  Here a line of sight belongs to a GROUP of 4 lanes:
+//   * the sub-steps of the LOS (segments x (n_subsamples-1)) form one flat stream that the group
+//     consumes 4 at a time: lane q does the GEOMETRY of sub-step j0+q (extend, interp_weights, the
+//     4-corner gathers from one interleaved 64-byte record per voxel) -- four sub-steps in parallel;
+//   * then the four sub-steps are applied in order; for each, the owning lane broadcasts the
+//     interpolated (q = exp(-dl^2 T), n, dtau_s, dtau_a, S, ds) with shuffles and every lane
+//     integrates 5 of the 20 wavelength points (lambda index = sub + 4m), the transmission vector
+//     P[5] staying in registers; the wavelength sum is two shuffles;
+//   * groups pull lines of sight from a device-wide queue, so the 8 groups of a warp stay busy
+//     whatever the segment counts (1..2*n_rb+n_sb) of their lines of sight are.
+// In double the per-wavelength line shape exp(-lambda_i^2 T) is formed from q = exp(-dl^2 T) by
+// repeated products (lambda_i = i dl => q^(i^2)): one exp per sub-step instead of 20; the products
+// carry ~4e-14 relative error against a 1e-6 tolerance.  In float expf is cheap and is kept.
 #include "common.hpp"
 
 namespace b200rt {
@@ -33,7 +43,9 @@ template <> struct MathB<double> {
 };
 template <> struct MathB<float> {
   __device__ static float exp_(float x) { return expf(x); }
-  __device__ static float log_(float x) { return logf(x); }
+  // std::log(float) of the host libm is (nearly) correctly rounded; CUDA logf is not (1 ulp), and one ulp of
+  // logf(r) moves the radial interpolation weight by ~3e-5.  Rounding the double log gives the host's result.
+  __device__ static float log_(float x) { return (float) log((double) x); }
   // atmo_point::xyz calls the unqualified (double) hypot / acos even when Real = float
   // (atmo_vec.cpp:53-54) and rounds on assignment: do the same
   __device__ static float hypot2_(float a, float b, float c) { return (float) hypot(hypot((double) a, (double) b), (double) c); }
@@ -42,182 +54,345 @@ template <> struct MathB<float> {
   __device__ static float coneeps() { return 1e-2f; }   // Real.hpp:16
 };
 
+constexpr int LPR = 4;                       // lanes per line of sight
+constexpr int NLL = N_LAMBDA / LPR;          // wavelength points per lane (5)
+constexpr int REC = 8;                       // Reals per voxel record: T_ratio, density, dtau_species, dtau_absorber, S, pad
+
 template <class Real>
-struct Tracker {   // brightness_tracker + singlet_CFR_tracker<false> (los_tracker.hpp:11-170)
-  Real tau_sp, tau_abs, col, B;
-  Real P[N_LAMBDA];
+__device__ __forceinline__ Real shfl_real(unsigned mask, Real v, int src) { return __shfl_sync(mask, v, src); }
+
+// 4-corner interpolation of one voxel record: s = sum_k w[k]*q[idx[k]] left to right
+// (emission_voxels.hpp:58-70) for the five quantities at once
+template <class Real>
+__device__ __forceinline__ void interp_record(const Real *__restrict__ tab, const int (&idx)[4], const Real (&w)[4],
+                                              Real (&o)[5]);
+template <>
+__device__ __forceinline__ void interp_record<double>(const double *__restrict__ tab, const int (&idx)[4],
+                                                      const double (&w)[4], double (&o)[5]) {
+#pragma unroll
+  for (int q = 0; q < 5; q++) o[q] = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double2 *p = reinterpret_cast<const double2 *>(tab + (size_t) idx[k] * REC);
+    const double2 a = __ldg(p), b = __ldg(p + 1);
+    const double c = __ldg(tab + (size_t) idx[k] * REC + 4);
+    o[0] += w[k] * a.x; o[1] += w[k] * a.y; o[2] += w[k] * b.x; o[3] += w[k] * b.y; o[4] += w[k] * c;
+  }
+}
+template <>
+__device__ __forceinline__ void interp_record<float>(const float *__restrict__ tab, const int (&idx)[4],
+                                                     const float (&w)[4], float (&o)[5]) {
+#pragma unroll
+  for (int q = 0; q < 5; q++) o[q] = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(tab + (size_t) idx[k] * REC));
+    const float c = __ldg(tab + (size_t) idx[k] * REC + 4);
+    o[0] += w[k] * a.x; o[1] += w[k] * a.y; o[2] += w[k] * a.z; o[3] += w[k] * a.w; o[4] += w[k] * c;
+  }
+}
+
+template <class Real>
+__global__ void pack_records_kernel(const Real *__restrict__ Tr, const Real *__restrict__ dn,
+                                    const Real *__restrict__ ds, const Real *__restrict__ da,
+                                    const Real *__restrict__ S, int n_vox, Real *__restrict__ rec) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vox) return;
+  Real *o = rec + (size_t) v * REC;
+  o[0] = Tr[v]; o[1] = dn[v]; o[2] = ds[v]; o[3] = da[v]; o[4] = S[v]; o[5] = 0; o[6] = 0; o[7] = 0;
+}
+
+// per-lane line shapes of one sub-step.  double: from q = exp(-dl^2 T) by products; float: expf
+template <class Real> struct LineShape;
+template <> struct LineShape<double> {
+  // what the geometry lane broadcasts
+  __device__ static double param(double Tr) {
+    const double dl = 4.0 / (N_LAMBDA - 1);
+    return exp(-(dl * dl) * Tr);
+  }
+  __device__ static void eval(double q, int sub, double (&phi)[NLL]) {
+    const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8, q32 = q16 * q16;
+    // phi_sub = q^(sub^2); D = q^(8 sub + 16); phi_{i+4} = phi_i * D; D *= q^32
+    double p = (sub == 0) ? 1.0 : (sub == 1) ? q : (sub == 2) ? q4 : q8 * q;
+    double D = (sub == 0) ? q16 : (sub == 1) ? q16 * q8 : (sub == 2) ? q32 : q32 * q8;
+#pragma unroll
+    for (int m = 0; m < NLL; m++) {
+      phi[m] = p;
+      p *= D;
+      D *= q32;
+    }
+  }
+};
+template <> struct LineShape<float> {
+  __device__ static float param(float Tr) { return Tr; }
+  __device__ static void eval(float Tr, int sub, float (&phi)[NLL]) {
+    const float dl = 4.0f / (N_LAMBDA - 1);
+#pragma unroll
+    for (int m = 0; m < NLL; m++) {
+      const float l = (sub + LPR * m) * dl;
+      phi[m] = expf(-(l * l) * Tr);
+    }
+  }
 };
 
-// singlet_CFR::update_tracker_start<false> + update_tracker_brightness
-template <class Real>
-__device__ __forceinline__ void step(Tracker<Real> &t, Real Tr, Real dens, Real dts, Real dta, Real s, Real Sv,
-                                     Real gfac) {
-  t.col += dens * s;
-  const Real tau_species_voxel = dts * s;
-  t.tau_sp += tau_species_voxel;
-  t.tau_abs += dta * s;
-  const Real delta_lambda = Real(4.0) / (N_LAMBDA - 1);
-  const Real common = dts * s;
-  Real T_int = 0;
-#pragma unroll
-  for (int i = 0; i < N_LAMBDA; i++) {
-    const Real l = i * delta_lambda;
-    const Real lineshape = MathB<Real>::exp_(-(l * l) * Tr);
-    const Real tau = (dta + dts * lineshape) * s;
-    const Real tp = MathB<Real>::exp_(-tau);
-    const Real wgt = (i == 0 || i == N_LAMBDA - 1) ? delta_lambda : Real(2.0) * delta_lambda;
-    Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : (Real(1.0) - tp) / tau;
-    c *= (wgt * lineshape * t.P[i]) * common;
-    T_int += c;
-    t.P[i] *= tp;
-  }
-  if (T_int > tau_species_voxel) T_int = tau_species_voxel;
-  t.B += Sv * gfac * T_int;     // gfac = g * branching / sigma_ref / sqrt(pi) / 1e9
-}
-
-template <class Real>
-__device__ __forceinline__ Real interp4(const Real *__restrict__ q, const int (&idx)[4], const Real (&w)[4]) {
-  Real s = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) s += w[k] * q[idx[k]];
-  return s;
-}
-
 template <class Real, int NEM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> em1,
                   const Real *__restrict__ los_in, long long los_stride, long long first, long long count,
-                  ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total) {
-  const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const long long los = first + i;
+                  ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total,
+                  int *queue) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n_rb = g.n_rb, n_sb = g.n_sb, n_sb1 = n_sb - 1;
+  Real *s_rb = reinterpret_cast<Real *>(smem_raw);   // [n_rb]
+  Real *s_sb = s_rb + n_rb;                          // [n_sb]
+  Real *s_pr = s_sb + n_sb;                          // [n_rb-1]
+  Real *s_lpr = s_pr + n_rb;                         // [n_rb-1]
+  Real *s_ps = s_lpr + n_rb;                         // [n_sb-1]
+  for (int i = threadIdx.x; i < n_rb; i += blockDim.x) s_rb[i] = g.rb[i];
+  for (int i = threadIdx.x; i < n_sb; i += blockDim.x) s_sb[i] = g.sb[i];
+  for (int i = threadIdx.x; i < n_rb - 1; i += blockDim.x) { s_pr[i] = g.pts_r[i]; s_lpr[i] = g.log_pts_r[i]; }
+  for (int i = threadIdx.x; i < n_sb1; i += blockDim.x) s_ps[i] = g.pts_s[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (LPR - 1);
+  const int lead = lane & ~(LPR - 1);
+  const unsigned gmask = 0xFu << lead;
   const EmissionView<Real> em[2] = {em0, em1};
+  const bool interp = n_subsamples != 0;
+  const int nsd = interp ? n_subsamples : 2;
+  const int nss = nsd - 1;                           // sub-steps per segment
+  const Real eps = MathB<Real>::eps(), ceps = MathB<Real>::coneeps();
+  const Real scale = Real(1e9);
+  const Real delta_lambda = Real(4.0) / (N_LAMBDA - 1);
 
-  const Real px = los_in[0 * los_stride + los], py = los_in[1 * los_stride + los], pz = los_in[2 * los_stride + los];
-  const Real lx = los_in[5 * los_stride + los], ly = los_in[6 * los_stride + los], lz = los_in[7 * los_stride + los];
-
-  Tracker<Real> tr[NEM];
+  Real wgt[NLL];
+#pragma unroll
+  for (int m = 0; m < NLL; m++) {
+    const int i = sub + LPR * m;
+    wgt[m] = (i == 0 || i == N_LAMBDA - 1) ? delta_lambda : Real(2.0) * delta_lambda;
+  }
   Real gfac[NEM];
 #pragma unroll
-  for (int e = 0; e < NEM; e++) {
-    tr[e].tau_sp = 0; tr[e].tau_abs = 0; tr[e].col = 0; tr[e].B = 0;
-#pragma unroll
-    for (int k = 0; k < N_LAMBDA; k++) tr[e].P[k] = Real(1);
+  for (int e = 0; e < NEM; e++)
     gfac[e] = em[e].g_factor * em[e].branching / em[e].sigma_ref * (Real) 0.56418958354775628695 / Real(1e9);
-  }
 
-  const int len = lists.len[i];
-  const int n_sb1 = g.n_sb - 1;
-  if (len > 0) {
-    const Real *dl = lists.dist + (size_t) i * lists.cap;
-    const int *el = lists.ent + (size_t) i * lists.cap;
-    const int nsd = (n_subsamples == 0) ? 2 : n_subsamples;
-    const Real eps = MathB<Real>::eps(), ceps = MathB<Real>::coneeps();
-    const Real scale = Real(1e9);
-    Real dprev = dl[0];
-    int cur = el[0];
-    for (int ib = 1; ib < len; ib++) {
+  // group state
+  bool have = false, exhausted = false;
+  long long los = 0;
+  int total = 0, j0 = 0, flagbits = 0;
+  const Real *dl = nullptr;
+  const int *el = nullptr;
+  Real px = 0, py = 0, pz = 0, lx = 0, ly = 0, lz = 0;
+  Real P[NEM][NLL], acc_B[NEM], acc_tsp[NEM], acc_tab[NEM], acc_col[NEM];
+
+  while (true) {
+    // ---- groups without work pull the next line of sight
+    while (!have && !exhausted) {
+      int t = 0;
+      if (sub == 0) t = atomicAdd(queue, 1);
+      t = __shfl_sync(gmask, t, lead);
+      if (t >= count) { exhausted = true; break; }
+      los = first + t;
+      const int len = lists.len[t];
+      if (len <= 0) {     // misses the grid: tracker reset values
+        if (sub == 0) {
+#pragma unroll
+          for (int e = 0; e < NEM; e++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) out[((size_t) e * 4 + q) * n_los_total + los] = Real(0);
+        }
+        continue;
+      }
+      total = (len - 1) * nss;
+      flagbits = lists.flag[t];
+      dl = lists.dist + (size_t) t * lists.cap;
+      el = lists.ent + (size_t) t * lists.cap;
+      px = los_in[0 * los_stride + los]; py = los_in[1 * los_stride + los]; pz = los_in[2 * los_stride + los];
+      lx = los_in[5 * los_stride + los]; ly = los_in[6 * los_stride + los]; lz = los_in[7 * los_stride + los];
+#pragma unroll
+      for (int e = 0; e < NEM; e++) {
+        acc_B[e] = 0; acc_tsp[e] = 0; acc_tab[e] = 0; acc_col[e] = 0;
+#pragma unroll
+        for (int m = 0; m < NLL; m++) P[e][m] = Real(1);
+      }
+      j0 = 0;
+      have = true;
+    }
+    if (__all_sync(0xffffffffu, !have)) break;
+
+    // ---- geometry of sub-step j0+sub (four sub-steps of the group in parallel)
+    Real my_s = 0;
+    Real my_in[NEM][5];
+#pragma unroll
+    for (int e = 0; e < NEM; e++)
+#pragma unroll
+      for (int q = 0; q < 5; q++) my_in[e][q] = 0;
+    const int j = j0 + sub;
+    if (have && j < total) {
+      const int ib = j / nss + 1;
+      const int is = j - (ib - 1) * nss + 1;
+      Real d_start = dl[ib - 1];
       const Real dnext = dl[ib];
-      Real d_start = dprev;
+      const int cur = el[ib - 1];
       Real d_step = (dnext - d_start) / (nsd - 1);
       d_start += Real(0.5) * eps * d_step;          // RT_grid.hpp:268-271
       d_step *= Real(1.0) - eps;
-
-      if (n_subsamples == 0) {
+      my_s = d_step;
+      if (!interp) {
 #pragma unroll
-        for (int e = 0; e < NEM; e++)
-          step(tr[e], em[e].T_ratio[cur], em[e].density[cur], em[e].dtau_species[cur], em[e].dtau_absorber[cur],
-               d_step, em[e].sourcefn[cur], gfac[e]);
+        for (int e = 0; e < NEM; e++) {
+          const Real *r = em[e].rec_avg + (size_t) cur * REC;
+#pragma unroll
+          for (int q = 0; q < 5; q++) my_in[e][q] = r[q];
+        }
       } else {
-        const int r_idx = cur / n_sb1, sza_idx = cur % n_sb1;
-        const Real rb_lo = g.rb[r_idx], rb_hi = g.rb[r_idx + 1];
-        const Real sb_lo = g.sb[sza_idx], sb_hi = g.sb[sza_idx + 1];
-        const Real ps_c = g.pts_s[sza_idx];
-        for (int is = 1; is < nsd; is++) {
-          // ---- atmo_vector::extend
-          const Real dist = d_start + is * d_step;
-          const Real nx = px / scale + (lx * dist) / scale;
-          const Real ny = py / scale + (ly * dist) / scale;
-          const Real nz = pz / scale + (lz * dist) / scale;
-          const Real rr = MathB<Real>::hypot2_(nx, ny, nz);
-          Real t = MathB<Real>::acos_(nz / rr);
-          Real r = rr * scale;
-          // ---- interp_weights
-          if (r < rb_lo && rb_lo / r > (1 - eps)) r = rb_lo + eps;
-          if (rb_hi < r && r / rb_hi < (1 + eps)) r = rb_hi - eps;
-          if (t < sb_lo && sb_lo / t > (1 - ceps)) t = sb_lo + ceps;
-          if (sb_hi < t && t / sb_hi < (1 + ceps)) t = sb_hi - ceps;
-          int rlo, rhi;
-          Real r_wt;
-          if (r_idx == 0 && r <= g.pts_r[0]) { rlo = rhi = 0; r_wt = 1.0; }
-          else if (r_idx == g.n_rb - 2 && g.pts_r[g.n_rb - 2] <= r) { rlo = rhi = g.n_rb - 2; r_wt = 0.0; }
-          else {
-            rlo = (r < g.pts_r[r_idx]) ? r_idx - 1 : r_idx;
-            rhi = rlo + 1;
-            const Real l0 = g.log_pts_r[rlo], l1 = g.log_pts_r[rhi];
-            r_wt = (MathB<Real>::log_(r) - l0) / (l1 - l0);
-          }
-          int slo = (t < ps_c) ? sza_idx - 1 : sza_idx;
-          slo = max(0, min(slo, n_sb1 - 2));        // guard (the reference would index out of bounds)
-          const int shi = slo + 1;
-          const Real p0 = g.pts_s[slo], p1 = g.pts_s[shi];
-          const Real s_wt = (t - p0) / (p1 - p0);
-          int idx[4];
-          Real w[4];
-          idx[0] = rlo * n_sb1 + slo; w[0] = (Real(1.0) - r_wt) * (Real(1.0) - s_wt);
-          idx[1] = rhi * n_sb1 + slo; w[1] = r_wt * (Real(1.0) - s_wt);
-          idx[2] = rlo * n_sb1 + shi; w[2] = (Real(1.0) - r_wt) * s_wt;
-          idx[3] = rhi * n_sb1 + shi; w[3] = r_wt * s_wt;
+        const int r_idx = cur / n_sb1, sza_idx = cur - r_idx * n_sb1;
+        const Real rb_lo = s_rb[r_idx], rb_hi = s_rb[r_idx + 1];
+        const Real sb_lo = s_sb[sza_idx], sb_hi = s_sb[sza_idx + 1];
+        // ---- atmo_vector::extend
+        const Real dist = d_start + is * d_step;
+        const Real nx = px / scale + (lx * dist) / scale;
+        const Real ny = py / scale + (ly * dist) / scale;
+        const Real nz = pz / scale + (lz * dist) / scale;
+        const Real rr = MathB<Real>::hypot2_(nx, ny, nz);
+        Real t = MathB<Real>::acos_(nz / rr);
+        Real r = rr * scale;
+        // ---- interp_weights
+        if (r < rb_lo && rb_lo / r > (1 - eps)) r = rb_lo + eps;
+        if (rb_hi < r && r / rb_hi < (1 + eps)) r = rb_hi - eps;
+        if (t < sb_lo && sb_lo / t > (1 - ceps)) t = sb_lo + ceps;
+        if (sb_hi < t && t / sb_hi < (1 + ceps)) t = sb_hi - ceps;
+        int rlo, rhi;
+        Real r_wt;
+        if (r_idx == 0 && r <= s_pr[0]) { rlo = rhi = 0; r_wt = 1.0; }
+        else if (r_idx == n_rb - 2 && s_pr[n_rb - 2] <= r) { rlo = rhi = n_rb - 2; r_wt = 0.0; }
+        else {
+          rlo = (r < s_pr[r_idx]) ? r_idx - 1 : r_idx;
+          rhi = rlo + 1;
+          const Real l0 = s_lpr[rlo], l1 = s_lpr[rhi];
+          r_wt = (MathB<Real>::log_(r) - l0) / (l1 - l0);
+        }
+        int slo = (t < s_ps[sza_idx]) ? sza_idx - 1 : sza_idx;
+        slo = max(0, min(slo, n_sb1 - 2));          // guard (the reference would index out of bounds)
+        const int shi = slo + 1;
+        const Real p0 = s_ps[slo], p1 = s_ps[shi];
+        const Real s_wt = (t - p0) / (p1 - p0);
+        int idx[4];
+        Real w[4];
+        idx[0] = rlo * n_sb1 + slo; w[0] = (Real(1.0) - r_wt) * (Real(1.0) - s_wt);
+        idx[1] = rhi * n_sb1 + slo; w[1] = r_wt * (Real(1.0) - s_wt);
+        idx[2] = rlo * n_sb1 + shi; w[2] = (Real(1.0) - r_wt) * s_wt;
+        idx[3] = rhi * n_sb1 + shi; w[3] = r_wt * s_wt;
 #pragma unroll
-          for (int e = 0; e < NEM; e++) {
-            const Real Tr = interp4(em[e].T_ratio_pt, idx, w);
-            const Real dn = interp4(em[e].density_pt, idx, w);
-            const Real ds = interp4(em[e].dtau_species_pt, idx, w);
-            const Real da = interp4(em[e].dtau_absorber_pt, idx, w);
-            const Real Sv = interp4(em[e].sourcefn, idx, w);
-            step(tr[e], Tr, dn, ds, da, d_step, Sv, gfac[e]);
+        for (int e = 0; e < NEM; e++) interp_record<Real>(em[e].rec_pt, idx, w, my_in[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < NEM; e++) my_in[e][0] = LineShape<Real>::param(my_in[e][0]);
+    }
+
+    // ---- apply the four sub-steps in order
+    const int nvalid = have ? min(LPR, total - j0) : 0;
+#pragma unroll
+    for (int q = 0; q < LPR; q++) {
+      if (q < nvalid) {
+        const Real s = shfl_real<Real>(gmask, my_s, lead + q);
+#pragma unroll
+        for (int e = 0; e < NEM; e++) {
+          const Real lsp = shfl_real<Real>(gmask, my_in[e][0], lead + q);
+          const Real dens = shfl_real<Real>(gmask, my_in[e][1], lead + q);
+          const Real dts = shfl_real<Real>(gmask, my_in[e][2], lead + q);
+          const Real dta = shfl_real<Real>(gmask, my_in[e][3], lead + q);
+          const Real Sv = shfl_real<Real>(gmask, my_in[e][4], lead + q);
+          // singlet_CFR::update_tracker_start<false> + update_tracker_brightness
+          acc_col[e] += dens * s;
+          const Real tau_species_voxel = dts * s;
+          acc_tsp[e] += tau_species_voxel;
+          acc_tab[e] += dta * s;
+          const Real common = dts * s;
+          Real phi[NLL];
+          LineShape<Real>::eval(lsp, sub, phi);
+          Real T_int = 0;
+#pragma unroll
+          for (int m = 0; m < NLL; m++) {
+            const Real lineshape = phi[m];
+            const Real tau = (dta + dts * lineshape) * s;
+            const Real tp = MathB<Real>::exp_(-tau);
+            Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : (Real(1.0) - tp) / tau;
+            c *= (wgt[m] * lineshape * P[e][m]) * common;
+            T_int += c;
+            P[e][m] *= tp;
           }
+          T_int += __shfl_xor_sync(gmask, T_int, 1);
+          T_int += __shfl_xor_sync(gmask, T_int, 2);
+          if (T_int > tau_species_voxel) T_int = tau_species_voxel;
+          acc_B[e] += Sv * gfac[e] * T_int;
         }
       }
-      dprev = dnext;
-      cur = el[ib];
     }
-    if (lists.flag[i] & 1) {
+    j0 += LPR;
+
+    // ---- line of sight finished: write the four tracker members
+    if (have && j0 >= total) {
+      if (sub == 0) {
 #pragma unroll
-      for (int e = 0; e < NEM; e++) tr[e].tau_abs = Real(-1.0);   // los_tracker::exits_bottom
+        for (int e = 0; e < NEM; e++) {
+          out[((size_t) e * 4 + 0) * n_los_total + los] = acc_B[e];
+          out[((size_t) e * 4 + 1) * n_los_total + los] = acc_tsp[e];
+          out[((size_t) e * 4 + 2) * n_los_total + los] = (flagbits & 1) ? Real(-1.0) : acc_tab[e];   // exits_bottom
+          out[((size_t) e * 4 + 3) * n_los_total + los] = acc_col[e];
+        }
+      }
+      have = false;
     }
-  }
-#pragma unroll
-  for (int e = 0; e < NEM; e++) {
-    out[((size_t) e * 4 + 0) * n_los_total + los] = tr[e].B;
-    out[((size_t) e * 4 + 1) * n_los_total + los] = tr[e].tau_sp;
-    out[((size_t) e * 4 + 2) * n_los_total + los] = tr[e].tau_abs;
-    out[((size_t) e * 4 + 3) * n_los_total + los] = tr[e].col;
   }
 }
 
 } // namespace
 
 template <class Real>
+cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *rec_pt, Real *rec_avg, cudaStream_t s) {
+  const int threads = 256, blocks = (n_vox + threads - 1) / threads;
+  pack_records_kernel<Real><<<blocks, threads, 0, s>>>(em.T_ratio_pt, em.density_pt, em.dtau_species_pt,
+                                                        em.dtau_absorber_pt, em.sourcefn, n_vox, rec_pt);
+  pack_records_kernel<Real><<<blocks, threads, 0, s>>>(em.T_ratio, em.density, em.dtau_species, em.dtau_absorber,
+                                                        em.sourcefn, n_vox, rec_avg);
+  return cudaGetLastError();
+}
+
+template <class Real>
 cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em, const Real *los_in,
                               long long los_stride, long long first, long long count, ListView<Real> lists,
-                              int n_subsamples, Real *out, long long n_los_total, cudaStream_t s) {
+                              int n_subsamples, Real *out, long long n_los_total, int *queue, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
   const int threads = 128;
-  const unsigned blocks = (unsigned) ((count + threads - 1) / threads);
-  if (n_em == 1)
-    brightness_kernel<Real, 1><<<blocks, threads, 0, s>>>(g, em[0], em[0], los_in, los_stride, first, count, lists,
-                                                          n_subsamples, out, n_los_total);
-  else
-    brightness_kernel<Real, 2><<<blocks, threads, 0, s>>>(g, em[0], em[1], los_in, los_stride, first, count, lists,
-                                                          n_subsamples, out, n_los_total);
+  const size_t smem = (size_t) (4 * g.n_rb + 2 * g.n_sb) * sizeof(Real);
+  const long long groups = (count + 0);
+  long long blocks = (groups * LPR + threads - 1) / threads;
+  const long long persistent = (long long) NUM_SMS * 4;   // __launch_bounds__(128, 4)
+  if (blocks > persistent) blocks = persistent;
+  if (n_em == 1) {
+    e = cudaFuncSetAttribute(brightness_kernel<Real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    brightness_kernel<Real, 1><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[0], los_in, los_stride, first, count,
+                                                                        lists, n_subsamples, out, n_los_total, queue);
+  } else {
+    e = cudaFuncSetAttribute(brightness_kernel<Real, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    brightness_kernel<Real, 2><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[1], los_in, los_stride, first, count,
+                                                                        lists, n_subsamples, out, n_los_total, queue);
+  }
   return cudaGetLastError();
 }
 template cudaError_t launch_brightness<double>(const GridView<double> &, const EmissionView<double> *, int,
                                                const double *, long long, long long, long long, ListView<double>, int,
-                                               double *, long long, cudaStream_t);
+                                               double *, long long, int *, cudaStream_t);
 template cudaError_t launch_brightness<float>(const GridView<float> &, const EmissionView<float> *, int, const float *,
                                               long long, long long, long long, ListView<float>, int, float *,
-                                              long long, cudaStream_t);
+                                              long long, int *, cudaStream_t);
+template cudaError_t launch_pack_records<double>(const EmissionView<double> &, int, double *, double *, cudaStream_t);
+template cudaError_t launch_pack_records<float>(const EmissionView<float> &, int, float *, float *, cudaStream_t);
 
 } // namespace b200rt

@@ -79,6 +79,8 @@ struct EmissionView {
   const Real *T_ratio_pt, *density_pt, *dtau_species_pt, *dtau_absorber_pt;  // voxel points
   const Real *phi;        // [n_vox][N_LAMBDA] line shape exp(-lambda_i^2 T_ratio) of the averages
   const Real *sourcefn;   // [n_vox]
+  const Real *rec_pt;     // [n_vox][8] interleaved {T_ratio_pt, density_pt, dtau_species_pt, dtau_absorber_pt, S, pad}
+  const Real *rec_avg;    // [n_vox][8] the same for the voxel averages (brightness_nointerp)
   Real branching, sigma_ref, g_factor;
 };
 
@@ -98,6 +100,8 @@ struct Emission {
   DevBuf S0, tau_sp, tau_abs;  // n_vox double
   DevBuf S;        // n_vox double (solution)
   DevBuf S_real;   // n_vox Real   (what the brightness kernel reads)
+  DevBuf rec_pt, rec_avg;   // n_vox * 8 Real each: interleaved records for the brightness gathers
+  bool rec_dirty = true;    // tables or S changed since the records were packed
 };
 
 enum Phase { PH_TRAVERSE = 0, PH_INFLUENCE = 1, PH_SOLVE = 2, PH_BRIGHTNESS = 3, PH_COUNT = 4 };
@@ -193,7 +197,9 @@ template <class Real>
 cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em,
                               const Real *los_in, long long los_stride, long long first,
                               long long count, ListView<Real> lists, int n_subsamples, Real *out,
-                              long long n_los_total, cudaStream_t s);
+                              long long n_los_total, int *queue, cudaStream_t s);
+template <class Real>
+cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *rec_pt, Real *rec_avg, cudaStream_t s);
 
 // ---- peaks.cu
 int measure_fp64_peaks(b200rt_ctx *c, double *dfma_tflops, double *dmma_tflops);

@@ -4,10 +4,10 @@ import numpy as np
 TOL = {"f64": 1e-6, "f32": 1e-4}   # BASELINE.json north_star: 1e-6 relative (double Real), 1e-4 (float Real)
 # The north star names influence matrix, source function and brightness.  The other three tracker
 # outputs (tau_species_final, tau_absorber_final, species_col_dens) are sums of 4-point interpolants
-# whose radial weight is (logf(r) - l0)/(l1 - l0): in float that quotient carries ~2e-4 of rounding noise
-# (ulp(logf(3.5e8)) = 1.9e-6 over l1 - l0 ~ 1e-2), so two float builds that differ by one ulp in logf
-# already disagree at the 1e-4 level on them.  They are held to 1e-3 in float, 1e-6 in double.
-TOL_AUX = {"f64": 1e-6, "f32": 1e-3}
+# whose radial weight is (log(r) - l0)/(l1 - l0): in float one ulp of log(r) moves that weight by ~3e-5,
+# so the device rounds the DOUBLE log to float (what the host libm's logf returns in all but rare
+# cases); measured worst case over the test sets is 5.3e-5.  They are held to 2e-4 in float.
+TOL_AUX = {"f64": 1e-6, "f32": 2e-4}
 
 
 def rel_err(a, b, floor=0.0):
