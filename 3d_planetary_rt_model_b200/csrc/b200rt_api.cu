@@ -68,6 +68,7 @@ EmissionView<Real> em_view(b200rt_ctx *c, int e) {
   v.T_ratio = t + 0 * n; v.density = t + 1 * n; v.dtau_species = t + 2 * n; v.dtau_absorber = t + 3 * n;
   v.T_ratio_pt = t + 4 * n; v.density_pt = t + 5 * n; v.dtau_species_pt = t + 6 * n; v.dtau_absorber_pt = t + 7 * n;
   v.phi = E.phi.as<Real>();
+  v.mrec = E.mrec.as<Real>();
   v.sourcefn = E.S_real.as<Real>();
   v.rec_pt = E.rec_pt.as<Real>(); v.rec_avg = E.rec_avg.as<Real>();
   v.branching = (Real) E.branching; v.sigma_ref = (Real) E.sigma_ref; v.g_factor = (Real) E.g_factor;
@@ -381,6 +382,7 @@ int set_singlet_impl(b200rt_ctx *c, int e, const double *const arr[8]) {
   Emission &E = c->em[e];
   B200RT_CUDA(c, E.tabs.ensure((size_t) 8 * n * sizeof(Real)));
   B200RT_CUDA(c, E.phi.ensure((size_t) n * N_LAMBDA * sizeof(Real)));
+  B200RT_CUDA(c, E.mrec.ensure((size_t) n * 2 * N_LAMBDA * sizeof(Real)));
   B200RT_CUDA(c, E.K.ensure((size_t) n * n * sizeof(double)));
   B200RT_CUDA(c, E.S0.ensure(n * sizeof(double)));
   B200RT_CUDA(c, E.tau_sp.ensure(n * sizeof(double)));
@@ -395,7 +397,8 @@ int set_singlet_impl(b200rt_ctx *c, int e, const double *const arr[8]) {
   for (int a = 0; a < 8 && rc == B200RT_OK; a++)
     rc = upload_real<Real>(c, arr[a], E.tabs.as<Real>() + (size_t) a * n, n, stage);
   if (rc == B200RT_OK) {
-    cudaError_t er = launch_phi_table<Real>(E.tabs.as<Real>(), n, E.phi.as<Real>(), c->stream);
+    cudaError_t er = launch_phi_table<Real>(E.tabs.as<Real>(), E.tabs.as<Real>() + 2 * (size_t) n, E.tabs.as<Real>() + 3 * (size_t) n, n,
+                                            E.phi.as<Real>(), E.mrec.as<Real>(), c->stream);
     if (er == cudaSuccess) er = cudaStreamSynchronize(c->stream);
     if (er != cudaSuccess) rc = fail(c, B200RT_ERR_CUDA, cudaGetErrorString(er));
   }
@@ -444,10 +447,12 @@ int b200rt_destroy(b200rt_ctx *c) {
   for (DevBuf *b : bufs) b->release();
   for (int e = 0; e < MAX_EMISSIONS; e++) {
     Emission &E = c->em[e];
-    DevBuf *eb[] = {&E.tabs, &E.phi, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real, &E.rec_pt, &E.rec_avg};
+    DevBuf *eb[] = {&E.tabs, &E.phi, &E.mrec, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real, &E.rec_pt, &E.rec_avg};
     for (DevBuf *b : eb) b->release();
   }
   if (c->grid_view) ::operator delete(c->grid_view);
+  for (cudaEvent_t ev : c->lu_events) cudaEventDestroy(ev);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
   return B200RT_OK;

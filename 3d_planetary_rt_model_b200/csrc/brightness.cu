@@ -27,6 +27,7 @@
 // repeated products (lambda_i = i dl => q^(i^2)): one exp per sub-step instead of 20; the products
 // carry ~4e-14 relative error against a 1e-6 tolerance.  In float expf is cheap and is kept.
 #include "common.hpp"
+#include "fastmath.cuh"
 
 namespace b200rt {
 
@@ -34,7 +35,8 @@ namespace {
 
 template <class Real> struct MathB;
 template <> struct MathB<double> {
-  __device__ static double exp_(double x) { return exp(x); }
+  __device__ static double exp_(double x) { return fm::exp_nonpos(x); }   // arguments are <= 0 and finite
+  __device__ static double div_(double a, double b) { return fm::div_pos(a, b); }   // b >= 1e-3 where it is used
   __device__ static double log_(double x) { return log(x); }
   __device__ static double hypot2_(double a, double b, double c) { return hypot(hypot(a, b), c); }
   __device__ static double acos_(double x) { return acos(x); }
@@ -43,6 +45,7 @@ template <> struct MathB<double> {
 };
 template <> struct MathB<float> {
   __device__ static float exp_(float x) { return expf(x); }
+  __device__ static float div_(float a, float b) { return a / b; }
   // std::log(float) of the host libm is (nearly) correctly rounded; CUDA logf is not (1 ulp), and one ulp of
   // logf(r) moves the radial interpolation weight by ~3e-5.  Rounding the double log gives the host's result.
   __device__ static float log_(float x) { return (float) log((double) x); }
@@ -108,7 +111,7 @@ template <> struct LineShape<double> {
   // what the geometry lane broadcasts
   __device__ static double param(double Tr) {
     const double dl = 4.0 / (N_LAMBDA - 1);
-    return exp(-(dl * dl) * Tr);
+    return fm::exp_nonpos(-(dl * dl) * Tr);
   }
   __device__ static void eval(double q, int sub, double (&phi)[NLL]) {
     const double q2 = q * q, q4 = q2 * q2, q8 = q4 * q4, q16 = q8 * q8, q32 = q16 * q16;
@@ -136,7 +139,7 @@ template <> struct LineShape<float> {
 };
 
 template <class Real, int NEM>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, (NEM == 2 && sizeof(Real) == 8) ? 3 : 4)
 brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> em1,
                   const Real *__restrict__ los_in, long long los_stride, long long first, long long count,
                   ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total,
@@ -318,7 +321,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
             const Real lineshape = phi[m];
             const Real tau = (dta + dts * lineshape) * s;
             const Real tp = MathB<Real>::exp_(-tau);
-            Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : (Real(1.0) - tp) / tau;
+            Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::div_(Real(1.0) - tp, tau);
             c *= (wgt[m] * lineshape * P[e][m]) * common;
             T_int += c;
             P[e][m] *= tp;

@@ -78,6 +78,7 @@ struct EmissionView {
   const Real *T_ratio, *density, *dtau_species, *dtau_absorber;              // voxel averages
   const Real *T_ratio_pt, *density_pt, *dtau_species_pt, *dtau_absorber_pt;  // voxel points
   const Real *phi;        // [n_vox][N_LAMBDA] line shape exp(-lambda_i^2 T_ratio) of the averages
+  const Real *mrec;       // [n_vox][4][5]{kappa, wratio}: march records (influence.cu)
   const Real *sourcefn;   // [n_vox]
   const Real *rec_pt;     // [n_vox][8] interleaved {T_ratio_pt, density_pt, dtau_species_pt, dtau_absorber_pt, S, pad}
   const Real *rec_avg;    // [n_vox][8] the same for the voxel averages (brightness_nointerp)
@@ -96,6 +97,7 @@ struct Emission {
   double residual = -1;
   DevBuf tabs;     // 8 * n_vox Real
   DevBuf phi;      // n_vox * N_LAMBDA Real
+  DevBuf mrec;     // n_vox * 2 * N_LAMBDA Real
   DevBuf K;        // n_vox^2 double, row major
   DevBuf S0, tau_sp, tau_abs;  // n_vox double
   DevBuf S;        // n_vox double (solution)
@@ -139,6 +141,8 @@ struct b200rt_ctx {
 
   // dense solve workspace
   b200rt::DevBuf lu, lu_dinv, lu_flag;
+  cudaStream_t stream2 = nullptr;            // look-ahead stream of the LU
+  std::vector<cudaEvent_t> lu_events;
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -190,7 +194,8 @@ cudaError_t launch_single_scattering(const GridView<Real> &g, const EmissionView
                                      ListView<Real> lists, const int *shadow, double *S0,
                                      double *tau_sp, double *tau_abs, int *work_counter, cudaStream_t s);
 template <class Real>
-cudaError_t launch_phi_table(const Real *T_ratio, int n_vox, Real *phi, cudaStream_t s);
+cudaError_t launch_phi_table(const Real *T_ratio, const Real *dts, const Real *dta, int n_vox, Real *phi, Real *mrec,
+                             cudaStream_t s);
 
 // ---- brightness.cu
 template <class Real>

@@ -1,0 +1,61 @@
+// fastmath.cuh -- branch-free FP64 exp and division for the march kernels (sm_100a).
+//
+// Why not exp()/operator/ of the CUDA math library: in the march kernels they are ~all of the
+// arithmetic, and ncu's opcode mix of the first version showed 23-26 % of the issued
+// instructions were UMOV (the library's polynomial coefficients re-materialised through uniform
+// registers), 10 % BRA/BSSY/BSYNC (slow-path guards of exp and of the IEEE division) and only
+// ~35 % FP64.  Here the coefficients are constant-bank operands of the DFMAs and there is no
+// slow path: arguments of the marches are finite and <= 0 (exp) and normal, positive (division).
+// Accuracy: exp_nonpos <= 1 ulp (polynomial 1.5e-17 relative + Horner rounding), division <= 1 ulp.
+// The parity bar of these quantities is 1e-6 relative; geometry never uses these.
+#pragma once
+
+namespace b200rt {
+namespace fm {
+
+// degree-11 Chebyshev-node interpolant of exp on [-ln2/2, ln2/2] (max relative error 1.5e-17)
+__constant__ double EXPC[12] = {
+    1.0, 1.0, 0x1.0000000000011p-1, 0x1.555555555555ap-3, 0x1.555555554f067p-5, 0x1.111111110f205p-7,
+    0x1.6c16c1881156bp-10, 0x1.a01a01b150ad2p-13, 0x1.a01991731e6fap-16, 0x1.71ddf5514be0cp-19,
+    0x1.28b43a93fe57ap-22, 0x1.af635e4f6b5eep-26};
+__constant__ double EXPK[4] = {
+    1.4426950408889634074,        // log2(e)
+    6755399441055744.0,           // 1.5 * 2^52: adding it leaves rint(t) in the low mantissa bits
+    -6.93147180369123816490e-01,  // -ln2 high part (low 21 mantissa bits zero: k*hi is exact)
+    -1.90821492927058770002e-10}; // -ln2 low part
+
+// exp(x) for finite x <= 0 (also correct up to x ~ +700).  Underflows through the denormals to
+// exactly 0 like the host libm: the power of two is applied in two halves.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double t = fma(x, EXPK[0], EXPK[1]);
+  int k = __double2loint(t);
+  const double kd = t - EXPK[1];
+  double r = fma(kd, EXPK[2], x);
+  r = fma(kd, EXPK[3], r);
+  double p = EXPC[11];
+#pragma unroll
+  for (int i = 10; i >= 0; i--) p = fma(p, r, EXPC[i]);
+  k = max(k, -2000);
+  const int k1 = k >> 1, k2 = k - k1;
+  const double s1 = __hiloint2double((1023 + k1) << 20, 0);
+  const double s2 = __hiloint2double((1023 + k2) << 20, 0);
+  return (p * s1) * s2;
+}
+
+// a / b for normal positive b (|b| in [1e-290, 1e290]), no special cases
+__device__ __forceinline__ double div_pos(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  const double q = a * r;
+  const double rem = fma(-b, q, a);
+  return fma(rem, r, q);
+}
+
+} // namespace fm
+} // namespace b200rt

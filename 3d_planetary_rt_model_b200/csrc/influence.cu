@@ -16,9 +16,20 @@
 // 20 wavelength points (lambda index = sub + 4 m): the per-wavelength transmission
 // vector P[] lives in registers, the per-step sum over wavelengths is two shuffles,
 // and the step's contribution domega*G goes to K[row][voxel] with one fp64 RED.
-// Per-voxel line shapes phi(lambda_i; T) are tabulated once per emission
-// (phi_table_kernel) so a step costs one exp() per wavelength instead of three.
+//
+// Per-voxel tables (march_table_kernel, once per emission) replace everything in the step that
+// does not depend on the path length s:
+//     kappa_i  = dtau_absorber + dtau_species * phi_i            (tau_i = kappa_i * s, as the reference rounds it)
+//     wratio_i = w_i * dtau_species * phi_i / kappa_i
+// so that  c_i = (1 - exp(-tau_i))/tau_i * (w_i phi_i P_i dtau_species s)  [singlet_CFR.hpp:141-159]
+//              = wratio_i * P_i * (1 - exp(-tau_i))                        (s cancels: no division in the march)
+// and, below the reference's series switch tau_i < 1e-3,  c_i = wratio_i * P_i * (1 - tau_i/2) * tau_i.
+// The record of a voxel is laid out [lane 0..3][m 0..4]{kappa, wratio}: a lane reads its 80 bytes
+// with five 16-byte loads, and the record of the NEXT step is fetched while the current one is
+// integrated (software pipeline), because ncu showed the first version waiting on these loads.
+// exp is fm::exp_nonpos in double (fastmath.cuh), expf in float.
 #include "common.hpp"
+#include "fastmath.cuh"
 
 namespace b200rt {
 
@@ -26,6 +37,9 @@ namespace {
 
 template <class Real> __device__ __forceinline__ Real rexp(Real x);
 template <> __device__ __forceinline__ double rexp<double>(double x) { return exp(x); }
+template <class Real> __device__ __forceinline__ Real exp_neg(Real x);   // x <= 0, finite
+template <> __device__ __forceinline__ double exp_neg<double>(double x) { return fm::exp_nonpos(x); }
+template <> __device__ __forceinline__ float exp_neg<float>(float x) { return expf(x); }
 template <> __device__ __forceinline__ float rexp<float>(float x) { return expf(x); }
 template <class Real> __device__ __forceinline__ Real rsqrt_(Real x);
 template <> __device__ __forceinline__ double rsqrt_<double>(double x) { return sqrt(x); }
@@ -57,19 +71,42 @@ __global__ void phi_table_kernel(const Real *__restrict__ T_ratio, int n_vox, Re
 constexpr int LANES_PER_RAY = 4;
 constexpr int RAYS_PER_WARP = 32 / LANES_PER_RAY;
 constexpr int LAMBDA_PER_LANE = N_LAMBDA / LANES_PER_RAY;   // 5
+constexpr int MREC = 2 * N_LAMBDA;                          // Reals per voxel record
+
+// march record of voxel v: [sub][m]{kappa, wratio}, lambda index i = sub + 4 m
+template <class Real>
+__global__ void march_table_kernel(const Real *__restrict__ phi, const Real *__restrict__ dts,
+                                   const Real *__restrict__ dta, int n_vox, Real *__restrict__ mrec) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_vox * N_LAMBDA) return;
+  const int v = idx / N_LAMBDA, i = idx % N_LAMBDA;
+  const int sub = i % LANES_PER_RAY, m = i / LANES_PER_RAY;
+  const Real ls = phi[idx];
+  const Real kappa = dta[v] + dts[v] * ls;
+  const Real wr = (kappa > 0) ? weight_of<Real>(i) * (dts[v] * ls) / kappa : Real(0);
+  Real *o = mrec + (size_t) v * MREC + (sub * LAMBDA_PER_LANE + m) * 2;
+  o[0] = kappa;
+  o[1] = wr;
+}
+
+template <class Real> struct Rec2;      // {kappa, wratio} pair as one 16-byte (8-byte) load
+template <> struct Rec2<double> { typedef double2 type; };
+template <> struct Rec2<float> { typedef float2 type; };
 
 // MODE 0: rows of the influence matrix (voxel-origin rays); MODE 1: sun-ward rays -> S0, tau
 template <class Real, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_rays_total,
              ListView<Real> lists, const int *__restrict__ shadow, double *__restrict__ K,
              double *__restrict__ S0, double *__restrict__ tau_sp_out, double *__restrict__ tau_abs_out,
              int *work_counter, unsigned long long *step_counter) {
+  typedef typename Rec2<Real>::type R2;
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LANES_PER_RAY - 1);
   const int grp = lane / LANES_PER_RAY;
   const int cap = lists.cap;
   const long long n_tasks = (n_rays_total + RAYS_PER_WARP - 1) / RAYS_PER_WARP;
+  const R2 *__restrict__ mrec = reinterpret_cast<const R2 *>(em.mrec) + sub * LAMBDA_PER_LANE;
 
   Real w[LAMBDA_PER_LANE], l2[LAMBDA_PER_LANE];
 #pragma unroll
@@ -95,10 +132,10 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
     }
     const Real Tr0 = valid ? em.T_ratio[v0] : Real(1);
     const Real renorm = one_over_sqrt_pi<Real>() * rsqrt_<Real>(Tr0);   // line_shape_normalization
-    Real ls0[LAMBDA_PER_LANE], P[LAMBDA_PER_LANE];
+    Real nl0[LAMBDA_PER_LANE], P[LAMBDA_PER_LANE];                      // norm(T0) * phi0_i ;  transmission
 #pragma unroll
     for (int m = 0; m < LAMBDA_PER_LANE; m++) {
-      ls0[m] = rexp<Real>(-l2[m] * Tr0);
+      nl0[m] = renorm * rexp<Real>(-l2[m] * Tr0);
       P[m] = Real(1);
     }
     const Real domega = (MODE == 0 && valid) ? g.ray_domega[ir] : Real(1);
@@ -110,46 +147,67 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
 
     const Real *dl = lists.dist + (size_t) (valid ? ray : 0) * cap;
     const int *el = lists.ent + (size_t) (valid ? ray : 0) * cap;
-    Real dprev = (len > 1) ? dl[0] : Real(0);
-    int vox = (len > 1) ? el[0] : 0;
+    double *Krow = (MODE == 0) ? K + (size_t) v0 * g.n_vox : nullptr;
+
+    // software pipeline: everything step k needs is loaded during step k-1
+    Real d_prev = 0, d_cur = 0;
+    int vox = 0, vox_next = 0;
+    R2 rec[LAMBDA_PER_LANE];
+#pragma unroll
+    for (int m = 0; m < LAMBDA_PER_LANE; m++) rec[m] = R2{0, 0};
+    if (len > 1) {
+      d_prev = dl[0];
+      d_cur = dl[1];
+      vox = el[0];
+      vox_next = el[1];
+#pragma unroll
+      for (int m = 0; m < LAMBDA_PER_LANE; m++) rec[m] = mrec[(size_t) vox * N_LAMBDA + m];
+    }
 
     for (int k = 1; k < maxlen; k++) {
       const bool active = k < len;
-      Real G = 0;
-      int vox_next = 0;
-      if (active) {
+      // ---- prefetch for step k+1
+      const bool more = k + 1 < len;
+      Real d_next = 0;
+      int vox_next2 = 0;
+      R2 rec_next[LAMBDA_PER_LANE];
+      if (more) {
+        d_next = dl[k + 1];
+        vox_next2 = el[k + 1];
 #ifdef B200RT_CHECKS
-        if (vox < 0 || vox >= g.n_vox || k >= cap || v0 < 0 || v0 >= g.n_vox)
-          printf("march<%d>: bad index ray=%lld k=%d len=%d vox=%d v0=%d cap=%d\n", MODE, ray, k, len, vox, v0, cap);
+        if (vox_next < 0 || vox_next >= g.n_vox) printf("march<%d>: bad voxel %d ray=%lld k=%d len=%d\n", MODE, vox_next, ray, k, len);
 #endif
-        const Real dk = dl[k];
-        vox_next = el[k];
-        const Real s = dk - dprev;                                   // boundaries.hpp:366,376
-        dprev = dk;
-        const Real dts = em.dtau_species[vox];
-        const Real dta = em.dtau_absorber[vox];
-        if (MODE == 1) { tau_sp += dts * s; tau_abs += dta * s; }
-        const Real *ph = em.phi + (size_t) vox * N_LAMBDA + sub;
+#pragma unroll
+        for (int m = 0; m < LAMBDA_PER_LANE; m++) rec_next[m] = mrec[(size_t) vox_next * N_LAMBDA + m];
+      } else {
+#pragma unroll
+        for (int m = 0; m < LAMBDA_PER_LANE; m++) rec_next[m] = R2{0, 0};
+      }
+      // ---- step k: voxel `vox`, path length s
+      Real G = 0;
+      if (active) {
+        const Real s = d_cur - d_prev;                                   // boundaries.hpp:366,376
+        if (MODE == 1) { tau_sp += em.dtau_species[vox] * s; tau_abs += em.dtau_absorber[vox] * s; }
 #pragma unroll
         for (int m = 0; m < LAMBDA_PER_LANE; m++) {
-          const Real lineshape = ph[LANES_PER_RAY * m];
-          const Real tau = (dta + dts * lineshape) * s;
-          const Real tp = rexp<Real>(-tau);
-          const Real Pf = P[m] * tp;
+          const Real tau = rec[m].x * s;
+          const Real tp = exp_neg<Real>(-tau);
           if (MODE == 0) {
-            Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : (Real(1.0) - tp) / tau;
-            c *= (w[m] * lineshape * P[m] * dts * s);
-            G += c * renorm * ls0[m];
+            const Real f = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) * tau : (Real(1.0) - tp);
+            G += (rec[m].y * P[m]) * f * nl0[m];
           }
-          P[m] = Pf;
+          P[m] *= tp;
         }
       }
       if (MODE == 0) {
         G += __shfl_xor_sync(0xffffffffu, G, 1);
         G += __shfl_xor_sync(0xffffffffu, G, 2);
-        if (active && sub == 0) atomicAdd(&K[(size_t) v0 * g.n_vox + vox], (double) (domega * G));
+        if (active && sub == 0) atomicAdd(&Krow[vox], (double) (domega * G));
       }
-      vox = vox_next;
+      d_prev = d_cur; d_cur = d_next;
+      vox = vox_next; vox_next = vox_next2;
+#pragma unroll
+      for (int m = 0; m < LAMBDA_PER_LANE; m++) rec[m] = rec_next[m];
     }
     if (MODE == 0) {
       if (sub == 0 && len > 1) my_steps += (unsigned long long) (len - 1);
@@ -157,7 +215,7 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
       // holstein_T_final = sum_i w_i * norm(T0) * phi0_i * P_i   (singlet_CFR.hpp:183-186)
       Real T = 0;
 #pragma unroll
-      for (int m = 0; m < LAMBDA_PER_LANE; m++) T += w[m] * renorm * ls0[m] * P[m];
+      for (int m = 0; m < LAMBDA_PER_LANE; m++) T += w[m] * nl0[m] * P[m];
       T += __shfl_xor_sync(0xffffffffu, T, 1);
       T += __shfl_xor_sync(0xffffffffu, T, 2);
       if (valid && sub == 0) {
@@ -177,9 +235,11 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
 } // namespace
 
 template <class Real>
-cudaError_t launch_phi_table(const Real *T_ratio, int n_vox, Real *phi, cudaStream_t s) {
+cudaError_t launch_phi_table(const Real *T_ratio, const Real *dts, const Real *dta, int n_vox, Real *phi, Real *mrec,
+                             cudaStream_t s) {
   const int n = n_vox * N_LAMBDA;
   phi_table_kernel<Real><<<(n + 255) / 256, 256, 0, s>>>(T_ratio, n_vox, phi);
+  march_table_kernel<Real><<<(n + 255) / 256, 256, 0, s>>>(phi, dts, dta, n_vox, mrec);
   return cudaGetLastError();
 }
 
@@ -217,8 +277,8 @@ cudaError_t launch_single_scattering(const GridView<Real> &g, const EmissionView
   return cudaGetLastError();
 }
 
-template cudaError_t launch_phi_table<double>(const double *, int, double *, cudaStream_t);
-template cudaError_t launch_phi_table<float>(const float *, int, float *, cudaStream_t);
+template cudaError_t launch_phi_table<double>(const double *, const double *, const double *, int, double *, double *, cudaStream_t);
+template cudaError_t launch_phi_table<float>(const float *, const float *, const float *, int, float *, float *, cudaStream_t);
 template cudaError_t launch_influence<double>(const GridView<double> &, const EmissionView<double> &, int, int,
                                               ListView<double>, double *, int *, unsigned long long *, cudaStream_t);
 template cudaError_t launch_influence<float>(const GridView<float> &, const EmissionView<float> &, int, int,

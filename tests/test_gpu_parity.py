@@ -20,7 +20,12 @@ def compare_models(synth, O, G, scn, prec, los_sets):
     assert ns_o == ns_g
     for e in range(scn.n_em):
         Ko, Kg = O.K(e), G.K(e)
-        assert np.array_equal(Ko != 0, Kg != 0)
+        # zero pattern: entries at the underflow edge of Real (< 1e-290 / 1e-30, against row sums of order 1)
+        # depend on the order in which the products of a step are formed (the device uses per-voxel
+        # kappa / wratio tables, influence.cu) and are compared as zeros
+        floor = 1e-290 if prec == "f64" else 1e-30
+        assert np.array_equal(np.abs(Ko) > floor, np.abs(Kg) > floor)
+        Ko, Kg = np.where(np.abs(Ko) > floor, Ko, 0.0), np.where(np.abs(Kg) > floor, Kg, 0.0)
         assert rel_err(Ko, Kg) < tol
         vo, vg = O.vectors(e), G.vectors(e, want_S=False)
         for k in ("S0", "tau_species_ss", "tau_absorber_ss"):

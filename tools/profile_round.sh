@@ -9,7 +9,7 @@ $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain
 tail -c 600 $OUT/plain_$TAG.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
-for K in brightness_kernel march_kernel traverse_kernel update_kernel; do
+for K in ${KERNELS:-brightness_kernel march_kernel traverse_kernel update_kernel}; do
   ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -f -o $OUT/prof_${K}_$TAG $CMD > $OUT/ncu_${K}_$TAG.log 2>&1
   echo "$K rc=$?"
 done
