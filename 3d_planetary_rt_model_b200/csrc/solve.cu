@@ -5,31 +5,33 @@
 // reference GPU path's cuSOLVER Sgetrf/Sgetrs + 2x cublasSgeam + prepare kernel
 // (emission_voxels.hpp:307-478, singlet_CFR.hpp:641-668).  Always FP64.
 //
-// Algorithm: right-looking blocked LU of the row-major matrix A = I - w K, two-level blocking
-// (64-wide panels inside 128-wide outer blocks).  Every row of K is a set of scattering
-// probabilities (entries >= 0, row sum < 1), so A is strictly diagonally dominant by rows; for
-// such matrices Gaussian elimination needs no row exchanges (growth factor <= 2), and partial
-// pivoting applied to A^T would provably pick the diagonal every time.  The dominance margin is
-// checked on the device while A is formed and the call fails with B200RT_ERR_NOT_DOMINANT if it
-// does not hold; the residual of the returned solution is computed in FP64 and reported.
+// Algorithm: right-looking BLOCK LU (block size 128) of the row-major matrix A = I - w K with
+// explicitly inverted diagonal blocks:
+//     A = [ I    0 ] [ A11  A12 ]        L21 = A21 * A11^-1,   S = A22 - L21 * A12,
+//         [ L21  I ] [ 0    S   ]
+// Every row of K is a set of scattering probabilities (entries >= 0, row sum < 1), so A is strictly
+// diagonally dominant by rows, and so is every Schur complement S: no row exchanges are needed
+// (partial pivoting would pick the diagonal every time) and the diagonal blocks are safely
+// invertible by Gauss-Jordan without pivoting.  The dominance margin is checked on the device
+// while A is formed and the call fails with B200RT_ERR_NOT_DOMINANT if it does not hold; the
+// residual of the returned solution is computed in FP64 and reported.
 //
-// Per outer block K (panels k = 2K, 2K+1), the "chain":
-//   diag_kernel(k)   : LU of the 64x64 diagonal block in shared memory + explicit inverses of its
-//                      two triangular factors;
-//   panel_kernel(k)  : L21 = A21 * U11^-1,  U12 = L11^-1 * A12,  y_k = L11^-1 b_k  (64x64x64 DMMA products);
-//   rhs_kernel(k)    : b2 -= L21 y_k;
-//   strip_kernel(2K) : the 64-wide column / row strips next to panel 2K get A -= L21 U12 so that
-//                      panel 2K+1 can be factored;
-// then update_kernel : A22 -= [L21(2K) L21(2K+1)] * [U12(2K); U12(2K+1)]  -- 128x128 tiles, k = 128,
-//                      4-stage cp.async pipeline, accumulators initialised from the C tile (one
-//                      read and one write of A22 per outer block).
-// Look-ahead: the update of outer block K is split into the L-shaped part next to the diagonal
-// (what chain K+1 needs) and the rest; chain K+1 runs on a second stream concurrently with the rest.
+// Per block column KB, the "chain" (critical path, on a high-priority stream):
+//   gj128_kernel   : in-register Gauss-Jordan inverse of the 128x128 diagonal block (one CTA, each
+//                    thread owns an 8x8 tile, pivot row / column broadcast through shared memory);
+//   gemm128<PANEL> : L21 = A21 * A11^-1 (128x128 tiles, DMMA);
+//   rhs128_kernel  : b2 -= L21 b1;
+// then gemm128<UPDATE>: A22 -= L21 * A12 -- 128x128 tiles, k = 128, 4-stage cp.async pipeline,
+//                    accumulators initialised from the C tile (one read and one write of A22 per
+//                    block column).
+// Look-ahead: the update of block column KB is split into the L-shaped part next to the diagonal
+// (what chain KB+1 needs) and the rest; chain KB+1 runs concurrently with the rest.
 // All products use mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4: tcgen05 has no FP64 kind, so
-// this is the FP64 tensor-core path on sm_100a).  Back substitution walks the block
-// columns from the right with the stored U_kk^-1.
+// this is the FP64 tensor-core path on sm_100a).  Back substitution walks the block columns from
+// the right:  x_K = A_KK^-1 y_K ;  y_I -= A_IK x_K  (I < K).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include "common.hpp"
 
@@ -37,7 +39,6 @@ namespace b200rt {
 
 namespace {
 
-constexpr int NB = 64;
 
 __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -79,220 +80,94 @@ __global__ void prepare_kernel(const double *__restrict__ K, int n, int np, doub
   }
 }
 
-// ---- (1) diagonal block: LU without exchanges + inverses of L (unit lower) and U.
-// Thread i owns row i in REGISTERS (the j loops are fully unrolled so every register index is
-// static); pivot rows are broadcast through shared memory, one barrier per step.
-//   pass 1 (threads 0..63)   : right-looking elimination  A = L U, packed into shared memory;
-//   pass 2 (threads 0..63)   : X = L^-1, rows from the top down      } concurrently, each pair of
-//   pass 3 (threads 64..127) : Y = U^-1, rows from the bottom up     } warps on its own named barrier
-constexpr int DS = NB + 1;   // row stride of the shared arrays (column reads are conflict free)
-__device__ __forceinline__ void bar_named(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// ---- (1) diagonal block: in-place Gauss-Jordan inverse, no pivoting.
+// 256 threads = 16 x 16, thread (ty, tx) owns rows ty*8.., columns tx*8.. in registers.  The inner
+// 8 steps are unrolled so that every register index is static.
+__device__ __forceinline__ double rcp_fast(double b) {   // 1/b for normal b, <= 1 ulp
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  return fma(r, e, r);
 }
-__global__ void __launch_bounds__(2 * NB)
-diag_kernel(double *__restrict__ A, int np, int k, double *__restrict__ dinv) {
-  extern __shared__ __align__(16) double dsm[];
-  double *LUs = dsm;                // packed LU: U on and above the diagonal, L below
-  double *Xs = dsm + NB * DS;       // rows of L^-1
-  double *Ys = dsm + 2 * NB * DS;   // rows of U^-1
-  const int tid = threadIdx.x;
-  double *Akk = A + ((size_t) k * NB) * np + (size_t) k * NB;
-  double a[NB];
-  if (tid < NB) {
-    const double2 *row = reinterpret_cast<const double2 *>(Akk + (size_t) tid * np);
-#pragma unroll
-    for (int c = 0; c < NB / 2; c++) {
-      const double2 v = row[c];
-      a[2 * c] = v.x;
-      a[2 * c + 1] = v.y;
-    }
-    // ---- pass 1
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-      if (tid == j) {
-#pragma unroll
-        for (int c = j; c < NB; c++) LUs[j * DS + c] = a[c];
-      }
-      bar_named(1, NB);
-      if (tid > j) {
-        const double l = a[j] / LUs[j * DS + j];
-        LUs[tid * DS + j] = l;
-#pragma unroll
-        for (int c = j + 1; c < NB; c++) a[c] = fma(-l, LUs[j * DS + c], a[c]);
-      }
-    }
-  }
-  __syncthreads();
-  double *Li = dinv + (size_t) k * 2 * NB * NB, *Ui = Li + NB * NB;
-#pragma unroll
-  for (int c = 0; c < NB; c++) a[c] = 0.0;
-  if (tid < NB) {
-    // ---- pass 2: x = row tid of L^-1 (entries c < tid; the diagonal is 1)
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-      if (tid == j) {
-#pragma unroll
-        for (int c = 0; c < j; c++) Xs[j * DS + c] = a[c];
-        Xs[j * DS + j] = 1.0;
-      }
-      bar_named(1, NB);
-      if (tid > j) {
-        const double l = LUs[tid * DS + j];
-#pragma unroll
-        for (int c = 0; c <= j; c++) a[c] = fma(-l, Xs[j * DS + c], a[c]);
-      }
-    }
-  } else {
-    // ---- pass 3: y = row t of U^-1 (entries c >= t), rows from the bottom up
-    const int t = tid - NB;
-#pragma unroll
-    for (int j = NB - 1; j >= 0; j--) {
-      if (t == j) {
-        const double inv = 1.0 / LUs[j * DS + j];
-        Ys[j * DS + j] = inv;            // y[j] = 1 at its turn
-#pragma unroll
-        for (int c = j + 1; c < NB; c++) Ys[j * DS + c] = a[c] * inv;
-      }
-      bar_named(2, NB);
-      if (t < j) {
-        const double u = LUs[t * DS + j];
-#pragma unroll
-        for (int c = j; c < NB; c++) a[c] = fma(-u, Ys[j * DS + c], a[c]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int e = tid; e < NB * NB; e += 2 * NB) {
-    const int r = e / NB, c = e % NB;
-    Akk[(size_t) r * np + c] = LUs[r * DS + c];
-    Li[e] = (c <= r) ? Xs[r * DS + c] : 0.0;
-    Ui[e] = (c >= r) ? Ys[r * DS + c] : 0.0;
-  }
-}
-
-// 64x64x64 product on the tensor pipe: out = P * Q, both staged in shared memory
-// (P row stride SP, Q row stride SQ chosen so the fragment loads are conflict free).
-constexpr int SP = NB + 4;   // 68: (row*68 + col) mod 16 distinct for row,col < 4
-constexpr int SQ = NB + 4;
-__device__ __forceinline__ void tile_product_64(const double *Ps, const double *Qs, double (&acc)[4][4][2], int warp,
-                                                int lane) {
-  // 4 warps: warp tile 32x32 = 4 (m) x 4 (n) DMMA tiles
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
-  const int g = lane >> 2, tq = lane & 3;
-#pragma unroll
-  for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-#pragma unroll 4
-  for (int k0 = 0; k0 < NB; k0 += 4) {
-    double af[4], bf[4];
-#pragma unroll
-    for (int mt = 0; mt < 4; mt++) af[mt] = Ps[(wm + 8 * mt + g) * SP + k0 + tq];
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) bf[nt] = Qs[(k0 + tq) * SQ + wn + 8 * nt + g];
-#pragma unroll
-    for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-      for (int nt = 0; nt < 4; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-  }
-}
-
-// ---- (2) panel: blockIdx.x < nrest : L21 tile (rows below) = A * Uinv
-//                 else               : U12 tile (cols right)  = Linv * A ; last block: y_k = Linv b_k
-__global__ void __launch_bounds__(128)
-panel_kernel(double *__restrict__ A, int np, int k, const double *__restrict__ dinv, double *__restrict__ b) {
-  extern __shared__ __align__(16) double sm[];
-  double *Ps = sm, *Qs = sm + NB * SP;
-  const int nrest = np / NB - k - 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const double *Li = dinv + (size_t) k * 2 * NB * NB, *Ui = Li + NB * NB;
-  const int bid = blockIdx.x;
-  if (bid == 2 * nrest) {   // y_k = Linv * b_k
-    double *bk = b + (size_t) k * NB;
-    __shared__ double bs[NB];
-    if (threadIdx.x < NB) bs[threadIdx.x] = bk[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x < NB) {
-      double s = 0;
-      for (int j = 0; j <= (int) threadIdx.x; j++) s += Li[threadIdx.x * NB + j] * bs[j];
-      bk[threadIdx.x] = s;
-    }
-    return;
-  }
-  const bool lower = bid < nrest;
-  const int t = lower ? bid : bid - nrest;
-  double *tile = lower ? A + ((size_t) (k + 1 + t) * NB) * np + (size_t) k * NB
-                       : A + ((size_t) k * NB) * np + (size_t) (k + 1 + t) * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e / NB, c = e % NB;
-    const double tv = tile[(size_t) r * np + c];
-    if (lower) { Ps[r * SP + c] = tv; Qs[r * SQ + c] = Ui[e]; }
-    else { Ps[r * SP + c] = Li[e]; Qs[r * SQ + c] = tv; }
-  }
-  __syncthreads();
-  double acc[4][4][2];
-  tile_product_64(Ps, Qs, acc, warp, lane);
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32, g = lane >> 2, tq = lane & 3;
-#pragma unroll
-  for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-      double *o = tile + (size_t) (wm + 8 * mt + g) * np + wn + 8 * nt + 2 * tq;
-      *reinterpret_cast<double2 *>(o) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-    }
-}
-
-// ---- rhs: b[r] -= L21[r][k-panel] . y_k for every row below panel k (one warp per row)
+constexpr int TB = 128;   // block size of the factorisation
 __global__ void __launch_bounds__(256)
-rhs_kernel(const double *__restrict__ A, int np, int k, double *__restrict__ b) {
-  const int row = (k + 1) * NB + blockIdx.x * 8 + (threadIdx.x >> 5);
+gj128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ dinv) {
+  __shared__ __align__(16) double prow[2][TB], pcol[2][TB];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const double *Akk = A + ((size_t) KB * TB) * np + (size_t) KB * TB;
+  double a[8][8];
+#pragma unroll
+  for (int rr = 0; rr < 8; rr++)
+#pragma unroll
+    for (int c2 = 0; c2 < 4; c2++) {
+      const double2 v = *reinterpret_cast<const double2 *>(Akk + (size_t) (ty * 8 + rr) * np + tx * 8 + 2 * c2);
+      a[rr][2 * c2] = v.x;
+      a[rr][2 * c2 + 1] = v.y;
+    }
+  for (int jb = 0; jb < 16; jb++) {
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+      const int j = jb * 8 + jj, buf = jj & 1;
+      if (ty == jb) {
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) prow[buf][tx * 8 + cc] = a[jj][cc];
+      }
+      if (tx == jb) {
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) pcol[buf][ty * 8 + rr] = a[rr][jj];
+      }
+      __syncthreads();
+      const double p = rcp_fast(prow[buf][j]);
+      double sp[8], f[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; cc++) sp[cc] = prow[buf][tx * 8 + cc] * p;
+#pragma unroll
+      for (int rr = 0; rr < 8; rr++) f[rr] = pcol[buf][ty * 8 + rr];
+#pragma unroll
+      for (int rr = 0; rr < 8; rr++)
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) a[rr][cc] = fma(-f[rr], sp[cc], a[rr][cc]);
+      if (ty == jb) {
+#pragma unroll
+        for (int cc = 0; cc < 8; cc++) a[jj][cc] = sp[cc];
+      }
+      if (tx == jb) {
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) a[rr][jj] = -f[rr] * p;
+        if (ty == jb) a[jj][jj] = p;
+      }
+    }
+  }
+  double *out = dinv + (size_t) KB * TB * TB;
+#pragma unroll
+  for (int rr = 0; rr < 8; rr++)
+#pragma unroll
+    for (int c2 = 0; c2 < 4; c2++)
+      *reinterpret_cast<double2 *>(out + (size_t) (ty * 8 + rr) * TB + tx * 8 + 2 * c2) =
+          make_double2(a[rr][2 * c2], a[rr][2 * c2 + 1]);
+}
+
+// ---- rhs: b[r] -= L21[r][block column KB] . b_KB for every row below (one warp per row)
+__global__ void __launch_bounds__(256)
+rhs128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ b) {
+  const int row = (KB + 1) * TB + blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= np) return;
-  const double *Ar = A + (size_t) row * np + (size_t) k * NB;
-  const double *yk = b + (size_t) k * NB;
-  double s = Ar[lane] * yk[lane] + Ar[lane + 32] * yk[lane + 32];
+  const double *Ar = A + (size_t) row * np + (size_t) KB * TB;
+  const double *yk = b + (size_t) KB * TB;
+  double s = 0;
+#pragma unroll
+  for (int q = 0; q < TB / 32; q++) s += Ar[lane + 32 * q] * yk[lane + 32 * q];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) b[row] -= s;
 }
 
-// ---- strip: after panel k (even), the 64x64 tiles of block column k+1 (rows > k) and of block row
-// k+1 (columns > k+1) get  C -= L21 * U12  so that panel k+1 can be factored
-__global__ void __launch_bounds__(128)
-strip_kernel(double *__restrict__ A, int np, int k) {
-  extern __shared__ __align__(16) double sm[];
-  double *Ps = sm, *Qs = sm + NB * SP;
-  const int nb = np / NB;
-  const int ncol = nb - k - 1;                 // tiles (i, k+1), i = k+1 .. nb-1
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int ti, tj;
-  if ((int) blockIdx.x < ncol) { ti = k + 1 + blockIdx.x; tj = k + 1; }
-  else { ti = k + 1; tj = k + 2 + (blockIdx.x - ncol); }
-  const double *L = A + ((size_t) ti * NB) * np + (size_t) k * NB;    // L21 tile (ti, k)
-  const double *U = A + ((size_t) k * NB) * np + (size_t) tj * NB;    // U12 tile (k, tj)
-  double *Ct = A + ((size_t) ti * NB) * np + (size_t) tj * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e / NB, c = e % NB;
-    Ps[r * SP + c] = L[(size_t) r * np + c];
-    Qs[r * SQ + c] = U[(size_t) r * np + c];
-  }
-  __syncthreads();
-  double acc[4][4][2];
-  tile_product_64(Ps, Qs, acc, warp, lane);
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32, g = lane >> 2, tq = lane & 3;
-#pragma unroll
-  for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-      double2 *o = reinterpret_cast<double2 *>(Ct + (size_t) (wm + 8 * mt + g) * np + wn + 8 * nt + 2 * tq);
-      double2 v = *o;
-      v.x -= acc[mt][nt][0];
-      v.y -= acc[mt][nt][1];
-      *o = v;
-    }
-}
-
-// ---- trailing update of outer block K:  C[128x128 tile] -= L[128x128] * U[128x128]
+// ---- 128x128x128 tile products on the FP64 tensor pipe
 constexpr int TM = 128, TN = 128, TK = 128;
 constexpr int KC = 16;                 // k-chunk per pipeline stage
 constexpr int STAGES = 4;
@@ -307,27 +182,34 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// mode 0: the L-shaped set of tiles next to the diagonal (block column K+1 from the diagonal down,
-//         block row K+1 right of the diagonal) -- what the next chain needs;
-// mode 1: the square (i, j >= K+2).   Tile indices in units of 128.
+// MODE 0: update, the L-shaped set of tiles next to the diagonal (block column KB+1 from the diagonal
+//         down, block row KB+1 right of the diagonal) -- what the next chain needs:  C -= L21 * A12
+// MODE 1: update, the square (i, j >= KB+2)
+// MODE 2: panel,  tile (KB+1+blockIdx.x, KB):  A21 <- A21 * A_KK^-1  (in place)
+template <int MODE>
 __global__ void __launch_bounds__(256)
-update_kernel(double *__restrict__ A, int np, int K, int mode) {
+gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict__ dinv) {
   extern __shared__ __align__(16) double sm[];
   const int nB = np / TM;
   int ti, tj;
-  if (mode == 0) {
-    const int ncol = nB - K - 1;
-    if ((int) blockIdx.x < ncol) { ti = K + 1 + blockIdx.x; tj = K + 1; }
-    else { ti = K + 1; tj = K + 2 + (blockIdx.x - ncol); }
+  if (MODE == 0) {
+    const int ncol = nB - KB - 1;
+    if ((int) blockIdx.x < ncol) { ti = KB + 1 + blockIdx.x; tj = KB + 1; }
+    else { ti = KB + 1; tj = KB + 2 + (blockIdx.x - ncol); }
+  } else if (MODE == 1) {
+    const int m = nB - KB - 2;
+    ti = KB + 2 + blockIdx.x / m;
+    tj = KB + 2 + blockIdx.x % m;
   } else {
-    const int m = nB - K - 2;
-    ti = K + 2 + blockIdx.x / m;
-    tj = K + 2 + blockIdx.x % m;
+    ti = KB + 1 + blockIdx.x;
+    tj = KB;
   }
-  const int row0 = ti * TM, col0 = tj * TN, kc = K * TK;
+  const int row0 = ti * TM, col0 = tj * TN, kc = KB * TK;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double *Lg = A + (size_t) row0 * np + kc;      // [128 rows][128 k]
-  const double *Ug = A + (size_t) kc * np + col0;      // [128 k][128 cols]
+  const double *Lg = A + (size_t) row0 * np + kc;                              // [128 rows][128 k], ld np
+  const double *Ug = (MODE == 2) ? dinv + (size_t) KB * TB * TB : A + (size_t) kc * np + col0;   // [128 k][128 cols]
+  const int ldu = (MODE == 2) ? TB : np;
+  double *Cg = A + (size_t) row0 * np + col0;
 
   auto issue = [&](int chunk) {
     double *As = sm + (chunk % STAGES) * STAGE_DOUBLES;
@@ -341,14 +223,14 @@ update_kernel(double *__restrict__ A, int np, int K, int mode) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {       // B chunk: 16 rows x 128 doubles = 1024 x 16 B
       const int kk = (tid >> 6) + 4 * i, p = tid & 63;
-      cp_async16(Bs + kk * SB + 2 * p, Ug + (size_t) (k0 + kk) * np + 2 * p);
+      cp_async16(Bs + kk * SB + 2 * p, Ug + (size_t) (k0 + kk) * ldu + 2 * p);
     }
   };
   constexpr int NCHUNK = TK / KC;
 #pragma unroll
   for (int c = 0; c < STAGES - 1; c++) { issue(c); cp_async_commit(); }
 
-  // 8 warps: 4 (m) x 2 (n); warp tile 32 x 64 = 4 x 8 DMMA tiles; accumulators start from C
+  // 8 warps: 4 (m) x 2 (n); warp tile 32 x 64 = 4 x 8 DMMA tiles
   const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
   const int g = lane >> 2, tq = lane & 3;
   double acc[4][8][2];
@@ -356,9 +238,12 @@ update_kernel(double *__restrict__ A, int np, int K, int mode) {
   for (int mt = 0; mt < 4; mt++)
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-      const double2 v = *reinterpret_cast<const double2 *>(A + (size_t) (row0 + wm + 8 * mt + g) * np + col0 + wn + 8 * nt + 2 * tq);
-      acc[mt][nt][0] = v.x;
-      acc[mt][nt][1] = v.y;
+      if (MODE == 2) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+      else {   // the accumulators start from C; the A fragments are negated below
+        const double2 v = *reinterpret_cast<const double2 *>(Cg + (size_t) (wm + 8 * mt + g) * np + wn + 8 * nt + 2 * tq);
+        acc[mt][nt][0] = v.x;
+        acc[mt][nt][1] = v.y;
+      }
     }
 
   for (int c = 0; c < NCHUNK; c++) {
@@ -372,7 +257,10 @@ update_kernel(double *__restrict__ A, int np, int K, int mode) {
     for (int k0 = 0; k0 < KC; k0 += 4) {
       double af[4], bf[8];
 #pragma unroll
-      for (int mt = 0; mt < 4; mt++) af[mt] = -As[(wm + 8 * mt + g) * SA + k0 + tq];
+      for (int mt = 0; mt < 4; mt++) {
+        const double v = As[(wm + 8 * mt + g) * SA + k0 + tq];
+        af[mt] = (MODE == 2) ? v : -v;
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) bf[nt] = Bs[(k0 + tq) * SB + wn + 8 * nt + g];
 #pragma unroll
@@ -381,33 +269,61 @@ update_kernel(double *__restrict__ A, int np, int K, int mode) {
         for (int nt = 0; nt < 8; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
     }
   }
+  // MODE 2 writes over its own A operand: every chunk has been consumed by every warp first
+  if (MODE == 2) __syncthreads();
 #pragma unroll
   for (int mt = 0; mt < 4; mt++)
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
-      *reinterpret_cast<double2 *>(A + (size_t) (row0 + wm + 8 * mt + g) * np + col0 + wn + 8 * nt + 2 * tq) =
+      *reinterpret_cast<double2 *>(Cg + (size_t) (wm + 8 * mt + g) * np + wn + 8 * nt + 2 * tq) =
           make_double2(acc[mt][nt][0], acc[mt][nt][1]);
 }
 
-// ---- back substitution, block column k: x_k = Uinv_kk y_k ; y_i -= U_ik x_k for i < k
-__global__ void __launch_bounds__(64)
-backsolve_kernel(const double *__restrict__ A, int np, int k, const double *__restrict__ dinv, double *__restrict__ b,
-                 double *__restrict__ x) {
-  __shared__ double xk[NB], yk[NB];
-  const double *Ui = dinv + (size_t) k * 2 * NB * NB + NB * NB;
-  const int tid = threadIdx.x;
-  yk[tid] = b[(size_t) k * NB + tid];
+// ---- back substitution, block column KB:  x_K = A_KK^-1 y_K ;  y_I -= A_IK x_K for I < K.
+// grid = KB+1 blocks of 512 threads (16 warps x 8 rows, coalesced row reads, all loads of a warp in
+// flight together); every block forms x_K itself, block KB stores it, block I < KB updates its rows of y.
+__global__ void __launch_bounds__(512)
+backsolve128_kernel(const double *__restrict__ A, int np, int KB, const double *__restrict__ dinv,
+                    double *__restrict__ b, double *__restrict__ x) {
+  __shared__ double xk[TB], yk[TB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double *Ai = dinv + (size_t) KB * TB * TB;
+  if (tid < TB) yk[tid] = b[(size_t) KB * TB + tid];
   __syncthreads();
-  double s = 0;
-  for (int j = tid; j < NB; j++) s += Ui[tid * NB + j] * yk[j];
-  xk[tid] = s;
+  double v[TB / 32], m[8][TB / 32];
+#pragma unroll
+  for (int q = 0; q < TB / 32; q++) v[q] = yk[lane + 32 * q];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int q = 0; q < TB / 32; q++) m[i][q] = Ai[(size_t) (warp * 8 + i) * TB + lane + 32 * q];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < TB / 32; q++) s += m[i][q] * v[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) xk[warp * 8 + i] = s;
+  }
   __syncthreads();
-  const int i = blockIdx.x;   // block row i < k updates, block k writes the solution
-  if (i == k) { x[(size_t) k * NB + tid] = xk[tid]; return; }
-  const double *Uik = A + ((size_t) i * NB + tid) * np + (size_t) k * NB;
-  double u = 0;
-  for (int j = 0; j < NB; j++) u += Uik[j] * xk[j];
-  b[(size_t) i * NB + tid] -= u;
+  const int I = blockIdx.x;
+  if (I == KB) { if (tid < TB) x[(size_t) KB * TB + tid] = xk[tid]; return; }
+#pragma unroll
+  for (int q = 0; q < TB / 32; q++) v[q] = xk[lane + 32 * q];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int q = 0; q < TB / 32; q++) m[i][q] = A[((size_t) I * TB + warp * 8 + i) * np + (size_t) KB * TB + lane + 32 * q];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < TB / 32; q++) s += m[i][q] * v[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) b[(size_t) I * TB + warp * 8 + i] -= s;
+  }
 }
 
 // ---- residual of the ORIGINAL system: |S0 - (S - w K S)|, one warp per row
@@ -443,12 +359,12 @@ template cudaError_t launch_convert<float>(const double *, float *, long long, c
 
 int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const double *S0, double *S,
                 SolveResult *res) {
-  const int np = ((n + 127) / 128) * 128;
-  const int nblk = np / NB;
+  const int np = ((n + TB - 1) / TB) * TB;
+  const int nK = np / TB;
   cudaStream_t st = c->stream;
   // workspace: A[np*np] | b[np] | x[np] | margin[np] | rabs[np]
   B200RT_CUDA(c, c->lu.ensure(((size_t) np * np + 4 * (size_t) np) * sizeof(double)));
-  B200RT_CUDA(c, c->lu_dinv.ensure((size_t) nblk * 2 * NB * NB * sizeof(double)));
+  B200RT_CUDA(c, c->lu_dinv.ensure((size_t) nK * TB * TB * sizeof(double)));
   double *A = c->lu.as<double>();
   double *b = A + (size_t) np * np, *x = b + np, *margin = x + np, *rabs = margin + np;
   double *dinv = c->lu_dinv.as<double>();
@@ -468,66 +384,80 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
                 "I - w*K is not strictly row diagonally dominant (min margin " + std::to_string(min_margin) +
                     "): the influence matrix rows are not scattering probabilities");
 
-  const size_t panel_smem = (size_t) (NB * SP + NB * SQ) * sizeof(double);
-  const size_t diag_smem = (size_t) 3 * NB * DS * sizeof(double);
-  B200RT_CUDA(c, cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) diag_smem));
-  const size_t update_smem = (size_t) STAGES * STAGE_DOUBLES * sizeof(double);
-  B200RT_CUDA(c, cudaFuncSetAttribute(panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) panel_smem));
-  B200RT_CUDA(c, cudaFuncSetAttribute(strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) panel_smem));
-  B200RT_CUDA(c, cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) update_smem));
+  const size_t gemm_smem = (size_t) STAGES * STAGE_DOUBLES * sizeof(double);
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
 
   // second stream + events for the look-ahead
-  if (!c->stream2) B200RT_CUDA(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  const int nK = np / TM;
+  if (!c->stream2) {   // the chain is the critical path: give its stream the highest priority
+    int lo = 0, hi = 0;
+    B200RT_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B200RT_CUDA(c, cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
+  }
   while ((int) c->lu_events.size() < 2 * nK + 1) {
     cudaEvent_t ev;
     B200RT_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     c->lu_events.push_back(ev);
   }
   cudaStream_t sB = c->stream2;
-  auto chain = [&](int KB, cudaStream_t s) {       // factor panels 2KB and 2KB+1
-    for (int h = 0; h < 2; h++) {
-      const int k = 2 * KB + h;
-      const int nrest = nblk - k - 1;
-      diag_kernel<<<1, 2 * NB, diag_smem, s>>>(A, np, k, dinv);
-      panel_kernel<<<2 * nrest + 1, 128, panel_smem, s>>>(A, np, k, dinv, b);
+  // B200RT_SOLVE_TRACE=1: timestamp every chain / update of the factorisation (development aid)
+  static const bool trace = getenv("B200RT_SOLVE_TRACE") != nullptr;
+  struct Mark { const char *what; int KB; cudaEvent_t ev; };
+  std::vector<Mark> marks;
+  auto mark = [&](const char *what, int KB, cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, s);
+    marks.push_back({what, KB, ev});
+  };
+  auto chain = [&](int KB, cudaStream_t s) {       // invert the diagonal block, form L21, forward-substitute
+    const int m1 = nK - KB - 1;
+    gj128_kernel<<<1, 256, 0, s>>>(A, np, KB, dinv);
+    launches++;
+    if (m1 > 0) {
+      gemm128_kernel<2><<<m1, 256, gemm_smem, s>>>(A, np, KB, dinv);
+      rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, s>>>(A, np, KB, b);
       launches += 2;
-      if (nrest > 0) {
-        rhs_kernel<<<(nrest * NB + 7) / 8, 256, 0, s>>>(A, np, k, b);
-        launches++;
-      }
-      if (h == 0) {
-        strip_kernel<<<2 * nrest - 1, 128, panel_smem, s>>>(A, np, k);   // nrest >= 1 here (np % 128 == 0)
-        launches++;
-      }
     }
   };
   cudaEvent_t ev_start = c->lu_events[2 * nK];
   B200RT_CUDA(c, cudaEventRecord(ev_start, st));
   B200RT_CUDA(c, cudaStreamWaitEvent(sB, ev_start, 0));
+  mark("start", 0, st);
+  mark("chain_begin", 0, sB);
   chain(0, sB);
+  mark("chain_end", 0, sB);
   B200RT_CUDA(c, cudaEventRecord(c->lu_events[0], sB));            // evP[0]
   for (int KB = 0; KB < nK; KB++) {
-    B200RT_CUDA(c, cudaStreamWaitEvent(st, c->lu_events[2 * KB], 0)); // panels of KB factored
-    const int m1 = nK - KB - 1;                                       // outer blocks after K
+    B200RT_CUDA(c, cudaStreamWaitEvent(st, c->lu_events[2 * KB], 0)); // block column KB factored
+    const int m1 = nK - KB - 1;                                       // block columns after KB
     if (m1 > 0) {
-      update_kernel<<<2 * m1 - 1, 256, update_smem, st>>>(A, np, KB, 0);
+      mark("ui_begin", KB, st);
+      gemm128_kernel<0><<<2 * m1 - 1, 256, gemm_smem, st>>>(A, np, KB, dinv);
+      mark("ui_end", KB, st);
       launches++;
       B200RT_CUDA(c, cudaEventRecord(c->lu_events[2 * KB + 1], st));  // evU[KB]
       B200RT_CUDA(c, cudaStreamWaitEvent(sB, c->lu_events[2 * KB + 1], 0));
+      mark("chain_begin", KB + 1, sB);
       chain(KB + 1, sB);
+      mark("chain_end", KB + 1, sB);
       B200RT_CUDA(c, cudaEventRecord(c->lu_events[2 * KB + 2], sB));  // evP[KB+1]
       const int m2 = m1 - 1;
       if (m2 > 0) {
-        update_kernel<<<m2 * m2, 256, update_smem, st>>>(A, np, KB, 1);
+        gemm128_kernel<1><<<m2 * m2, 256, gemm_smem, st>>>(A, np, KB, dinv);
+        mark("uii_end", KB, st);
         launches++;
       }
     }
   }
-  for (int k = nblk - 1; k >= 0; k--) {
-    backsolve_kernel<<<k + 1, NB, 0, st>>>(A, np, k, dinv, b, x);
+  mark("factor_end", 0, st);
+  for (int KB = nK - 1; KB >= 0; KB--) {
+    backsolve128_kernel<<<KB + 1, 512, 0, st>>>(A, np, KB, dinv, b, x);
     launches++;
   }
+  mark("backsolve_end", 0, st);
   B200RT_CUDA(c, cudaGetLastError());
   B200RT_CUDA(c, cudaMemcpyAsync(S, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   residual_kernel<<<(n + 7) / 8, 256, 0, st>>>(K, n, branching, S0, S, rabs);
@@ -537,6 +467,15 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   B200RT_CUDA(c, cudaMemcpyAsync(hr.data(), rabs, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200RT_CUDA(c, cudaMemcpyAsync(hs0.data(), S0, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200RT_CUDA(c, cudaStreamSynchronize(st));
+  if (trace && !marks.empty()) {
+    cudaStreamSynchronize(sB);
+    for (auto &m : marks) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+      fprintf(stderr, "solve-trace %-12s K=%3d t=%9.3f ms\n", m.what, m.KB, ms);
+    }
+    for (auto &m : marks) cudaEventDestroy(m.ev);
+  }
   double rmax = 0, smax = 0;
   for (int i = 0; i < n; i++) { rmax = std::max(rmax, hr[i]); smax = std::max(smax, std::fabs(hs0[i])); }
   if (res) { res->residual = rmax / (smax > 0 ? smax : 1.0); res->launches = launches; }
