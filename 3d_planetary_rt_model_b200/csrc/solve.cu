@@ -153,11 +153,11 @@ gj128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ 
 
 // ---- rhs: b[r] -= L21[r][block column KB] . b_KB for every row below (one warp per row)
 __global__ void __launch_bounds__(256)
-rhs128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ b) {
+rhs128_kernel(const double *__restrict__ Lbuf, int np, int KB, double *__restrict__ b) {
   const int row = (KB + 1) * TB + blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= np) return;
-  const double *Ar = A + (size_t) row * np + (size_t) KB * TB;
+  const double *Ar = Lbuf + (size_t) row * TB;
   const double *yk = b + (size_t) KB * TB;
   double s = 0;
 #pragma unroll
@@ -172,8 +172,6 @@ constexpr int TM = 128, TN = 128, TK = 128;
 constexpr int KC = 16;                 // k-chunk per pipeline stage
 constexpr int STAGES = 4;
 constexpr int SA = KC + 4;             // 20: (row*20 + col) mod 16 distinct for row, col < 4  (conflict-free LDS.64)
-constexpr int SB = TN + 4;             // 132: (k*132 + n) mod 16 distinct for k, n < 4
-constexpr int STAGE_DOUBLES = TM * SA + KC * SB;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
@@ -185,10 +183,16 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // MODE 0: update, the L-shaped set of tiles next to the diagonal (block column KB+1 from the diagonal
 //         down, block row KB+1 right of the diagonal) -- what the next chain needs:  C -= L21 * A12
 // MODE 1: update, the square (i, j >= KB+2)
-// MODE 2: panel,  tile (KB+1+blockIdx.x, KB):  A21 <- A21 * A_KK^-1  (in place)
-template <int MODE>
+// MODE 2: panel,  tile (KB+1+blockIdx.x, KB):  L21 = A21 * A_KK^-1 -> Lbuf[row][0..127] (the L panels live in
+//         a double-buffered side array: the updates of block column KB read one half while chain KB+1 fills the other)
+// NT = DMMA n-tiles per warp: 8 -> 128x128 output tile per CTA (bulk update), 4 -> 128x64 (the two
+// kernels on the critical path run as twice as many CTAs with half the latency; blockIdx.y picks the half).
+template <int MODE, int NT>
 __global__ void __launch_bounds__(256)
-gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict__ dinv) {
+gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict__ dinv, double *__restrict__ Lbuf) {
+  constexpr int TNc = 16 * NT;           // output tile width of this CTA
+  constexpr int SBc = TNc + 4;           // 132 / 68: (k*SB + n) mod 16 distinct for k, n < 4
+  constexpr int STAGE = TM * SA + KC * SBc;
   extern __shared__ __align__(16) double sm[];
   const int nB = np / TM;
   int ti, tj;
@@ -204,40 +208,43 @@ gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict_
     ti = KB + 1 + blockIdx.x;
     tj = KB;
   }
-  const int row0 = ti * TM, col0 = tj * TN, kc = KB * TK;
+  const int row0 = ti * TM, col0 = tj * TN + blockIdx.y * TNc, kc = KB * TK;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double *Lg = A + (size_t) row0 * np + kc;                              // [128 rows][128 k], ld np
-  const double *Ug = (MODE == 2) ? dinv + (size_t) KB * TB * TB : A + (size_t) kc * np + col0;   // [128 k][128 cols]
+  // L operand [128 rows][128 k]: the panel reads A21 in place, the updates read the panel's output
+  const double *Lg = (MODE == 2) ? A + (size_t) row0 * np + kc : Lbuf + (size_t) row0 * TB;
+  const int ldl = (MODE == 2) ? np : TB;
+  const double *Ug = (MODE == 2) ? dinv + (size_t) KB * TB * TB + blockIdx.y * TNc : A + (size_t) kc * np + col0;
   const int ldu = (MODE == 2) ? TB : np;
   double *Cg = A + (size_t) row0 * np + col0;
 
   auto issue = [&](int chunk) {
-    double *As = sm + (chunk % STAGES) * STAGE_DOUBLES;
+    double *As = sm + (chunk % STAGES) * STAGE;
     double *Bs = As + TM * SA;
     const int k0 = chunk * KC;
 #pragma unroll
     for (int i = 0; i < 4; i++) {       // A chunk: 128 rows x 16 doubles = 1024 x 16 B
       const int r = (tid >> 3) + 32 * i, p = tid & 7;
-      cp_async16(As + r * SA + 2 * p, Lg + (size_t) r * np + k0 + 2 * p);
+      cp_async16(As + r * SA + 2 * p, Lg + (size_t) r * ldl + k0 + 2 * p);
     }
+    constexpr int PPR = TNc / 2;        // 16-byte pieces per B row
 #pragma unroll
-    for (int i = 0; i < 4; i++) {       // B chunk: 16 rows x 128 doubles = 1024 x 16 B
-      const int kk = (tid >> 6) + 4 * i, p = tid & 63;
-      cp_async16(Bs + kk * SB + 2 * p, Ug + (size_t) (k0 + kk) * ldu + 2 * p);
+    for (int i = 0; i < KC * PPR / 256; i++) {
+      const int e = tid + 256 * i, kk = e / PPR, p = e % PPR;
+      cp_async16(Bs + kk * SBc + 2 * p, Ug + (size_t) (k0 + kk) * ldu + 2 * p);
     }
   };
   constexpr int NCHUNK = TK / KC;
 #pragma unroll
   for (int c = 0; c < STAGES - 1; c++) { issue(c); cp_async_commit(); }
 
-  // 8 warps: 4 (m) x 2 (n); warp tile 32 x 64 = 4 x 8 DMMA tiles
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
+  // 8 warps: 4 (m) x 2 (n); warp tile 32 x (8 NT) = 4 x NT DMMA tiles
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * (8 * NT);
   const int g = lane >> 2, tq = lane & 3;
-  double acc[4][8][2];
+  double acc[4][NT][2];
 #pragma unroll
   for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
+    for (int nt = 0; nt < NT; nt++) {
       if (MODE == 2) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
       else {   // the accumulators start from C; the A fragments are negated below
         const double2 v = *reinterpret_cast<const double2 *>(Cg + (size_t) (wm + 8 * mt + g) * np + wn + 8 * nt + 2 * tq);
@@ -251,31 +258,32 @@ gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict_
     __syncthreads();
     if (c + STAGES - 1 < NCHUNK) issue(c + STAGES - 1);
     cp_async_commit();
-    const double *As = sm + (c % STAGES) * STAGE_DOUBLES;
+    const double *As = sm + (c % STAGES) * STAGE;
     const double *Bs = As + TM * SA;
 #pragma unroll
     for (int k0 = 0; k0 < KC; k0 += 4) {
-      double af[4], bf[8];
+      double af[4], bf[NT];
 #pragma unroll
       for (int mt = 0; mt < 4; mt++) {
         const double v = As[(wm + 8 * mt + g) * SA + k0 + tq];
         af[mt] = (MODE == 2) ? v : -v;
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; nt++) bf[nt] = Bs[(k0 + tq) * SB + wn + 8 * nt + g];
+      for (int nt = 0; nt < NT; nt++) bf[nt] = Bs[(k0 + tq) * SBc + wn + 8 * nt + g];
 #pragma unroll
       for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        for (int nt = 0; nt < NT; nt++) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
     }
   }
-  // MODE 2 writes over its own A operand: every chunk has been consumed by every warp first
-  if (MODE == 2) __syncthreads();
+  // the panel does not write in place: the CTAs of the two column halves both read the whole A21 tile
+  double *Cout = (MODE == 2) ? Lbuf + (size_t) row0 * TB + blockIdx.y * TNc : Cg;
+  const int ldc = (MODE == 2) ? TB : np;
 #pragma unroll
   for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++)
-      *reinterpret_cast<double2 *>(Cg + (size_t) (wm + 8 * mt + g) * np + wn + 8 * nt + 2 * tq) =
+    for (int nt = 0; nt < NT; nt++)
+      *reinterpret_cast<double2 *>(Cout + (size_t) (wm + 8 * mt + g) * ldc + wn + 8 * nt + 2 * tq) =
           make_double2(acc[mt][nt][0], acc[mt][nt][1]);
 }
 
@@ -364,10 +372,13 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   cudaStream_t st = c->stream;
   // workspace: A[np*np] | b[np] | x[np] | margin[np] | rabs[np]
   B200RT_CUDA(c, c->lu.ensure(((size_t) np * np + 4 * (size_t) np) * sizeof(double)));
-  B200RT_CUDA(c, c->lu_dinv.ensure((size_t) nK * TB * TB * sizeof(double)));
+  // block inverses [nK][128][128] | L panels [2][np][128]
+  B200RT_CUDA(c, c->lu_dinv.ensure(((size_t) nK * TB * TB + 2 * (size_t) np * TB) * sizeof(double)));
   double *A = c->lu.as<double>();
   double *b = A + (size_t) np * np, *x = b + np, *margin = x + np, *rabs = margin + np;
   double *dinv = c->lu_dinv.as<double>();
+  double *Lbuf0 = dinv + (size_t) nK * TB * TB;
+  auto Lbuf = [&](int KB) { return Lbuf0 + (size_t) (KB & 1) * np * TB; };
   int launches = 0;
 
   prepare_kernel<<<np, 256, 0, st>>>(K, n, np, branching, S0, A, b, margin);
@@ -384,10 +395,11 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
                 "I - w*K is not strictly row diagonally dominant (min margin " + std::to_string(min_margin) +
                     "): the influence matrix rows are not scattering probabilities");
 
-  const size_t gemm_smem = (size_t) STAGES * STAGE_DOUBLES * sizeof(double);
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
+  const size_t gemm_smem = (size_t) STAGES * (TM * SA + KC * (TN + 4)) * sizeof(double);        // 128x128 tiles
+  const size_t gemm_smem_h = (size_t) STAGES * (TM * SA + KC * (TN / 2 + 4)) * sizeof(double);  // 128x64 tiles
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
 
   // second stream + events for the look-ahead
   if (!c->stream2) {   // the chain is the critical path: give its stream the highest priority
@@ -417,8 +429,8 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     gj128_kernel<<<1, 256, 0, s>>>(A, np, KB, dinv);
     launches++;
     if (m1 > 0) {
-      gemm128_kernel<2><<<m1, 256, gemm_smem, s>>>(A, np, KB, dinv);
-      rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, s>>>(A, np, KB, b);
+      gemm128_kernel<2, 4><<<dim3(m1, 2), 256, gemm_smem_h, s>>>(A, np, KB, dinv, Lbuf(KB));
+      rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, s>>>(Lbuf(KB), np, KB, b);
       launches += 2;
     }
   };
@@ -435,7 +447,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     const int m1 = nK - KB - 1;                                       // block columns after KB
     if (m1 > 0) {
       mark("ui_begin", KB, st);
-      gemm128_kernel<0><<<2 * m1 - 1, 256, gemm_smem, st>>>(A, np, KB, dinv);
+      gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
       mark("ui_end", KB, st);
       launches++;
       B200RT_CUDA(c, cudaEventRecord(c->lu_events[2 * KB + 1], st));  // evU[KB]
@@ -446,7 +458,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       B200RT_CUDA(c, cudaEventRecord(c->lu_events[2 * KB + 2], sB));  // evP[KB+1]
       const int m2 = m1 - 1;
       if (m2 > 0) {
-        gemm128_kernel<1><<<m2 * m2, 256, gemm_smem, st>>>(A, np, KB, dinv);
+        gemm128_kernel<1, 8><<<m2 * m2, 256, gemm_smem, st>>>(A, np, KB, dinv, Lbuf(KB));
         mark("uii_end", KB, st);
         launches++;
       }
