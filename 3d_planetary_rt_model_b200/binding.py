@@ -16,10 +16,11 @@ LIB_PATH = os.path.join(HERE, "libb200rt.so")
 
 F64, F32 = 0, 1
 ROW_MAJOR, COL_MAJOR = 0, 1
-PH_TRAVERSE, PH_INFLUENCE, PH_SOLVE, PH_BRIGHTNESS = 0, 1, 2, 3
+PH_TRAVERSE, PH_INFLUENCE, PH_SOLVE, PH_BRIGHTNESS, PH_IPH = 0, 1, 2, 3, 4
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_fp = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _vp = C.c_void_p
 
 # every symbol include/b200rt.h declares: name -> (restype, argtypes)
@@ -47,6 +48,11 @@ SIGNATURES = {
     "b200rt_los_upload": (C.c_int, [_vp, C.c_int] + [_dp] * 9),
     "b200rt_brightness_resident": (C.c_int, [_vp, C.c_int]),
     "b200rt_los_download": (C.c_int, [_vp] + [_vp] * 4),
+    "b200rt_iph_load_table": (C.c_int, [_vp, C.c_char_p]),
+    "b200rt_iph_set_table": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_float] + [_fp] * 7),
+    "b200rt_iph_background": (C.c_int, [_vp] + [C.c_float] * 4 + [C.c_int, _fp, _fp, _fp, _fp, _vp]),
+    "b200rt_iph_model": (C.c_int, [_vp, C.c_double, _dp, C.c_int, _dp, _dp, _dp]),
+    "b200rt_iph_extinction": (C.c_int, [C.c_int, _dp, _dp, _dp]),
     "b200rt_traverse_voxel_rays": (C.c_int, [_vp, C.c_int, C.c_int, C.c_longlong, _ip, _ip, _ip, _dp,
                                              C.POINTER(C.c_longlong)]),
     "b200rt_traverse_los": (C.c_int, [_vp, C.c_longlong, _ip, _ip, _ip, _dp, C.POINTER(C.c_longlong)]),
@@ -211,6 +217,42 @@ class Context:
         out = [np.zeros((self.n_em, self.n_los)) for _ in range(4)]
         self._ck(self.lib.b200rt_los_download(self.h, *[_ptr(o) for o in out]))
         return dict(brightness=out[0], tau_species_final=out[1], tau_absorber_final=out[2], species_col_dens=out[3])
+
+    # ---- interplanetary hydrogen background
+    def iph_load_table(self, fname):
+        self._ck(self.lib.b200rt_iph_load_table(self.h, os.fsencode(fname)))
+
+    def iph_set_table(self, tab):
+        """tab: dict with kmax, lmax, ninf, temp, alt_au, ang, dans, sot, so, sn, dinf_cm3 (file layout)"""
+        f = lambda k: np.ascontiguousarray(tab[k], dtype=np.float32)
+        self._ck(self.lib.b200rt_iph_set_table(self.h, int(tab["kmax"]), int(tab["lmax"]), int(tab["ninf"]),
+                                               float(tab["temp"]), f("alt_au"), f("ang"), f("dans"), f("sot"), f("so"),
+                                               f("sn"), f("dinf_cm3")))
+
+    def iph_background(self, fs, pos, u, v, w, want_steps=False):
+        n = len(u)
+        fln = np.zeros(n, np.float32)
+        steps = np.zeros(n, np.int32) if want_steps else None
+        a = [np.ascontiguousarray(x, dtype=np.float32) for x in (u, v, w)]
+        self._ck(self.lib.b200rt_iph_background(self.h, fs, pos[0], pos[1], pos[2], n, *a, fln, _ptr(steps)))
+        return (fln, steps) if want_steps else fln
+
+    def iph_model(self, g_lya, marspos, ra, dec):
+        n = len(ra)
+        out = np.zeros(n)
+        self._ck(self.lib.b200rt_iph_model(self.h, g_lya, np.ascontiguousarray(marspos, dtype=np.float64), n,
+                                           np.ascontiguousarray(ra, dtype=np.float64),
+                                           np.ascontiguousarray(dec, dtype=np.float64), out))
+        return out
+
+    def iph_extinction(self, iph, tau_abs):
+        iph = np.ascontiguousarray(iph, dtype=np.float64)
+        tau = np.ascontiguousarray(tau_abs, dtype=np.float64)
+        out = np.zeros_like(iph)
+        rc = self.lib.b200rt_iph_extinction(iph.size, iph.ravel(), tau.ravel(), out.ravel())
+        if rc != 0:
+            raise B200RTError(f"b200rt_iph_extinction: status {rc}")
+        return out
 
     # ---- traversal (parity surface)
     def traverse_voxel_rays(self, v0=0, v1=None):

@@ -443,7 +443,8 @@ int b200rt_destroy(b200rt_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->grid_tables, &c->sun_rays, &c->list_dist, &c->list_ent, &c->list_len, &c->list_flag,
-                    &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->lu, &c->lu_dinv, &c->lu_flag};
+                    &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->lu, &c->lu_dinv, &c->lu_flag,
+                    &c->iph.dev, &c->iph.io};
   for (DevBuf *b : bufs) b->release();
   for (int e = 0; e < MAX_EMISSIONS; e++) {
     Emission &E = c->em[e];
@@ -688,6 +689,39 @@ int b200rt_last_kernel_ms(b200rt_ctx *c, int phase, float *ms, int *n_launches) 
   if (!c || phase < 0 || phase >= PH_COUNT) return B200RT_ERR_ARG;
   if (ms) *ms = c->phase_ms[phase];
   if (n_launches) *n_launches = c->phase_launches[phase];
+  return B200RT_OK;
+}
+
+int b200rt_iph_load_table(b200rt_ctx *c, const char *fname) {
+  if (!c || !fname) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  return iph_load_table(c, fname);
+}
+
+int b200rt_iph_set_table(b200rt_ctx *c, int kmax, int lmax, int ninf, float temp, const float *alt_au, const float *ang,
+                         const float *dans, const float *sot, const float *so, const float *sn, const float *dinf_cm3) {
+  if (!c) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  return iph_set_table(c, kmax, lmax, ninf, temp, alt_au, ang, dans, sot, so, sn, dinf_cm3);
+}
+
+int b200rt_iph_background(b200rt_ctx *c, float fs, float xpos, float ypos, float zpos, int n_los, const float *u,
+                          const float *v, const float *w, float *fln, int *n_steps) {
+  if (!c) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  return iph_background(c, fs, xpos, ypos, zpos, n_los, u, v, w, fln, n_steps);
+}
+
+int b200rt_iph_model(b200rt_ctx *c, double g_lya, const double *marspos, int n_los, const double *ra, const double *dec,
+                     double *iph_kR) {
+  if (!c) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  return iph_model(c, g_lya, marspos, n_los, ra, dec, iph_kR);
+}
+
+int b200rt_iph_extinction(int n, const double *iph, const double *tau_abs, double *out) {
+  if (n < 0 || !iph || !tau_abs || !out) return B200RT_ERR_ARG;
+  for (int i = 0; i < n; i++) out[i] = (tau_abs[i] != -1) ? iph[i] * std::exp(-tau_abs[i]) : 0.0;
   return B200RT_OK;
 }
 

@@ -106,7 +106,17 @@ struct Emission {
   bool rec_dirty = true;    // tables or S changed since the records were packed
 };
 
-enum Phase { PH_TRAVERSE = 0, PH_INFLUENCE = 1, PH_SOLVE = 2, PH_BRIGHTNESS = 3, PH_COUNT = 4 };
+enum Phase { PH_TRAVERSE = 0, PH_INFLUENCE = 1, PH_SOLVE = 2, PH_BRIGHTNESS = 3, PH_IPH = 4, PH_COUNT = 5 };
+
+// Quemerais IPH model: tables and the constants of BACKGROUND (ipbackgroundCFR_fun.f:176-235), iph.cu
+struct IphTable {
+  bool loaded = false;
+  int kmax = 0, lmax = 0;
+  float ua = 0, dpi = 0, sig = 0, dtap = 0, sigmaf = 0, dinf_b = 0, dinf_o = 0;
+  float a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // wind-frame rotation A11..A33
+  DevBuf dev;   // alt[kmax] (m) | ang[lmax] | DANS | SO(:,:,2) | SN(:,:,2)
+  DevBuf io;    // u v w fln n_steps per line of sight
+};
 
 } // namespace b200rt
 
@@ -146,8 +156,10 @@ struct b200rt_ctx {
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  float phase_ms[b200rt::PH_COUNT] = {0, 0, 0, 0};
-  int phase_launches[b200rt::PH_COUNT] = {0, 0, 0, 0};
+  float phase_ms[b200rt::PH_COUNT] = {0, 0, 0, 0, 0};
+  int phase_launches[b200rt::PH_COUNT] = {0, 0, 0, 0, 0};
+
+  b200rt::IphTable iph;
 };
 
 namespace b200rt {
@@ -205,6 +217,15 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
                               long long n_los_total, int *queue, cudaStream_t s);
 template <class Real>
 cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *rec_pt, Real *rec_avg, cudaStream_t s);
+
+// ---- iph.cu  (compiled with -fmad=false)
+int iph_set_table(b200rt_ctx *c, int kmax, int lmax, int ninf, float temp, const float *alt_au, const float *ang,
+                  const float *dans, const float *sot, const float *so, const float *sn, const float *dinf_cm3);
+int iph_load_table(b200rt_ctx *c, const char *fname);
+int iph_background(b200rt_ctx *c, float fs, float xpos, float ypos, float zpos, int n_los, const float *u1,
+                   const float *v1, const float *w1, float *fln, int *n_steps);
+int iph_model(b200rt_ctx *c, double g_lya, const double *marspos, int n_los, const double *ra, const double *dec,
+              double *iph_kR);
 
 // ---- peaks.cu
 int measure_fp64_peaks(b200rt_ctx *c, double *dfma_tflops, double *dmma_tflops);

@@ -355,3 +355,43 @@ def random_los(n: int, seed: int = 20240607, r_lo: float = 1.05, r_hi: float = 2
     e2 = np.cross(phat, e1)
     dirs = (-phat) * ct[:, None] + e1 * (st * np.cos(az))[:, None] + e2 * (st * np.sin(az))[:, None]
     return np.ascontiguousarray(locs), np.ascontiguousarray(dirs)
+
+
+# ------------------------------------------------------------------ interplanetary hydrogen (IPH) inputs
+def make_iph_table(kmax: int = 59, lmax: int = 19, ninf: int = 5, temp: float = 8000.0):
+    """A synthetic table with the layout of the reference's Quemerais model file
+    (quemerais_IPH_model/fsm99td12v20t80: KMAX x LMAX nodes, 5 densities at infinity), for machines
+    where that file is not available.  Physics-shaped, not physical: a hot-model-like ionisation
+    cavity n/n_inf = exp(-r_c(theta)/r), optically thin source ~ n/r^2, primary and multiply
+    scattered source functions attenuated / enhanced with the density at infinity."""
+    alt = 0.2 * (551.6 / 0.2) ** (np.arange(kmax) / (kmax - 1.0)) ** 1.0
+    alt = np.round(alt.astype(np.float64), 3)
+    alt[0], alt[-1] = 0.2, 551.6
+    ang = np.linspace(0.0, 180.0, lmax)
+    th = np.radians(ang)[None, :]
+    r = alt[:, None]
+    r_c = 4.0 * (1.0 + 0.6 * (1.0 - np.cos(th)) / 2.0 * 3.0)          # cavity deeper downwind
+    dans = np.exp(-r_c / r)
+    dans[0, :] = 0.0
+    dinf = 0.05 * (1 + np.arange(ninf))
+    sot = dans / r ** 2
+    so = np.empty((ninf, kmax, lmax))
+    sn = np.empty((ninf, kmax, lmax))
+    for i in range(ninf):
+        tau = 0.8 * dinf[i] / 0.05 * np.sqrt(r)                        # grows outward and with density
+        so[i] = dinf[i] * 1e6 * sot * np.exp(-0.3 * tau)               # like the real file: SO ~ SOT * n_inf [m^-3]
+        sn[i] = so[i] * (1.0 + 0.25 * tau / (1.0 + 0.1 * tau))
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return dict(kmax=kmax, lmax=lmax, ninf=ninf, temp=temp, alt_au=f32(alt), ang=f32(ang), dans=f32(dans), sot=f32(sot),
+                so=f32(so), sn=f32(sn), dinf_cm3=f32(dinf))
+
+
+def random_sky(n: int, seed: int = 7):
+    """n directions uniform on the sky -> (ra_deg, dec_deg)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    ra = rng.uniform(0.0, 360.0, n)
+    dec = np.degrees(np.arcsin(rng.uniform(-1.0, 1.0, n)))
+    return ra, dec
+
+
+MARS_ECLIPTIC_POS = (1.41, 0.3, 0.0)   # AU, SURVEY.md 8(d) config 3

@@ -139,6 +139,30 @@ int b200rt_brightness_resident(b200rt_ctx *ctx, int n_subsamples);
 int b200rt_los_download(b200rt_ctx *ctx, double *brightness, double *tau_species_final,
                         double *tau_absorber_final, double *species_col_dens);
 
+/* ---- interplanetary hydrogen background ---------------------------------------------
+ * replaces quemerais_iph_model -> Fortran BACKGROUND (quemerais_IPH_model/iph_model_interface.cpp:19-82,
+ * ipbackgroundCFR_fun.f:1-741).  The table file (fsm99td12v20t80 layout, :107-164) is parsed ONCE per
+ * context (the Fortran re-reads it on every call); lines of sight are independent device threads
+ * (the Fortran loop :295-320 is serial).  float32 like the Fortran.
+ *   set_table: arrays as they stand in the file -- alt_au[kmax] (AU), ang[lmax] (deg), dans/sot[kmax][lmax],
+ *              so/sn[ninf][kmax][lmax], dinf_cm3[ninf]; temp = TEMP of the header line.
+ *   background: BACKGROUND's own arguments (fs = line-centre solar flux at 1 AU [ph cm-2 s-1 A-1], observer
+ *              [AU, ecliptic], look vectors [ecliptic]); fln = xsn(2) in rayleigh; n_steps (may be NULL) =
+ *              outer march steps per line of sight.
+ *   model:     quemerais_iph_model's arguments (g factor at Mars, Mars ecliptic position [AU], RA/Dec [deg]);
+ *              result in kR, Real = double.
+ *   extinction: observation::update_iph_extinction (observation.hpp:144-154), host helper:
+ *              out = (tau_absorber_final == -1) ? 0 : iph * exp(-tau_absorber_final). */
+int b200rt_iph_load_table(b200rt_ctx *ctx, const char *filename);
+int b200rt_iph_set_table(b200rt_ctx *ctx, int kmax, int lmax, int ninf, float temp, const float *alt_au,
+                         const float *ang, const float *dans, const float *sot, const float *so, const float *sn,
+                         const float *dinf_cm3);
+int b200rt_iph_background(b200rt_ctx *ctx, float fs, float xpos, float ypos, float zpos, int n_los,
+                          const float *u, const float *v, const float *w, float *fln, int *n_steps);
+int b200rt_iph_model(b200rt_ctx *ctx, double g_lya, const double *mars_ecliptic_pos, int n_los,
+                     const double *ra, const double *dec, double *iph_kR);
+int b200rt_iph_extinction(int n, const double *iph_unextincted, const double *tau_absorber_final, double *iph_observed);
+
 /* ---- traversal (parity surface) -------------------------------------------------
  * grid.ray_voxel_intersections (grid_spherical_azimuthally_symmetric.hpp:459-509) for the
  * voxel-origin rays of source voxels [v_begin, v_end) (ray order: voxel major, ray minor)
@@ -154,7 +178,7 @@ int b200rt_traverse_los(b200rt_ctx *ctx, long long capacity,
 
 /* ---- timing ---------------------------------------------------------------------
  * device time (CUDA events on the ctx stream) of the kernels of the last call:
- * phase 0 = traversal, 1 = influence march, 2 = solve, 3 = brightness march */
+ * phase 0 = traversal, 1 = influence march, 2 = solve, 3 = brightness march, 4 = IPH */
 int b200rt_last_kernel_ms(b200rt_ctx *ctx, int phase, float *ms, int *n_launches);
 int b200rt_synchronize(b200rt_ctx *ctx);
 /* measured FP64 peaks of this device (TFLOP/s): plain DFMA and DMMA.8x8x4 (mma.sync m8n8k4.f64).

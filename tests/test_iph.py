@@ -1,0 +1,137 @@
+"""Quemerais IPH background: oracle properties (CPU) and device parity (gpu marker).
+
+The reference has no known-answer vector for this model and its Fortran cannot be compiled here
+(parity unpinned, see oracle/iph_oracle.c); the oracle is held to the model's own invariants and the
+device kernel to the oracle, at 1e-4 relative (float Real, BASELINE.json north_star)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import iphbind
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "iph_real_table.npz")
+TOL = 1e-4
+
+
+def golden():
+    z = np.load(GOLD)
+    tab = {k[4:]: z[k] for k in z.files if k.startswith("tab_")}
+    for k in ("kmax", "lmax", "ninf"):
+        tab[k] = int(tab[k])
+    tab["temp"] = float(tab["temp"])
+    return z, tab
+
+
+def test_oracle_reproduces_golden_fixture():
+    z, tab = golden()
+    O = iphbind.IphOracle(table=tab)
+    kR = O.model(float(z["g_lya"]), z["marspos"], z["ra"], z["dec"])
+    assert np.array_equal(kR, z["kR"])                      # same code, same tables: bit identical
+    assert 0.15 < kR.min() and kR.max() < 0.9               # ~0.2-0.8 kR across the sky from Mars' orbit
+
+
+@pytest.mark.skipif(not os.path.exists(iphbind.REF_TABLE), reason="reference table file not present")
+def test_oracle_parser_matches_fixture_tables():
+    _, tab = golden()
+    T = iphbind.IphOracle(fname=iphbind.REF_TABLE).table()
+    for k, v in tab.items():
+        assert np.array_equal(np.asarray(v), np.asarray(T[k])), k
+    assert (T["kmax"], T["lmax"], T["ninf"]) == (59, 19, 5)
+    assert np.allclose(T["dinf_cm3"], [0.05, 0.10, 0.15, 0.20, 0.25])
+    assert T["alt_au"][0] == np.float32(0.2) and abs(T["alt_au"][-1] - 551.6) < 0.01
+    assert np.array_equal(T["ang"], np.arange(19, dtype=np.float32) * 10)
+
+
+def test_oracle_invariants(synth):
+    tab = synth.make_iph_table()
+    O = iphbind.IphOracle(table=tab)
+    ra, dec = synth.random_sky(300)
+    g = synth.lyman_alpha_typical_g_factor
+    b = O.model(g, synth.MARS_ECLIPTIC_POS, ra, dec)
+    assert np.isfinite(b).all() and (b > 0).all()
+    # linear in the solar flux (GRAL multiplies every term, ipbackgroundCFR_fun.f:219-221,638-647)
+    b2 = O.model(2 * g, synth.MARS_ECLIPTIC_POS, ra, dec)
+    assert np.allclose(b2, 2 * b, rtol=2e-6)
+    # an observer beyond the last radial node sees nothing (INTENSM_PH returns at once, :598)
+    far = O.model(g, (600.0, 0.0, 0.0), ra[:5], dec[:5])
+    assert (far == 0).all()
+    # the march takes a few hundred steps per line of sight from Mars' orbit
+    u = np.cos(np.radians(dec)) * np.cos(np.radians(ra))
+    v = np.cos(np.radians(dec)) * np.sin(np.radians(ra))
+    w = np.sin(np.radians(dec))
+    _, steps = O.background(3e11, synth.MARS_ECLIPTIC_POS, u, v, w, want_steps=True)
+    assert steps.min() > 50 and steps.max() < 5000
+
+
+def test_extinction_host_helper(binding):
+    lib = binding.load()
+    iph = np.array([1.0, 2.0, 3.0])
+    tau = np.array([0.0, -1.0, 0.5])
+    out = np.zeros(3)
+    assert lib.b200rt_iph_extinction(3, iph, tau, out) == 0
+    assert np.allclose(out, [1.0, 0.0, 3.0 * np.exp(-0.5)])      # observation.hpp:144-154
+
+
+# ---------------------------------------------------------------------------------- device
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["synthetic", "real"])
+def test_device_matches_oracle(synth, binding, which):
+    if which == "real":
+        z, tab = golden()
+        ra, dec, g, pos = z["ra"], z["dec"], float(z["g_lya"]), z["marspos"]
+    else:
+        tab = synth.make_iph_table()
+        ra, dec = synth.random_sky(4000)
+        g, pos = synth.lyman_alpha_typical_g_factor, np.array(synth.MARS_ECLIPTIC_POS)
+    O = iphbind.IphOracle(table=tab)
+    ctx = binding.Context(0, binding.F64)
+    ctx.iph_set_table(tab)
+    bo = O.model(g, pos, ra, dec)
+    bg = ctx.iph_model(g, pos, ra, dec)
+    if which == "real":
+        assert np.abs(bo - z["kR"]).max() == 0
+    rel = np.abs(bo - bg) / np.abs(bo)
+    assert rel.max() < TOL, rel.max()
+    # the march takes the same path on both sides: identical outer step counts
+    u = (np.cos(np.radians(dec)) * np.cos(np.radians(ra))).astype(np.float32)
+    v = (np.cos(np.radians(dec)) * np.sin(np.radians(ra))).astype(np.float32)
+    w = np.sin(np.radians(dec)).astype(np.float32)
+    fo, so = O.background(3e11, pos, u, v, w, want_steps=True)
+    fg, sg = ctx.iph_background(3e11, [float(x) for x in pos], u, v, w, want_steps=True)
+    assert np.array_equal(so, sg)
+    assert (np.abs(fo - fg) / np.abs(fo)).max() < TOL
+
+
+@pytest.mark.gpu
+def test_device_edge_cases(synth, binding):
+    tab = synth.make_iph_table()
+    ctx = binding.Context(0, binding.F64)
+    with pytest.raises(binding.B200RTError):            # no table yet: state error, not garbage
+        ctx.iph_model(1e-3, [1.4, 0, 0], np.array([10.0]), np.array([5.0]))
+    ctx.iph_set_table(tab)
+    O = iphbind.IphOracle(table=tab)
+    # observer outside the model, inside the innermost node, and exactly along / against the wind axis
+    for pos in ([600.0, 0.0, 0.0], [0.1, 0.05, 0.0], [1.0, 0.0, 0.0]):
+        ra = np.array([0.0, 72.3, 252.3, 180.0, 359.9])
+        dec = np.array([0.0, -8.7, 8.7, 89.9, -89.9])
+        bo = O.model(1e-3, pos, ra, dec)
+        bg = ctx.iph_model(1e-3, pos, ra, dec)
+        assert np.isfinite(bg).all()
+        assert np.allclose(bo, bg, rtol=TOL, atol=0)
+    bad = dict(tab)
+    bad["kmax"] = 100
+    with pytest.raises(binding.B200RTError):
+        ctx.iph_set_table(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(iphbind.REF_TABLE), reason="reference table file not present")
+def test_device_parser(binding):
+    _, tab = golden()
+    a, b = binding.Context(0, binding.F64), binding.Context(0, binding.F64)
+    a.iph_load_table(iphbind.REF_TABLE)
+    b.iph_set_table(tab)
+    ra, dec = np.linspace(0, 350, 36), np.linspace(-80, 80, 36)
+    assert np.array_equal(a.iph_model(2e-3, [1.41, 0.3, 0.0], ra, dec), b.iph_model(2e-3, [1.41, 0.3, 0.0], ra, dec))
