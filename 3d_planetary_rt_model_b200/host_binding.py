@@ -1,0 +1,147 @@
+"""ctypes binding of the C handles over the C++ observation_fit facade (host/capi.cpp, libb200rt_host.so).
+
+The class below has the method names of the reference's Cython class Pyobservation_fit
+(python/py_corona_sim.pyx:176-562) for the H Lyman alpha / beta path, plus brightness_batch."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200rt_host.so")
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+SIGNATURES = {
+    "obsfit_last_error": (C.c_char_p, []),
+    "obsfit_create": (_vp, [C.c_char_p, C.c_int]),
+    "obsfit_destroy": (None, [_vp]),
+    "obsfit_add_observation": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "obsfit_set_g_factor": (C.c_int, [_vp, C.c_double, C.c_double]),
+    "obsfit_add_observation_ra_dec": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp]),
+    "obsfit_generate_source_function": (C.c_int, [_vp, C.c_double, C.c_double, C.c_char_p]),
+    "obsfit_set_use_CO2_absorption": (C.c_int, [_vp, C.c_int]),
+    "obsfit_set_CO2_exobase_density": (C.c_int, [_vp, C.c_double]),
+    "obsfit_save_influence_matrix": (C.c_int, [_vp, C.c_char_p]),
+    "obsfit_get": (C.c_int, [_vp, C.c_int, _dp]),
+    "obsfit_source_function": (C.c_int, [_vp, C.c_int, _dp]),
+    "obsfit_radial_boundaries": (C.c_int, [_vp, _dp]),
+    "obsfit_brightness_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_double)]),
+    "obsfit_atmosphere_tables": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+}
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run __graft_entry__.build()")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def atmosphere_tables(nH, nCO2, T, n_rb=40, n_sb=20, rmethod=0):
+    """host only: the C++ chamb_diff_1d restatement -> (radial_boundaries[n_rb], tables[6][n_vox])"""
+    lib = load()
+    rb = np.zeros(n_rb)
+    tabs = np.zeros((6, (n_rb - 1) * (n_sb - 1)))
+    if lib.obsfit_atmosphere_tables(nH, nCO2, T, n_rb, n_sb, rmethod, rb, tabs) != 0:
+        raise RuntimeError(lib.obsfit_last_error().decode())
+    return rb, tabs
+
+
+class Pyobservation_fit:
+    n_emissions, n_rb, n_sb = 2, 40, 20
+    n_vox = (n_rb - 1) * (n_sb - 1)
+
+    def __init__(self, iph_table_fname="", device=0):
+        self.lib = load()
+        self.h = self.lib.obsfit_create(os.fsencode(iph_table_fname), device)
+        if not self.h:
+            raise RuntimeError(self.lib.obsfit_last_error().decode())
+        self.n_obs = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.obsfit_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.obsfit_last_error().decode())
+
+    def add_observation(self, loc_arr, dir_arr):
+        loc = np.ascontiguousarray(loc_arr, dtype=np.float64)
+        d = np.ascontiguousarray(dir_arr, dtype=np.float64)
+        self.n_obs = len(loc)
+        self._ck(self.lib.obsfit_add_observation(self.h, self.n_obs, loc, d))
+
+    def set_g_factor(self, g):
+        self._ck(self.lib.obsfit_set_g_factor(self.h, float(g[0]), float(g[1])))
+
+    def add_observation_ra_dec(self, mars_ecliptic_coords, ra, dec):
+        self._ck(self.lib.obsfit_add_observation_ra_dec(self.h, np.ascontiguousarray(mars_ecliptic_coords, dtype=np.float64),
+                                                        len(ra), np.ascontiguousarray(ra, dtype=np.float64),
+                                                        np.ascontiguousarray(dec, dtype=np.float64)))
+
+    def generate_source_function(self, nH, T, sourcefn_fname=""):
+        self._ck(self.lib.obsfit_generate_source_function(self.h, nH, T, os.fsencode(sourcefn_fname)))
+
+    def set_use_CO2_absorption(self, use=True):
+        self._ck(self.lib.obsfit_set_use_CO2_absorption(self.h, int(use)))
+
+    def set_CO2_exobase_density(self, n):
+        self._ck(self.lib.obsfit_set_CO2_exobase_density(self.h, n))
+
+    def save_influence_matrix(self, fname):
+        self._ck(self.lib.obsfit_save_influence_matrix(self.h, os.fsencode(fname)))
+
+    def _get(self, which):
+        out = np.zeros((self.n_emissions, self.n_obs))
+        self._ck(self.lib.obsfit_get(self.h, which, out))
+        return out
+
+    def brightness(self):
+        return self._get(0)
+
+    def species_col_dens(self):
+        return self._get(1)
+
+    def tau_species_final(self):
+        return self._get(2)
+
+    def tau_absorber_final(self):
+        return self._get(3)
+
+    def iph_brightness_observed(self):
+        return self._get(4)
+
+    def iph_brightness_unextincted(self):
+        return self._get(5)
+
+    def source_function(self, e):
+        out = np.zeros(self.n_vox)
+        self._ck(self.lib.obsfit_source_function(self.h, e, out))
+        return out
+
+    def radial_boundaries(self):
+        out = np.zeros(self.n_rb)
+        self._ck(self.lib.obsfit_radial_boundaries(self.h, out))
+        return out
+
+    def brightness_batch(self, nH, T, contexts_per_gpu=4, n_gpus=-1):
+        nH = np.ascontiguousarray(nH, dtype=np.float64)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        out = np.zeros((len(nH), self.n_emissions, self.n_obs))
+        sec = C.c_double(0)
+        self._ck(self.lib.obsfit_brightness_batch(self.h, len(nH), nH, T, contexts_per_gpu, n_gpus, out, C.byref(sec)))
+        self.last_batch_seconds = sec.value
+        return out

@@ -395,3 +395,26 @@ def random_sky(n: int, seed: int = 7):
 
 
 MARS_ECLIPTIC_POS = (1.41, 0.3, 0.0)   # AU, SURVEY.md 8(d) config 3
+
+
+def write_iph_table(tab, fname):
+    """Write a table dict in the text layout of the reference's Quemerais file (the READ sequence of
+    ipbackgroundCFR_fun.f:107-164: header lines, then 4 angle blocks of 5,5,5,4 columns per array)."""
+    k, l, n = int(tab["kmax"]), int(tab["lmax"]), int(tab["ninf"])
+    cols = [(0, 5), (5, 10), (10, 15), (15, 19)]
+
+    def blocks(f, arr):
+        for a, b in cols:
+            f.write("       " + "".join(f"  {tab['ang'][j]:4.0f}.  " for j in range(a, b)) + "\n")
+            for i in range(k):
+                f.write(f"{tab['alt_au'][i]:9.3f}" + "".join(f" {arr[i, j]:13.6E}" for j in range(a, b)) + "\n")
+
+    with open(fname, "w") as f:
+        f.write(f"  {k}  {l}  {n}\n")
+        for ii in range(n):
+            f.write(f"   20.00  254.00   7.50 {tab['temp']:5.0f}.  0.99 0.120E+07 0.0 {tab['dinf_cm3'][ii]:9.3f}\n")
+            if ii == 0:
+                blocks(f, np.asarray(tab["dans"]).reshape(k, l))
+                blocks(f, np.asarray(tab["sot"]).reshape(k, l))
+            blocks(f, np.asarray(tab["so"]).reshape(n, k, l)[ii])
+            blocks(f, np.asarray(tab["sn"]).reshape(n, k, l)[ii])

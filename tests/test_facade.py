@@ -1,0 +1,111 @@
+"""The C++ host facade (observation_fit, host/) and its Boost-free chamb_diff_1d atmosphere.
+
+CPU: the C++ atmosphere against the Python generator the other tests use (same algorithm, two
+implementations).  GPU: generate_source_function(nH, T) + brightness() through the facade against the
+oracle pipeline on the same parameters; the batched sweep against the sequential calls."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from util import rel_err
+
+PKG = "3d_planetary_rt_model_b200"
+
+
+@pytest.fixture(scope="module")
+def hb():
+    return importlib.import_module(PKG + ".host_binding")
+
+
+@pytest.mark.parametrize("nH,T", [(5e5, 200.0), (1e4, 100.0), (1e7, 400.0), (3.3e6, 275.0)])
+def test_atmosphere_matches_python_generator(synth, hb, nH, T):
+    rb, tabs = hb.atmosphere_tables(nH, 2e8, T, 40, 20, 0)
+    scn = synth.make_scenario(40, 20, 7, 12, n_em=2, nH_exo=nH, T_exo=T)
+    assert rel_err(scn.rb, rb) < 1e-12
+    for q in range(6):
+        assert rel_err(scn.vox_in[q], tabs[q], floor=1e-300) < 1e-9, q
+    assert (np.diff(rb) > 0).all() and rb[0] == synth.rMars + 80e5
+
+
+def test_atmosphere_log_n_species_grid(synth, hb):
+    rb, _ = hb.atmosphere_tables(5e5, 2e8, 200.0, 40, 20, 1)
+    scn = synth.make_scenario(40, 20, 7, 12, n_em=2, rmethod=synth.RMETHOD_LOG_N_SPECIES)
+    assert rel_err(scn.rb, rb) < 1e-9
+
+
+def test_host_library_exports(hb):
+    lib = hb.load()
+    for name in hb.SIGNATURES:
+        assert hasattr(lib, name)
+
+
+@pytest.mark.gpu
+def test_facade_matches_oracle_pipeline(synth, hb, oraclebind, tmp_path):
+    nH, T = 5e5, 200.0
+    F = hb.Pyobservation_fit()
+    locs, dirs = synth.random_los(1500)
+    F.add_observation(locs, dirs)
+    F.generate_source_function(nH, T, str(tmp_path / "S.dat"))
+    b = F.brightness()
+    scn = synth.make_scenario(40, 20, 7, 12, n_em=2, nH_exo=nH, T_exo=T)
+    O = oraclebind.OracleModel(scn, "f64")
+    O.build_rows()
+    O.solve()
+    for e in range(2):
+        assert rel_err(O.vectors(e)["S"], F.source_function(e)) < 1e-6
+    _, bo = O.brightness(locs, dirs, 10)
+    assert rel_err(bo[:, 0], b, floor=1e-300) < 1e-6
+    assert rel_err(bo[:, 3], F.species_col_dens(), floor=1e-300) < 1e-6
+    assert rel_err(bo[:, 2], F.tau_absorber_final(), floor=1e-300) < 1e-6
+    # save_S layout (grid_spherical_azimuthally_symmetric.hpp:630-665): what the reference's notebook parses
+    txt = (tmp_path / "S.dat").read_text()
+    assert txt.startswith("radial boundaries [cm]: ") and "For H Lyman alpha" in txt and "For H Lyman beta" in txt
+    assert txt.count("    Source function: ") == 2 * 19
+    first = txt.split("    Source function: ")[1].split("\n")[0].split()
+    assert len(first) == 39 and abs(float(first[0]) - F.source_function(0)[0]) < 1e-5 * abs(F.source_function(0)[0])
+    # error behaviour
+    with pytest.raises(RuntimeError):
+        hb.Pyobservation_fit().brightness()
+
+
+@pytest.mark.gpu
+def test_facade_iph_and_options(synth, hb, tmp_path):
+    # write a table file in the reference's layout from the synthetic table, then go through load_table
+    tab = synth.make_iph_table()
+    fname = tmp_path / "iph_table"
+    synth.write_iph_table(tab, fname)
+    F = hb.Pyobservation_fit(str(fname))
+    locs, dirs = synth.random_los(400)
+    F.add_observation(locs, dirs)
+    ra, dec = synth.random_sky(400)
+    F.add_observation_ra_dec(synth.MARS_ECLIPTIC_POS, ra, dec)
+    F.generate_source_function(5e5, 200.0)
+    b = F.brightness()
+    un, ob, ta = F.iph_brightness_unextincted(), F.iph_brightness_observed(), F.tau_absorber_final()
+    assert (un[0] > 0).all() and np.allclose(un[1], un[0] * synth.lyman_beta_typical_g_factor / synth.lyman_alpha_typical_g_factor)
+    expect = np.where(ta == -1, 0.0, un * np.exp(-ta))
+    assert np.allclose(ob, expect, rtol=1e-12)
+    G = hb.Pyobservation_fit()
+    G.add_observation(locs, dirs)
+    G.generate_source_function(5e5, 200.0)
+    assert np.allclose(b, G.brightness() + ob, rtol=1e-12)
+    # no CO2 absorption -> no absorber optical depth along any line of sight that stays above the surface
+    G.set_use_CO2_absorption(False)
+    G.generate_source_function(5e5, 200.0)
+    ta0 = G.tau_absorber_final()
+    assert ((ta0 == 0) | (ta0 == -1)).all()
+
+
+@pytest.mark.gpu
+def test_batch_equals_sequential(synth, hb):
+    F = hb.Pyobservation_fit()
+    locs, dirs = synth.random_los(500)
+    F.add_observation(locs, dirs)
+    nH = np.array([1e5, 5e5, 2e6, 8e6, 3e4, 6e5])
+    T = np.array([150.0, 200.0, 250.0, 350.0, 120.0, 310.0])
+    batch = F.brightness_batch(nH, T, contexts_per_gpu=3)
+    for i in range(len(nH)):
+        F.generate_source_function(nH[i], T[i])
+        assert rel_err(F.brightness(), batch[i], floor=1e-300) < 1e-12, i
