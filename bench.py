@@ -17,8 +17,8 @@ roofline  = dominant kernel against the measured HBM peak (these kernels are FP6
 cpu_baseline / --impl reference = the reference's own CPU (OpenMP) source built in place
             (oracle/_ref), on a bounded sample of the same workload.
 
-N > 1 (torchrun): influence rows are split by source voxel, exchanged with NCCL broadcasts of
-row blocks, rank 0 solves and broadcasts S, lines of sight are split per GPU (no communication).
+N > 1 (torchrun): influence rows are split by source voxel and gathered onto rank 0 with one grouped
+NCCL send/recv, rank 0 solves and broadcasts S, lines of sight are split per GPU (no communication).
 """
 import argparse
 import importlib
@@ -160,6 +160,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200RT_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -195,6 +196,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_rows():
+        """the one exchange on the path: every rank's row block -> rank 0's resident K, one grouped NCCL
+        send/recv over NVLink (only the solving GPU needs the matrix)"""
+        ops = []
+        if rank == 0:
+            for r in range(1, world):
+                a, b = partition(n_vox, world, r)
+                if b > a:
+                    ops.append(dist.P2POp(dist.irecv, K_t[a:b], r))
+        elif v1 > v0:
+            ops.append(dist.P2POp(dist.isend, K_t[v0:v1], 0))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        torch.cuda.synchronize()
+
     def one_step():
         """-> dict of device/wall times (s) for this rank"""
         t = {}
@@ -206,12 +223,8 @@ def run_ours(args):
         t["march_launches"] = ctx.kernel_ms(binding.PH_INFLUENCE)[1] - 1      # minus the single-scattering march
         steps = ctx.last_step_count()
         w1 = time.perf_counter()
-        if world > 1:                                           # exchange row blocks over NVLink
-            for r in range(world):
-                a, b = partition(n_vox, world, r)
-                if b > a:
-                    dist.broadcast(K_t[a:b], src=r)
-            torch.cuda.synchronize()
+        if world > 1:                                           # gather the row blocks onto the solving GPU (NVLink)
+            gather_rows()
         w2 = time.perf_counter()
         if rank == 0:
             ctx.solve()
@@ -244,11 +257,7 @@ def run_ours(args):
         sol = ctx.solution(0, want_S=False)                     # D2H: S0 + optical depths
         w1 = time.perf_counter()
         if world > 1:
-            for r in range(world):
-                a, b = partition(n_vox, world, r)
-                if b > a:
-                    dist.broadcast(K_t[a:b], src=r)
-            torch.cuda.synchronize()
+            gather_rows()
         if rank == 0:
             ctx.solve()
             S = ctx.solution(0)["S"]                            # D2H: S
@@ -399,6 +408,18 @@ def run_ours(args):
                                         "sample": f"every {args.ref_stride}th source-voxel row ({ns} steps) and {args.ref_los} LOS"}
         except Exception as ex:   # the baseline is a reported number, never a reason to lose the bench line
             line["cpu_baseline"] = {"error": str(ex)}
+    # ---- the other two configs of BASELINE.json that are not part of the timed step: the Quemerais IPH
+    # background for the same number of lines of sight, and the 512-set (nH, T) sweep on grid D (N = 1 only)
+    if world == 1 and not args.no_extras:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import extra_bench
+            del ctx
+            ex = extra_bench.iph(n_los)
+            ex.update(extra_bench.sweep(512, 10000, 4, 1))
+            line["extras"] = ex
+        except Exception as exn:
+            line["extras"] = {"error": str(exn)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -414,6 +435,7 @@ def main():
     ap.add_argument("--ref-stride", type=int, default=8, help="CPU sample: every k-th source-voxel row")
     ap.add_argument("--ref-los", type=int, default=50000, help="CPU sample: lines of sight per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the IPH and sweep measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

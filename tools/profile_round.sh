@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out
-CMD="python bench.py --steps 1 --warmup 0 --n-los 200000 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 0 --n-los 200000 --no-cpu-baseline --no-extras"
 $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain_$TAG.log; exit 1; }
 tail -c 600 $OUT/plain_$TAG.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1
