@@ -93,9 +93,7 @@ def make_workload(synth, n_los):
 
 def partition(n, world, rank):
     """contiguous block of source voxels / lines of sight for this rank"""
-    base, rem = divmod(n, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    return importlib.import_module(PKG + ".multi").partition(n, world, rank)
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -196,20 +194,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    multi = importlib.import_module(PKG + ".multi")
+
     def gather_rows():
         """the one exchange on the path: every rank's row block -> rank 0's resident K, one grouped NCCL
         send/recv over NVLink (only the solving GPU needs the matrix)"""
-        ops = []
-        if rank == 0:
-            for r in range(1, world):
-                a, b = partition(n_vox, world, r)
-                if b > a:
-                    ops.append(dist.P2POp(dist.irecv, K_t[a:b], r))
-        elif v1 > v0:
-            ops.append(dist.P2POp(dist.isend, K_t[v0:v1], 0))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        multi.gather_rows(dist, K_t, n_vox, rank, world, 0)
         torch.cuda.synchronize()
 
     def one_step():
