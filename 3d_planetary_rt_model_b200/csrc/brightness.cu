@@ -36,9 +36,12 @@ namespace {
 template <class Real> struct MathB;
 template <> struct MathB<double> {
   __device__ static double exp_(double x) { return fm::exp_nonpos(x); }   // arguments are <= 0 and finite
-  __device__ static double div_(double a, double b) { return fm::div_pos(a, b); }   // b >= 1e-3 where it is used
+  __device__ static double div_(double a, double b) { return fm::div_approx(a, b); }   // b >= 1e-3 where it is used
+  __device__ static double divc_(double a, double b, double rb) { return fm::div_by(a, b, rb); }   // rb = 1/b precomputed
+  __device__ static double rcp_(double b) { return 1.0 / b; }
   __device__ static double log_(double x) { return log(x); }
-  __device__ static double hypot2_(double a, double b, double c) { return hypot(hypot(a, b), c); }
+  // the coordinates are O(1) after the 1e9 scaling: no overflow guards needed
+  __device__ static double hypot2_(double a, double b, double c) { return fm::norm3(a, b, c); }
   __device__ static double acos_(double x) { return acos(x); }
   __device__ static double eps() { return 1e-6; }       // EPS      Real.hpp:23
   __device__ static double coneeps() { return 1e-6; }   // CONEEPS  Real.hpp:25
@@ -46,6 +49,8 @@ template <> struct MathB<double> {
 template <> struct MathB<float> {
   __device__ static float exp_(float x) { return expf(x); }
   __device__ static float div_(float a, float b) { return a / b; }
+  __device__ static float divc_(float a, float b, float) { return a / b; }
+  __device__ static float rcp_(float b) { return 1.0f / b; }
   // std::log(float) of the host libm is (nearly) correctly rounded; CUDA logf is not (1 ulp), and one ulp of
   // logf(r) moves the radial interpolation weight by ~3e-5.  Rounding the double log gives the host's result.
   __device__ static float log_(float x) { return (float) log((double) x); }
@@ -168,6 +173,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
   const Real eps = MathB<Real>::eps(), ceps = MathB<Real>::coneeps();
   const Real scale = Real(1e9);
   const Real delta_lambda = Real(4.0) / (N_LAMBDA - 1);
+  const Real r_scale = MathB<Real>::rcp_(scale), r_nss = MathB<Real>::rcp_((Real) (nsd - 1));
 
   Real wgt[NLL];
 #pragma unroll
@@ -186,7 +192,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
   int total = 0, j0 = 0, flagbits = 0;
   const Real *dl = nullptr;
   const int *el = nullptr;
-  Real px = 0, py = 0, pz = 0, lx = 0, ly = 0, lz = 0;
+  Real px = 0, py = 0, pz = 0, lx = 0, ly = 0, lz = 0;   // px, py, pz already divided by the 1e9 scale
   Real P[NEM][NLL], acc_B[NEM], acc_tsp[NEM], acc_tab[NEM], acc_col[NEM];
 
   while (true) {
@@ -211,7 +217,9 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       flagbits = lists.flag[t];
       dl = lists.dist + (size_t) t * lists.cap;
       el = lists.ent + (size_t) t * lists.cap;
-      px = los_in[0 * los_stride + los]; py = los_in[1 * los_stride + los]; pz = los_in[2 * los_stride + los];
+      px = MathB<Real>::divc_(los_in[0 * los_stride + los], scale, r_scale);
+      py = MathB<Real>::divc_(los_in[1 * los_stride + los], scale, r_scale);
+      pz = MathB<Real>::divc_(los_in[2 * los_stride + los], scale, r_scale);
       lx = los_in[5 * los_stride + los]; ly = los_in[6 * los_stride + los]; lz = los_in[7 * los_stride + los];
 #pragma unroll
       for (int e = 0; e < NEM; e++) {
@@ -238,7 +246,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       Real d_start = dl[ib - 1];
       const Real dnext = dl[ib];
       const int cur = el[ib - 1];
-      Real d_step = (dnext - d_start) / (nsd - 1);
+      Real d_step = MathB<Real>::divc_(dnext - d_start, (Real) (nsd - 1), r_nss);
       d_start += Real(0.5) * eps * d_step;          // RT_grid.hpp:268-271
       d_step *= Real(1.0) - eps;
       my_s = d_step;
@@ -255,11 +263,11 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
         const Real sb_lo = s_sb[sza_idx], sb_hi = s_sb[sza_idx + 1];
         // ---- atmo_vector::extend
         const Real dist = d_start + is * d_step;
-        const Real nx = px / scale + (lx * dist) / scale;
-        const Real ny = py / scale + (ly * dist) / scale;
-        const Real nz = pz / scale + (lz * dist) / scale;
+        const Real nx = px + MathB<Real>::divc_(lx * dist, scale, r_scale);
+        const Real ny = py + MathB<Real>::divc_(ly * dist, scale, r_scale);
+        const Real nz = pz + MathB<Real>::divc_(lz * dist, scale, r_scale);
         const Real rr = MathB<Real>::hypot2_(nx, ny, nz);
-        Real t = MathB<Real>::acos_(nz / rr);
+        Real t = MathB<Real>::acos_(MathB<Real>::div_(nz, rr));
         Real r = rr * scale;
         // ---- interp_weights
         if (r < rb_lo && rb_lo / r > (1 - eps)) r = rb_lo + eps;
@@ -274,13 +282,13 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
           rlo = (r < s_pr[r_idx]) ? r_idx - 1 : r_idx;
           rhi = rlo + 1;
           const Real l0 = s_lpr[rlo], l1 = s_lpr[rhi];
-          r_wt = (MathB<Real>::log_(r) - l0) / (l1 - l0);
+          r_wt = MathB<Real>::div_(MathB<Real>::log_(r) - l0, l1 - l0);
         }
         int slo = (t < s_ps[sza_idx]) ? sza_idx - 1 : sza_idx;
         slo = max(0, min(slo, n_sb1 - 2));          // guard (the reference would index out of bounds)
         const int shi = slo + 1;
         const Real p0 = s_ps[slo], p1 = s_ps[shi];
-        const Real s_wt = (t - p0) / (p1 - p0);
+        const Real s_wt = MathB<Real>::div_(t - p0, p1 - p0);
         int idx[4];
         Real w[4];
         idx[0] = rlo * n_sb1 + slo; w[0] = (Real(1.0) - r_wt) * (Real(1.0) - s_wt);

@@ -57,5 +57,25 @@ __device__ __forceinline__ double div_pos(double a, double b) {
   return fma(rem, r, q);
 }
 
+// a / b to ~1e-13 relative (two Newton steps, no final correction): for quantities held to 1e-6
+__device__ __forceinline__ double div_approx(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return a * r;
+}
+
+// a / b with the reciprocal r ~ 1/b (<= 1 ulp) supplied: one correction step, result <= 1 ulp
+__device__ __forceinline__ double div_by(double a, double b, double r) {
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+
+// sqrt(a^2 + b^2 + c^2) for moderate magnitudes (no overflow / underflow guards), <= 1 ulp from hypot(hypot(a,b),c)
+__device__ __forceinline__ double norm3(double a, double b, double c) { return sqrt(fma(a, a, fma(b, b, c * c))); }
+
 } // namespace fm
 } // namespace b200rt
