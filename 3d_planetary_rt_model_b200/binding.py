@@ -31,6 +31,8 @@ SIGNATURES = {
     "b200rt_device_count": (C.c_int, []),
     "b200rt_set_grid_sph": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int] + [_dp] * 7),
     "b200rt_make_grid_sph": (C.c_int, [C.c_int] * 5 + [_dp, C.c_int, C.c_int] + [_dp] * 6),
+    "b200rt_set_grid_pp": (C.c_int, [_vp, C.c_int, C.c_int] + [_dp] * 4),
+    "b200rt_make_grid_pp": (C.c_int, [C.c_int] * 3 + [_dp] * 4),
     "b200rt_set_singlet": (C.c_int, [_vp, C.c_int, C.c_int] + [C.c_double] * 4 + [_dp] * 8),
     "b200rt_set_g_factor": (C.c_int, [_vp, C.c_int, C.c_double]),
     "b200rt_generate_S": (C.c_int, [_vp]),
@@ -139,6 +141,24 @@ class Context:
         self.n_rb, self.n_sb, self.n_rays = n_rb, n_sb, n_rays
         self.n_vox = (n_rb - 1) * (n_sb - 1)
         self.cap = 2 * n_rb + n_sb
+
+    def make_grid_pp(self, n_rb, n_theta, rb):
+        """plane_parallel_grid<n_rb, n_theta>::setup_voxels / setup_rays"""
+        out = dict(radial_boundaries=np.ascontiguousarray(rb, dtype=np.float64), pts_radii=np.zeros(n_rb - 1),
+                   ray_theta=np.zeros(n_theta), ray_domega=np.zeros(n_theta))
+        rc = self.lib.b200rt_make_grid_pp(self.precision, n_rb, n_theta, out["radial_boundaries"], out["pts_radii"],
+                                          out["ray_theta"], out["ray_domega"])
+        if rc != 0:
+            raise B200RTError(f"b200rt_make_grid_pp: status {rc}")
+        return out
+
+    def set_grid_pp(self, g):
+        n_rb, n_rays = len(g["radial_boundaries"]), len(g["ray_theta"])
+        self._ck(self.lib.b200rt_set_grid_pp(self.h, n_rb, n_rays, g["radial_boundaries"], g["pts_radii"],
+                                             g["ray_theta"], g["ray_domega"]))
+        self.n_rb, self.n_sb, self.n_rays = n_rb, 2, n_rays
+        self.n_vox = n_rb - 1
+        self.cap = 2 * n_rb + 2
 
     # ---- emissions
     def set_singlet(self, e, n_em, branching, T_ref, sigma_ref, g, tabs):
@@ -312,8 +332,12 @@ class GpuModel:
         self.scn = scn
         self.prec = F64 if precision == "f64" else F32
         self.ctx = Context(device, self.prec)
-        self.g = self.ctx.make_grid(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.rb, scn.szamethod, scn.raymethod)
-        self.ctx.set_grid(self.g)
+        if getattr(scn, "pp", False):
+            self.g = self.ctx.make_grid_pp(scn.n_rb, scn.n_theta, scn.rb)
+            self.ctx.set_grid_pp(self.g)
+        else:
+            self.g = self.ctx.make_grid(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.rb, scn.szamethod, scn.raymethod)
+            self.ctx.set_grid(self.g)
         self.n_vox, self.n_rays = self.ctx.n_vox, self.ctx.n_rays
         for e in range(scn.n_em):
             b, T, s, g = (float(x) for x in scn.em_scalars[e])
@@ -322,6 +346,8 @@ class GpuModel:
     def grid(self):
         nphi = self.scn.n_phi
         g = dict(self.g)
+        if getattr(self.scn, "pp", False):
+            return g
         g["ray_theta"] = self.g["ray_theta"][::nphi].copy()
         g["ray_phi"] = self.g["ray_phi"][:nphi].copy()
         return g

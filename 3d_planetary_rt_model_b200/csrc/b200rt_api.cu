@@ -221,6 +221,8 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
   if (n_subsamples == 1 || n_subsamples < 0)
     return fail(c, B200RT_ERR_ARG, "n_subsamples must be 0 or > 1 (RT_grid.hpp:237)");
   if (c->n_los <= 0) return fail(c, B200RT_ERR_STATE, "no lines of sight uploaded");
+  if (c->hg.pp)
+    return fail(c, B200RT_ERR_STATE, "interp_weights not implemented in grid_plane_parallel (grid_plane_parallel.hpp:304-311)");
   for (int e = 0; e < c->n_em; e++)
     if (!c->em[e].have_S) return fail(c, B200RT_ERR_STATE, "source function not available (solve or set_sourcefn first)");
   GridView<Real> &g = gv<Real>(c);
@@ -484,10 +486,42 @@ int b200rt_set_grid_sph(b200rt_ctx *c, int n_rb, int n_sb, int n_rays, const dou
     return fail(c, B200RT_ERR_ARG, "b200rt_set_grid_sph: bad argument");
   cudaSetDevice(c->device);
   HostGrid &h = c->hg;
+  h.pp = false;
   h.n_rb = n_rb; h.n_sb = n_sb; h.n_vox = (n_rb - 1) * (n_sb - 1); h.n_rays = n_rays; h.cap = 2 * n_rb + n_sb;
   h.rb.assign(rb, rb + n_rb); h.sb.assign(sb, sb + n_sb);
   h.pts_r.assign(pts_r, pts_r + n_rb - 1); h.pts_s.assign(pts_s, pts_s + n_sb - 1);
   h.ray_t.assign(ray_t, ray_t + n_rays); h.ray_p.assign(ray_p, ray_p + n_rays);
+  h.ray_domega.assign(ray_domega, ray_domega + n_rays);
+  int rc = is64(c) ? upload_grid<double>(c) : upload_grid<float>(c);
+  if (rc) return rc;
+  c->have_grid = true;
+  c->n_em = 0;
+  for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
+  return B200RT_OK;
+}
+
+int b200rt_make_grid_pp(int precision, int n_rb, int n_theta, const double *rb, double *pts_r, double *ray_t,
+                        double *ray_domega) {
+  if (n_rb < 2 || n_theta < 1 || !rb || !pts_r || !ray_t || !ray_domega) return B200RT_ERR_ARG;
+  if (precision == B200RT_F64) make_grid_pp<double>(n_rb, n_theta, rb, pts_r, ray_t, ray_domega);
+  else make_grid_pp<float>(n_rb, n_theta, rb, pts_r, ray_t, ray_domega);
+  return B200RT_OK;
+}
+
+int b200rt_set_grid_pp(b200rt_ctx *c, int n_rb, int n_rays, const double *rb, const double *pts_r,
+                       const double *ray_t, const double *ray_domega) {
+  if (!c) return B200RT_ERR_ARG;
+  if (n_rb < 2 || n_rays < 1 || !rb || !pts_r || !ray_t || !ray_domega)
+    return fail(c, B200RT_ERR_ARG, "b200rt_set_grid_pp: bad argument");
+  cudaSetDevice(c->device);
+  HostGrid &h = c->hg;
+  // one SZA column [0, pi] whose voxel points sit on the +z axis (pt.xyz(0,0,pts_radii[i]) => pt.t = 0,
+  // grid_plane_parallel.hpp:189-204); rays have phi = 0 (:219)
+  h.pp = true;
+  h.n_rb = n_rb; h.n_sb = 2; h.n_vox = n_rb - 1; h.n_rays = n_rays; h.cap = 2 * n_rb + 2;
+  h.rb.assign(rb, rb + n_rb); h.sb.assign({0.0, M_PI});
+  h.pts_r.assign(pts_r, pts_r + n_rb - 1); h.pts_s.assign(1, 0.0);
+  h.ray_t.assign(ray_t, ray_t + n_rays); h.ray_p.assign(n_rays, 0.0);
   h.ray_domega.assign(ray_domega, ray_domega + n_rays);
   int rc = is64(c) ? upload_grid<double>(c) : upload_grid<float>(c);
   if (rc) return rc;

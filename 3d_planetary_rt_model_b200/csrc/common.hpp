@@ -37,6 +37,7 @@ struct DevBuf {
 template <class Real>
 struct GridView {
   int n_rb, n_sb, n_vox, n_rays, cap;
+  int pp;                  // 1 = plane_parallel_grid: boundaries are the planes z = rb[i], n_sb = 2 (no cones)
   const Real *rb;          // [n_rb]   radial boundaries
   const Real *sph_R2;      // [n_rb]   (rb/1e9)^2            sphere::set_radius
   const Real *sb;          // [n_sb]   sza boundaries
@@ -88,6 +89,7 @@ struct EmissionView {
 // ------------------------------------------------------------------ host-side state
 struct HostGrid {
   int n_rb = 0, n_sb = 0, n_vox = 0, n_rays = 0, cap = 0;
+  bool pp = false;         // plane_parallel_grid (grid/grid_plane_parallel.hpp)
   std::vector<double> rb, sb, pts_r, pts_s, ray_t, ray_p, ray_domega;
 };
 
@@ -184,6 +186,8 @@ template <class Real>
 void make_grid_sph(int n_rb, int n_sb, int n_theta, int n_phi, const double *rb, int szamethod,
                    int raymethod, double *sb, double *pts_r, double *pts_s, double *ray_t,
                    double *ray_p, double *ray_domega);
+template <class Real>
+void make_grid_pp(int n_rb, int n_theta, const double *rb, double *pts_r, double *ray_t, double *ray_domega);
 template <class Real>
 void los_from_MSO(int n, const double *loc, const double *dir, double *x, double *y, double *z,
                   double *r, double *t, double *lx, double *ly, double *lz, double *cost);

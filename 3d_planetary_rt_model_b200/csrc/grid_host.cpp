@@ -124,7 +124,7 @@ int upload_grid(b200rt_ctx *c) {
   if (c->grid_view) { ::operator delete(c->grid_view); c->grid_view = nullptr; }
   GridView<Real> *g = new GridView<Real>;
   char *base = static_cast<char *>(c->grid_tables.p);
-  g->n_rb = n_rb; g->n_sb = n_sb; g->n_vox = n_vox; g->n_rays = n_rays; g->cap = h.cap;
+  g->n_rb = n_rb; g->n_sb = n_sb; g->n_vox = n_vox; g->n_rays = n_rays; g->cap = h.cap; g->pp = h.pp ? 1 : 0;
   g->rb = (const Real *) (base + o_rb);          g->sph_R2 = (const Real *) (base + o_R2);
   g->sb = (const Real *) (base + o_sb);          g->cone_cos = (const Real *) (base + o_cc);
   g->cone_cos2 = (const Real *) (base + o_cc2);  g->pts_r = (const Real *) (base + o_pr);
@@ -240,6 +240,31 @@ template void make_grid_sph<double>(int, int, int, int, const double *, int, int
                                     double *, double *, double *);
 template void make_grid_sph<float>(int, int, int, int, const double *, int, int, double *, double *, double *,
                                    double *, double *, double *);
+
+// What plane_parallel_grid::setup_voxels / setup_rays derive from the radial boundaries
+// (grid/grid_plane_parallel.hpp:189-223): geometric-mean voxel points, Gauss-Legendre theta on [0, pi]
+// with weights w sin(theta), phi = 0, domega = w * 2pi / (4 pi) (atmo_ray::set_ray_index atmo_vec.cpp:184-190).
+template <class Real>
+void make_grid_pp(int n_rb, int n_theta, const double *rb_in, double *pts_r, double *ray_t, double *ray_domega) {
+  const Real pi = M_PI;
+  std::vector<Real> rb(n_rb);
+  for (int i = 0; i < n_rb; i++) rb[i] = (Real) rb_in[i];
+  for (int i = 0; i < n_rb - 1; i++) {
+    Real p = ::sqrt(rb[i] * rb[i + 1]);
+    pts_r[i] = p;
+  }
+  std::vector<Real> th(n_theta), wt(n_theta);
+  gauleg<Real>(0, pi, th, wt);
+  for (int i = 0; i < n_theta; i++) wt[i] *= std::sin(th[i]);
+  const Real quarter = 0.25;
+  for (int i = 0; i < n_theta; i++) {
+    Real dom = wt[i] * (2 * pi) * quarter / pi;
+    ray_t[i] = th[i];
+    ray_domega[i] = dom;
+  }
+}
+template void make_grid_pp<double>(int, int, const double *, double *, double *, double *);
+template void make_grid_pp<float>(int, int, const double *, double *, double *, double *);
 
 // observation::add_MSO_observation (observation.hpp:46-65): model = (MSO_z, -MSO_y, MSO_x);
 // atmo_point::xyz (atmo_vec.cpp:51-61); atmo_vector::ptxyz (atmo_vec.cpp:256-290).

@@ -9,7 +9,8 @@
 // What it computes (reference src/, restated; nothing is shared with RT_gpu.cu):
 //   spherical_azimuthally_symmetric_grid::ray_voxel_intersections
 //       grid/grid_spherical_azimuthally_symmetric.hpp:459-509
-//   sphere::intersections / cone::intersections      grid/intersections.cpp:58-95, 120-164
+//   plane_parallel_grid::ray_voxel_intersections     grid/grid_plane_parallel.hpp:268-302 (GridView::pp)
+//   sphere:: / cone:: / plane::intersections         grid/intersections.cpp:58-95, 120-164, 25-46
 //   boundary_set::add_intersections / sort / propagate_indices /
 //       assign_voxel_indices / trim                  grid/boundaries.hpp:131-232
 //   boundary_intersection_stepper::init_stepper      grid/boundaries.hpp:334-349
@@ -103,6 +104,17 @@ __device__ __forceinline__ int sphere_hits(Real r, Real cost, Real R2, Real &fir
     second = in_order ? dd[1] : dd[0];
   }
   return nh;
+}
+
+// plane::intersections (grid/intersections.cpp:25-46): the plane z = zb, at most one hit
+template <class Real>
+__device__ __forceinline__ int plane_hits(Real z, Real lz, Real zb, Real &first, Real &second) {
+  first = second = Lim<Real>::inf();
+  if (lz != 0) {
+    const Real d = (zb - z) / lz;
+    if (d > 0) { first = d; return 1; }
+  }
+  return 0;
 }
 
 template <class Real>
@@ -209,7 +221,8 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
     // ---- pass 1: spheres -> shared, and the keys of the first in-grid entry / first exit
     for (int ir = lane; ir < n_rb; ir += 32) {
       Real f, s;
-      sphere_hits(r, cost, g.sph_R2[ir], f, s);
+      if (g.pp) plane_hits(z, lz, g.rb[ir], f, s);   // plane_parallel_grid::ray_voxel_intersections (grid_plane_parallel.hpp:282-288)
+      else sphere_hits(r, cost, g.sph_R2[ir], f, s);
       sph_d[2 * ir] = f;
       sph_d[2 * ir + 1] = s;
     }

@@ -270,6 +270,7 @@ class Scenario:
     em_scalars: np.ndarray         # [n_em][4] branching, T_ref, sigma_ref, g
     abs_sigma: np.ndarray          # [n_em]
     vox_in: np.ndarray             # [6][n_vox]
+    pp: bool = False               # plane_parallel_grid<n_rb, n_theta> (n_sb = 2, n_phi = 1)
 
     @property
     def n_vox(self):
@@ -296,6 +297,21 @@ def make_scenario(n_rb=40, n_sb=20, n_theta=7, n_phi=12, n_em=2, rmethod=RMETHOD
     sig = [CO2_lyman_alpha_absorption_cross_section, CO2_lyman_beta_absorption_cross_section][:n_em]
     return Scenario(n_rb, n_sb, n_theta, n_phi, rb, atm.rexo, szamethod, raymethod,
                     np.array(em, dtype=np.float64), np.array(sig, dtype=np.float64), vox)
+
+
+def make_scenario_pp(n_rb=40, n_theta=7, n_em=2, nH_exo=5e5, T_exo=200.0, nCO2_exo=2e8,
+                     rmethod=RMETHOD_LOG_N_SPECIES) -> Scenario:
+    """Plane-parallel scenario (reference grid/grid_plane_parallel.hpp; observation_fit uses <40, 7> with
+    rmethod_log_n_species, observation_fit.cpp:28): shell averages are slab averages here
+    (atmosphere_average_1d.cpp:141-157, the non-spherical branch)."""
+    atm = ChamberlainAtmosphere(nH_exo=nH_exo, T_exo=T_exo, nCO2_exo=nCO2_exo)
+    rb = radial_boundaries(atm, n_rb, rmethod)
+    vox = voxel_tables(atm, rb, 2)
+    em = [[1.0, T_exo, atm.sH_lya(T_exo), lyman_alpha_typical_g_factor],
+          [lyman_beta_branching_ratio, T_exo, atm.sH_lyb(T_exo), lyman_beta_typical_g_factor]][:n_em]
+    sig = [CO2_lyman_alpha_absorption_cross_section, CO2_lyman_beta_absorption_cross_section][:n_em]
+    return Scenario(n_rb, 2, n_theta, 1, rb, atm.rexo, SZAMETHOD_UNIFORM_COS, RAYMETHOD_GAUSS,
+                    np.array(em, dtype=np.float64), np.array(sig, dtype=np.float64), vox, pp=True)
 
 
 # ------------------------------------------------------------------ lines of sight

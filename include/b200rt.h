@@ -69,6 +69,18 @@ int b200rt_make_grid_sph(int precision, int n_rb, int n_sb, int n_theta, int n_p
                          double *sza_boundaries, double *pts_radii, double *pts_sza,
                          double *ray_theta, double *ray_phi, double *ray_domega);
 
+/* plane-parallel geometry: replaces RT_grid::RT_to_device() for grid_type = plane_parallel_grid
+ * (grid/grid_plane_parallel.hpp:17-60; observation_fit uses <40, 7>, observation_fit.hpp:48-50,
+ * generate_source_function.cpp <40, 6>, :85-93).  n_vox = n_rb-1; boundaries are the planes
+ * z = radial_boundaries[i] (plane::intersections, intersections.cpp:25-46); voxel points sit on the
+ * +z axis (:204); rays have phi = 0 (:219).  Source function only: the reference has no
+ * interp_weights on this grid (:304-311), so b200rt_brightness* fails with B200RT_ERR_STATE.
+ * make_grid_pp = what setup_voxels()/setup_rays() derive from the boundaries (:189-223). */
+int b200rt_set_grid_pp(b200rt_ctx *ctx, int n_rb, int n_rays, const double *radial_boundaries,
+                       const double *pts_radii, const double *ray_theta, const double *ray_domega);
+int b200rt_make_grid_pp(int precision, int n_rb, int n_theta, const double *radial_boundaries,
+                        double *pts_radii, double *ray_theta, double *ray_domega);
+
 /* ---- emissions ------------------------------------------------------------------
  * replaces singlet_CFR::copy_to_device_influence / copy_to_device_brightness
  * (singlet_CFR.hpp:565-613) + emission_voxels::copy_to_device_* (emission_voxels.hpp:241-268).

@@ -35,6 +35,8 @@ def _load(precision: str):
     lib = C.CDLL(lib_path(precision))
     lib.oracle_create.restype = C.c_void_p
     lib.oracle_create.argtypes = [C.c_int] * 4 + [_dp, C.c_int, C.c_int]
+    lib.oracle_create_pp.restype = C.c_void_p
+    lib.oracle_create_pp.argtypes = [C.c_int, C.c_int, _dp]
     lib.oracle_destroy.argtypes = [C.c_void_p]
     lib.oracle_get_grid.argtypes = [C.c_void_p] + [_dp] * 6
     lib.oracle_define_singlet.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5 + [_dp]
@@ -61,8 +63,11 @@ class OracleModel:
         self.scn = scn
         self.n_vox = scn.n_vox
         self.n_rays = scn.n_rays
-        self.h = self.lib.oracle_create(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi,
-                                        np.ascontiguousarray(scn.rb), scn.szamethod, scn.raymethod)
+        if getattr(scn, "pp", False):      # plane_parallel_grid<n_rb, n_theta>
+            self.h = self.lib.oracle_create_pp(scn.n_rb, scn.n_theta, np.ascontiguousarray(scn.rb))
+        else:
+            self.h = self.lib.oracle_create(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi,
+                                            np.ascontiguousarray(scn.rb), scn.szamethod, scn.raymethod)
         for e in range(scn.n_em):
             b, T, s, g = (float(x) for x in scn.em_scalars[e])
             self.lib.oracle_define_singlet(self.h, e, b, T, s, g, float(scn.abs_sigma[e]),

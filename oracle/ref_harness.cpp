@@ -335,6 +335,132 @@ struct ref_model_impl : ref_model {
   }
 };
 
+// ---- plane-parallel grid (grid/grid_plane_parallel.hpp): source function only -- the reference has no
+// interp_weights on this grid (:304-311), so there is no line-of-sight brightness to pin
+template <int NR, int NTH, int NEM>
+struct ref_model_pp : ref_model {
+  typedef plane_parallel_grid<NR,NTH> grid_type;
+  static const int NV = grid_type::n_voxels;
+  typedef singlet_CFR<NV> emission_type;
+  typedef singlet_peek<NV> peek_type;
+  typedef RT_grid<emission_type, NEM, grid_type> RT_type;
+  typedef boundary_intersection_stepper<grid_type::n_dimensions, grid_type::n_max_intersections> stepper_type;
+
+  table_atmosphere atm;
+  peek_type em[NEM];
+  emission_type *emp[NEM];
+  RT_type *RT;
+  ref_model_pp() : RT(NULL) { for (int e=0;e<NEM;e++) emp[e]=&em[e]; }
+  ~ref_model_pp() { delete RT; }
+  int n_voxels() override { return NV; }
+  int n_rays() override { return grid_type::n_rays; }
+
+  int setup(const double *rb, double rexo, int rmethod, int, int, int n_em, const double *em_scalars,
+	    const double *abs_sigma, const double *vox_in) override {
+    if (n_em != NEM) return -2;
+    atm.nrb = NR;
+    atm.rb.assign(rb, rb+NR);
+    atm.rmin = rb[0]; atm.rexo = rexo; atm.rmax = rb[NR-1];
+    atm.n_avg.assign(vox_in+0*NV, vox_in+1*NV);    atm.n_pt.assign(vox_in+1*NV, vox_in+2*NV);
+    atm.T_avg.assign(vox_in+2*NV, vox_in+3*NV);    atm.T_pt.assign(vox_in+3*NV, vox_in+4*NV);
+    atm.nabs_avg.assign(vox_in+4*NV, vox_in+5*NV); atm.nabs_pt.assign(vox_in+5*NV, vox_in+6*NV);
+    for (int e=0;e<NEM;e++) atm.abs_sigma[e]=abs_sigma[e];
+    delete RT; RT=NULL;
+    grid_type *g = new grid_type;
+    g->rmethod = rmethod;           // 1 = rmethod_log_n_species (boundary injection through table_atmosphere)
+    g->setup_voxels(atm);
+    g->setup_rays();
+    for (int e=0;e<NEM;e++) {
+      const double *s = em_scalars+4*e;
+      char name[32]; snprintf(name, sizeof(name), "emission %d", e);
+      em[e].define(name, (Real) s[0], (Real) s[1], (Real) s[2], atm,
+		   &table_atmosphere::n_species_voxel_avg, &table_atmosphere::Temp_voxel_avg,
+		   &table_atmosphere::n_absorber_voxel_avg,
+		   e==0 ? &table_atmosphere::abs_sigma0 : &table_atmosphere::abs_sigma1,
+		   g->voxels);
+      em[e].set_emission_g_factor((Real) s[3]);
+    }
+    RT = new RT_type(*g, emp);
+    delete g;
+    return 0;
+  }
+  // sza_b / pts_sza / ray_phi are not filled (1-D grid)
+  void get_grid(double *, double *pts_r, double *, double *ray_theta, double *, double *ray_domega, double *rad_b) override {
+    const grid_type &g = RT->grid;
+    for (int i=0;i<NR-1;i++) pts_r[i]=g.pts_radii[i];
+    for (int i=0;i<NTH;i++) { ray_theta[i]=g.rays[i].t; ray_domega[i]=g.rays[i].domega; }
+    for (int i=0;i<NR;i++) rad_b[i]=g.radial_boundaries[i];
+  }
+  void get_arrays(int e, double *out) override { em[e].dump_arrays(out); }
+  long traverse_voxel_rays(int v0, int v1, long cap, int *len, int *exits_bottom, int *entering, double *distance) override {
+    long pos=0;
+    stepper_type *st = new stepper_type;
+    for (int iv=v0; iv<v1; iv++)
+      for (int ir=0; ir<grid_type::n_rays; ir++) {
+	atmo_vector vec;
+	vec.ptray(RT->grid.voxels[iv].pt, RT->grid.rays[ir]);
+	RT->grid.ray_voxel_intersections(vec, *st);
+	long idx = (long)(iv-v0)*grid_type::n_rays+ir;
+	const int n = st->boundaries.size();
+	len[idx] = n;
+	exits_bottom[idx] = (n>0 && st->exits_bottom) ? 1 : 0;
+	for (int k=0;k<n;k++) {
+	  if (pos+k >= cap) { delete st; return -1; }
+	  entering[pos+k] = st->boundaries[k].entering;
+	  distance[pos+k] = st->boundaries[k].distance;
+	}
+	pos += n;
+      }
+    delete st;
+    return pos;
+  }
+  long traverse_los(int, const double *, const double *, long, int *, int *, int *, double *, double *) override { return -1; }
+  double generate_S() override {
+    for (int e=0;e<NEM;e++) em[e].zero_K();
+    double t0 = omp_get_wtime();
+    RT->generate_S();
+    return omp_get_wtime()-t0;
+  }
+  double build_rows(int v0, int v1, int stride, long *n_steps) override {
+    for (int e=0;e<NEM;e++) em[e].zero_K();
+    long steps_total = 0;
+    double t0 = omp_get_wtime();
+    {
+      typename emission_type::influence_tracker ti[NEM];
+      for (int e=0;e<NEM;e++) ti[e].init();
+      atmo_vector vec;
+      stepper_type *st = new stepper_type;
+      for (int i_vox=v0; i_vox<v1; i_vox+=stride) {
+	for (int i_ray=0; i_ray<grid_type::n_rays; i_ray++) {
+	  vec.ptray(RT->grid.voxels[i_vox].pt, RT->grid.rays[i_ray]);
+	  for (int e=0;e<NEM;e++) emp[e]->reset_tracker(i_vox, ti[e]);
+	  RT->voxel_traverse(vec, &RT_type::influence_update, ti);
+	  for (int e=0;e<NEM;e++) emp[e]->accumulate_influence(i_vox, ti[e]);
+	  RT->grid.ray_voxel_intersections(vec, *st);
+	  if (st->boundaries.size()>0) steps_total += st->boundaries.size()-1;
+	}
+	for (int e=0;e<NEM;e++) emp[e]->reset_tracker(i_vox, ti[e]);
+	RT->get_single_scattering(RT->grid.voxels[i_vox].pt, ti);
+      }
+      delete st;
+    }
+    if (n_steps) *n_steps = steps_total;
+    return omp_get_wtime()-t0;
+  }
+  double solve() override { double t0 = omp_get_wtime(); RT->solve(); return omp_get_wtime()-t0; }
+  void get_K(int e, double *out) override { em[e].dump_K(out); }
+  void get_vectors(int e, double *S0, double *tsp, double *tab, double *S) override { em[e].dump_vectors(S0,tsp,tab,S); }
+  void set_sourcefn(int e, const double *S) override { em[e].set_sourcefn(S); }
+  double brightness(int, const double *, const double *, int, double *) override { return -1; }
+};
+
+template <int NR, int NTH>
+ref_model* make_model_pp(int n_em) {
+  if (n_em==1) return new ref_model_pp<NR,NTH,1>;
+  if (n_em==2) return new ref_model_pp<NR,NTH,2>;
+  return NULL;
+}
+
 template <int NR, int NSZA, int NTH, int NPH>
 ref_model* make_model(int n_em) {
   if (n_em==1) return new ref_model_impl<NR,NSZA,NTH,NPH,1>;
@@ -360,6 +486,15 @@ void* ref_create(int NR, int NSZA, int NTH, int NPH, int n_em) {
 #define X(a,b,c,d) if (NR==a && NSZA==b && NTH==c && NPH==d) return make_model<a,b,c,d>(n_em);
   REF_SHAPES
 #undef X
+  return NULL;
+}
+// plane-parallel shapes: observation_fit's <40, 7> (observation_fit.hpp:44-50), generate_source_function.cpp's
+// <40, 6> (:85-93) and two small test grids
+#define REF_PP_SHAPES Y(40,7) Y(40,6) Y(12,5) Y(8,4)
+void* ref_create_pp(int NR, int NTH, int n_em) {
+#define Y(a,c) if (NR==a && NTH==c) return make_model_pp<a,c>(n_em);
+  REF_PP_SHAPES
+#undef Y
   return NULL;
 }
 void ref_destroy(void *h) { delete static_cast<ref_model*>(h); }

@@ -33,6 +33,8 @@ def _load(precision: str):
     lib = C.CDLL(lib_path(precision))
     lib.ref_create.restype = C.c_void_p
     lib.ref_create.argtypes = [C.c_int] * 5
+    lib.ref_create_pp.restype = C.c_void_p
+    lib.ref_create_pp.argtypes = [C.c_int] * 3
     lib.ref_destroy.argtypes = [C.c_void_p]
     lib.ref_n_voxels.argtypes = [C.c_void_p]
     lib.ref_n_rays.argtypes = [C.c_void_p]
@@ -66,7 +68,10 @@ class RefModel:
     def __init__(self, scn, precision: str = "f64", rmethod_inject: bool = True):
         self.lib = _load(precision)
         self.scn = scn
-        self.h = self.lib.ref_create(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.n_em)
+        if getattr(scn, "pp", False):      # plane_parallel_grid<n_rb, n_theta>
+            self.h = self.lib.ref_create_pp(scn.n_rb, scn.n_theta, scn.n_em)
+        else:
+            self.h = self.lib.ref_create(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.n_em)
         if not self.h:
             raise ValueError(f"grid shape {(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi)} x{scn.n_em} "
                              "is not instantiated in oracle/ref_harness.cpp")

@@ -62,6 +62,7 @@ static const REAL lambda_max = RL(4.0);  /* los_tracker.hpp:123 */
 
 typedef struct {
   int n_rb, n_sb, n_theta, n_phi, n_vox, n_rays, cap;
+  int pp;   /* 1 = plane_parallel_grid (grid/grid_plane_parallel.hpp): n_sb = 2, planes z = rb[i] */
   REAL rmin, rmax;
   REAL *rb, *pts_r, *log_pts_r, *sph_R, *sph_R2;        /* radial */
   REAL *sb, *pts_s, *cone_cos, *cone_cos2;              /* sza    */
@@ -167,6 +168,44 @@ void* oracle_create(int n_rb, int n_sb, int n_theta, int n_phi,
       m->ray_cost[k]=STD_COS(th[i]); m->ray_sint[k]=STD_SIN(th[i]);   /* atmo_ray::tp */
       m->ray_domega[k]=wt[i]*phi_spacing*RL(0.25)/o_pi;               /* set_ray_index */
     }
+  free(th); free(wt);
+  return m;
+}
+
+/* plane_parallel_grid<NR, NTH>::setup_voxels / setup_rays (grid_plane_parallel.hpp:189-223) from given
+   radial boundaries: voxel i has the point xyz(0,0,pts_radii[i]); rays = Gauss-Legendre in theta on
+   [0, pi] with weights w*sin(theta), phi = 0, domega = w*2pi/(4pi) */
+void* oracle_create_pp(int n_rb, int n_theta, const double *rb_in) {
+  omodel *m = (omodel*) calloc(1, sizeof(omodel));
+  m->pp=1;
+  m->n_rb=n_rb; m->n_sb=2; m->n_theta=n_theta; m->n_phi=1;
+  m->n_vox=n_rb-1; m->n_rays=n_theta; m->cap=n_rb+1;          /* n_max_intersections = n_rb (+ origin slack) */
+  m->rb=ralloc(n_rb); m->pts_r=ralloc(n_rb-1); m->log_pts_r=ralloc(n_rb-1);
+  m->sph_R=ralloc(n_rb); m->sph_R2=ralloc(n_rb);
+  m->sb=ralloc(2); m->pts_s=ralloc(1); m->cone_cos=ralloc(1); m->cone_cos2=ralloc(1);
+  m->vx=ralloc(m->n_vox); m->vy=ralloc(m->n_vox); m->vz=ralloc(m->n_vox); m->vr=ralloc(m->n_vox); m->vt=ralloc(m->n_vox);
+  m->ray_t=ralloc(m->n_rays); m->ray_p=ralloc(m->n_rays); m->ray_cost=ralloc(m->n_rays);
+  m->ray_sint=ralloc(m->n_rays); m->ray_domega=ralloc(m->n_rays);
+  for (int i=0;i<n_rb;i++) m->rb[i]=(REAL) rb_in[i];
+  m->rmin=(REAL) rb_in[0]; m->rmax=(REAL) rb_in[n_rb-1];
+  m->sb[0]=0; m->sb[1]=o_pi;
+  for (int i=0;i<n_rb-1;i++) {
+    m->pts_r[i]=sqrt(m->rb[i]*m->rb[i+1]);                      /* :198 */
+    m->log_pts_r[i]=STD_LOG(m->pts_r[i]);
+    /* atmo_point::xyz(0,0,z) atmo_vec.cpp:51-61 */
+    REAL z=m->pts_r[i];
+    m->vx[i]=0.; m->vy[i]=0.; m->vz[i]=z;
+    m->vr[i]=hypot(hypot((REAL)0.,(REAL)0.),z);
+    m->vt[i]=acos(z/m->vr[i]);
+  }
+  REAL *th=ralloc(n_theta), *wt=ralloc(n_theta);
+  o_gauleg(0, o_pi, th, wt, n_theta);
+  for (int i=0;i<n_theta;i++) wt[i]*=STD_SIN(th[i]);
+  for (int i=0;i<n_theta;i++) {
+    m->ray_t[i]=th[i]; m->ray_p[i]=0.0;
+    m->ray_cost[i]=STD_COS(th[i]); m->ray_sint[i]=STD_SIN(th[i]);
+    m->ray_domega[i]=wt[i]*(2*o_pi)*RL(0.25)/o_pi;
+  }
   free(th); free(wt);
   return m;
 }
@@ -333,8 +372,22 @@ static int o_traverse(const omodel *m, const ovec *v, obnd *b, int *begin_out, i
     if (v->i_voxel<0 || v->i_voxel>m->n_vox-1) { o.idx[0]=o.idx[1]=-1; }
     else { o.idx[0]=v->i_voxel/(m->n_sb-1); o.idx[1]=v->i_voxel%(m->n_sb-1); }
   }
+  if (m->pp) {   /* plane_parallel_grid::point_to_indices / voxel_to_indices: one dimension */
+    if (v->i_voxel==-1) { o.idx[0]=o_find(v->r, m->rb, m->n_rb); o.idx[1]=0; o.entering=o_vox(m,o.idx[0],0); }
+    else { o.idx[1]=0; }
+  }
   b[n++]=o;
   REAL d[2]={-1,-1}; int nh=0;
+  if (m->pp) {   /* plane::intersections intersections.cpp:25-46, grid_plane_parallel.hpp:282-288 */
+    for (int ir=0;ir<m->n_rb;ir++) {
+      nh=0;
+      if (v->lz != 0) {
+	REAL dd=(m->rb[ir]-v->z)/v->lz;
+	if (dd > 0) { d[nh]=dd; nh++; }
+      }
+      o_add(b,&n,v->r,0,ir,m->rb[ir],d,nh);
+    }
+  } else
   for (int ir=0;ir<m->n_rb;ir++) {
     o_sphere(m,ir,v,d,&nh);
     o_add(b,&n,v->r,0,ir,m->rb[ir],d,nh);
