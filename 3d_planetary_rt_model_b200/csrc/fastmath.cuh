@@ -27,6 +27,9 @@ __constant__ double EXPK[4] = {
 // exp(x) for finite x <= 0 (also correct up to x ~ +700).  Underflows through the denormals to
 // exactly 0 like the host libm: the power of two is applied in two halves.
 __device__ __forceinline__ double exp_nonpos(double x) {
+  // x < -1000 (result 0 either way) is pinned to -1000 with integer compares on the high word, so that the
+  // rint trick below stays in range: a near-horizontal ray of the plane-parallel grid has path lengths ~1e24 cm
+  if ((unsigned) __double2hiint(x) > 0xC08F4000u) x = -1000.0;
   const double t = fma(x, EXPK[0], EXPK[1]);
   int k = __double2loint(t);
   const double kd = t - EXPK[1];

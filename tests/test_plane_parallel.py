@@ -47,6 +47,14 @@ def test_oracle_matches_reference_pp(synth, oraclebind, refbind, prec, shape):
         assert rel_err(Sr, O.vectors(e)["S"], floor=floor) < (1e-7 if prec == "f64" else 1e-3)
 
 
+def underflow_floor(Ka, Kb, prec):
+    """entries at the underflow edge of Real (against row sums of order 1) depend on the order in which the
+    products of a step are formed and are compared as zeros (same rule as tests/test_gpu_parity.py)"""
+    floor = 1e-290 if prec == "f64" else 1e-30
+    assert np.array_equal(np.abs(Ka) > floor, np.abs(Kb) > floor)
+    return np.where(np.abs(Ka) > floor, Ka, 0.0), np.where(np.abs(Kb) > floor, Kb, 0.0)
+
+
 def load_pp_golden(synth, prec):
     z = np.load(os.path.join(HERE, "golden", f"pp40x7_{prec}.npz"))
     scn = synth.Scenario(40, 2, 7, 1, z["rb"], float(z["rexo"]), synth.SZAMETHOD_UNIFORM_COS, synth.RAYMETHOD_GAUSS,
@@ -67,8 +75,7 @@ def check_pp_golden(M, z, prec, exact):
         if exact:
             assert same_bits(K, z[f"K{e}"])
         else:
-            assert np.array_equal(K != 0, z[f"K{e}"] != 0)
-            assert rel_err(K, z[f"K{e}"]) < tol
+            assert rel_err(*underflow_floor(K, z[f"K{e}"], prec)) < tol
         v = M.vectors(e, want_S=False) if not exact else M.vectors(e)
         for k in ("S0", "tau_species_ss", "tau_absorber_ss"):
             assert (same_bits(v[k], z[f"vec{e}_{k}"]) if exact else rel_err(v[k], z[f"vec{e}_{k}"]) < tol), k
@@ -105,7 +112,7 @@ def test_cuda_matches_oracle_pp(synth, binding, oraclebind, prec, shape):
     _, ns_g = G.build_rows()
     assert ns_o == ns_g
     for e in range(2):
-        assert rel_err(O.K(e), G.K(e)) < tol
+        assert rel_err(*underflow_floor(O.K(e), G.K(e), prec)) < tol
         vo, vg = O.vectors(e), G.vectors(e, want_S=False)
         for k in ("S0", "tau_species_ss", "tau_absorber_ss"):
             assert rel_err(vo[k], vg[k]) < tol, k
