@@ -80,11 +80,12 @@ class ChamberlainAtmosphere:
     T_tropo: float = 125.0
     r_tropo: float = rMars + 90e5
     shape: float = 11.4
+    m_species: float = mH              # 16*mH for the O I 102.6 nm scenarios
     _thermo_r: np.ndarray = field(init=False, repr=False, default=None)
 
     def __post_init__(self):
-        self.lambdac = G * mMars * mH / (kB * self.T_exo * self.rexo)
-        veff = 0.5 * math.sqrt(2.0 * kB * self.T_exo / (mH * math.pi)) * (1.0 + self.lambdac) * math.exp(-self.lambdac)
+        self.lambdac = G * mMars * self.m_species / (kB * self.T_exo * self.rexo)
+        veff = 0.5 * math.sqrt(2.0 * kB * self.T_exo / (self.m_species * math.pi)) * (1.0 + self.lambdac) * math.exp(-self.lambdac)
         self.escape_flux = self.nH_exo * veff
         if self.rmax is None:
             lo, hi = self.rexo, self.rexo * 1000.0
@@ -116,7 +117,7 @@ class ChamberlainAtmosphere:
     # exosphere -----------------------------------------------------------
     def _n_exo(self, r):
         r = np.maximum(np.asarray(r, dtype=np.float64), self.rexo)
-        lam = G * mMars * mH / (kB * self.T_exo * r)
+        lam = G * mMars * self.m_species / (kB * self.T_exo * r)
         psi = lam * lam / (lam + self.lambdac)
         frac = (1.0 + _P32(lam) - np.sqrt(np.maximum(1.0 - lam * lam / self.lambdac ** 2, 0.0))
                 * np.exp(-psi) * (1.0 + _P32(lam - psi)))
@@ -135,7 +136,7 @@ class ChamberlainAtmosphere:
             D = T ** 0.6 * 8.4e17 / nCO2
             K = 1.2e12 * math.sqrt(self.T_exo / nCO2)
             Hn_inv = G * mMars * mCO2 / (kB * T * r * r) + Tp / T
-            HH_inv = G * mMars * mH / (kB * T * r * r) + (1 + alpha) * Tp / T
+            HH_inv = G * mMars * self.m_species / (kB * T * r * r) + (1 + alpha) * Tp / T
             dCO2 = -Hn_inv
             dH = -(self.escape_flux * (self.rexo / r) ** 2 / nH + D * HH_inv + K * Hn_inv) / (D + K)
             return np.array([dCO2, dH])
@@ -312,6 +313,56 @@ def make_scenario_pp(n_rb=40, n_theta=7, n_em=2, nH_exo=5e5, T_exo=200.0, nCO2_e
     sig = [CO2_lyman_alpha_absorption_cross_section, CO2_lyman_beta_absorption_cross_section][:n_em]
     return Scenario(n_rb, 2, n_theta, 1, rb, atm.rexo, SZAMETHOD_UNIFORM_COS, RAYMETHOD_GAUSS,
                     np.array(em, dtype=np.float64), np.array(sig, dtype=np.float64), vox, pp=True)
+
+
+# ------------------------------------------------------------------ multiplet emissions
+MULT_O1026, MULT_H_LYMAN, MULT_H_SINGLET = 0, 1, 2      # O_1026_emission, H_lyman_multiplet, H_lyman_singlet
+# (n_lines, n_multiplets, n_lower, n_upper, n_lambda): O_1026_tracker.hpp:12-15,188; H_multiplet_tracker.hpp:12-15,146
+MULT_DIMS = {MULT_O1026: (6, 3, 3, 3, 21), MULT_H_LYMAN: (4, 2, 1, 4, 41), MULT_H_SINGLET: (2, 2, 1, 2, 41)}
+
+
+@dataclass
+class MultipletScenario:
+    """One multiplet CFR emission (reference emission/multiplet_CFR_emission.hpp) on a spherical grid."""
+    kind: int
+    n_rb: int
+    n_sb: int
+    n_theta: int
+    n_phi: int
+    rb: np.ndarray
+    rexo: float
+    szamethod: int
+    raymethod: int
+    solar: np.ndarray              # [2] pumping flux [ph/cm2/s/Hz]: O I: (Lyman beta, -); H: (Lyman alpha, Lyman beta)
+    vox_in: np.ndarray             # [6][n_vox] species avg/pt, temperature avg/pt, absorber avg/pt
+
+    @property
+    def n_vox(self):
+        return (self.n_rb - 1) * (self.n_sb - 1)
+
+    @property
+    def n_rays(self):
+        return self.n_theta * self.n_phi
+
+    @property
+    def dims(self):
+        return MULT_DIMS[self.kind]
+
+
+def make_multiplet_scenario(kind, n_rb=40, n_sb=20, n_theta=7, n_phi=12, sza_T_contrast=0.0,
+                            szamethod=SZAMETHOD_UNIFORM_COS, raymethod=RAYMETHOD_UNIFORM) -> MultipletScenario:
+    """BASELINE.json configs[4] (ii)/(iii).  O I: nO_exo = 2e7, T = 200 K, rmin = rMars + 100 km, solar Lyman beta
+    1.69e-3 ph/cm2/s/Hz (generate_source_function.cpp:27,43-47,132; observation_fit.cpp:656-708).
+    H: the config-1 atmosphere with the typical line-centre fluxes at Mars (constants.hpp:40-63)."""
+    if kind == MULT_O1026:
+        atm = ChamberlainAtmosphere(nH_exo=2e7, T_exo=200.0, nCO2_exo=2e8, rmin=rMars + 100e5, m_species=16 * mH)
+        solar = np.array([1.69e-3, 0.0])
+    else:
+        atm = ChamberlainAtmosphere()
+        solar = np.array([lyman_alpha_flux_Mars_typical, lyman_beta_flux_Mars_typical])
+    rb = radial_boundaries(atm, n_rb, RMETHOD_ALTITUDE)
+    vox = voxel_tables(atm, rb, n_sb, sza_T_contrast)
+    return MultipletScenario(kind, n_rb, n_sb, n_theta, n_phi, rb, atm.rexo, szamethod, raymethod, solar, vox)
 
 
 # ------------------------------------------------------------------ lines of sight

@@ -73,6 +73,7 @@ typedef struct {
   REAL branching[2], T_ref[2], sigma_ref[2], g_factor[2];
   REAL *arr[2][10];   /* T_ratio, T_ratio_pt, density, density_pt, dtau_sp, dtau_sp_pt, dtau_abs, dtau_abs_pt, abs, abs_pt */
   REAL *K[2], *S0[2], *tau_sp_ss[2], *tau_abs_ss[2], *S[2];
+  void *mult_state;   /* multiplet emission (multiplet_oracle.inc.c), allocated on first use */
 } omodel;
 
 enum { A_TR=0, A_TR_PT, A_N, A_N_PT, A_DTS, A_DTS_PT, A_DTA, A_DTA_PT, A_ABS, A_ABS_PT };
@@ -210,6 +211,7 @@ void* oracle_create_pp(int n_rb, int n_theta, const double *rb_in) {
   return m;
 }
 
+static void om_free(omodel *m);
 void oracle_destroy(void *h) {
   omodel *m=(omodel*) h;
   if (!m) return;
@@ -220,6 +222,7 @@ void oracle_destroy(void *h) {
     for (int a=0;a<10;a++) free(m->arr[e][a]);
     free(m->K[e]); free(m->S0[e]); free(m->tau_sp_ss[e]); free(m->tau_abs_ss[e]); free(m->S[e]);
   }
+  om_free(m);
   free(m);
 }
 
@@ -781,4 +784,20 @@ void oracle_brightness(void *h, int n_los, const double *loc, const double *dir,
     }
     free(b);
   }
+}
+
+/* ------------------------------------------------------------------ multiplet CFR emissions */
+#include "multiplet_oracle.inc.c"
+static omstate *om_get(omodel *m) {
+  if (!m->mult_state) m->mult_state=calloc(1, sizeof(omstate));
+  return (omstate*) m->mult_state;
+}
+static void om_free(omodel *m) {
+  omstate *s=(omstate*) m->mult_state;
+  if (!s) return;
+  for (int l=0;l<M_MAXLOW;l++) { free(s->n[l]); free(s->n_pt[l]); }
+  free(s->T); free(s->T_pt); free(s->nabs); free(s->nabs_pt);
+  free(s->K); free(s->S0); free(s->tsp); free(s->tab); free(s->S);
+  free(s);
+  m->mult_state=NULL;
 }
