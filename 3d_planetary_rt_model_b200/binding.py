@@ -35,6 +35,8 @@ SIGNATURES = {
     "b200rt_make_grid_pp": (C.c_int, [C.c_int] * 3 + [_dp] * 4),
     "b200rt_set_singlet": (C.c_int, [_vp, C.c_int, C.c_int] + [C.c_double] * 4 + [_dp] * 8),
     "b200rt_set_g_factor": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "b200rt_multiplet_desc_init": (C.c_int, [C.c_int, C.c_int, _vp]),
+    "b200rt_set_multiplet": (C.c_int, [_vp, _vp] + [_dp] * 6),
     "b200rt_generate_S": (C.c_int, [_vp]),
     "b200rt_influence": (C.c_int, [_vp, C.c_int, C.c_int]),
     "b200rt_solve": (C.c_int, [_vp]),
@@ -62,6 +64,22 @@ SIGNATURES = {
     "b200rt_synchronize": (C.c_int, [_vp]),
     "b200rt_measure_fp64_peaks": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
+
+MAX_LINES = 6
+
+
+class MultipletDesc(C.Structure):
+    """b200rt_multiplet_desc (include/b200rt.h)"""
+    _fields_ = [("kind", C.c_int), ("n_lines", C.c_int), ("n_multiplets", C.c_int), ("n_lower", C.c_int),
+                ("n_upper", C.c_int), ("n_lambda", C.c_int),
+                ("multiplet_index", C.c_int * MAX_LINES), ("lower_level_index", C.c_int * MAX_LINES),
+                ("upper_level_index", C.c_int * MAX_LINES),
+                ("line_sigma_total", C.c_double * MAX_LINES), ("line_A", C.c_double * MAX_LINES),
+                ("absorber_xsec", C.c_double * MAX_LINES), ("upper_state_decay_rate", C.c_double * MAX_LINES),
+                ("offset", C.c_double * MAX_LINES), ("norm", C.c_double * MAX_LINES), ("weight", C.c_double * MAX_LINES),
+                ("T_ref", C.c_double), ("lambda_max", C.c_double),
+                ("solar_flux", C.c_double * MAX_LINES), ("pumped", C.c_int * MAX_LINES)]
+
 
 _lib = None
 
@@ -162,12 +180,34 @@ class Context:
 
     # ---- emissions
     def set_singlet(self, e, n_em, branching, T_ref, sigma_ref, g, tabs):
+        self.mult = None
         """tabs: dict with the eight per-voxel tables of singlet_CFR (names as in the reference)"""
         names = ("T_ratio", "density", "dtau_species", "dtau_absorber",
                  "T_ratio_pt", "density_pt", "dtau_species_pt", "dtau_absorber_pt")
         arrs = [np.ascontiguousarray(tabs[k], dtype=np.float64) for k in names]
         self._ck(self.lib.b200rt_set_singlet(self.h, e, n_em, branching, T_ref, sigma_ref, g, *arrs))
         self.n_em = n_em
+
+    def multiplet_desc(self, kind, solar):
+        """tracker constants of the reference for `kind` + the pumping fluxes: O I: solar[0] = Lyman beta flux on
+        every line; H: solar[0] on the Lyman alpha lines, solar[1] on the Lyman beta lines"""
+        load()
+        d = MultipletDesc()
+        rc = self.lib.b200rt_multiplet_desc_init(kind, self.precision, C.byref(d))
+        if rc != 0:
+            raise B200RTError(f"b200rt_multiplet_desc_init: status {rc}")
+        for l in range(d.n_lines):
+            d.solar_flux[l] = float(solar[0]) if (kind == 0 or d.multiplet_index[l] == 0) else float(solar[1])
+        return d
+
+    def set_multiplet(self, desc, tabs):
+        """tabs: species_density[_pt] [n_lower][n_vox], species_T[_pt], absorber_density[_pt] [n_vox]"""
+        names = ("species_density", "species_density_pt", "species_T", "species_T_pt", "absorber_density",
+                 "absorber_density_pt")
+        arrs = [np.ascontiguousarray(tabs[k], dtype=np.float64).ravel() for k in names]
+        self._ck(self.lib.b200rt_set_multiplet(self.h, C.byref(desc), *arrs))
+        self.mult = desc
+        self.n_em = 1
 
     # ---- source function
     def generate_S(self):
@@ -185,13 +225,18 @@ class Context:
         return n.value
 
     def solution(self, e, want_S=True):
-        S = np.zeros(self.n_vox) if want_S else None
-        S0, tsp, tab = np.zeros(self.n_vox), np.zeros(self.n_vox), np.zeros(self.n_vox)
+        m = getattr(self, "mult", None)
+        n_el = self.n_vox * (m.n_upper if m else 1)
+        n_ln = self.n_vox * (m.n_lines if m else 1)
+        S = np.zeros(n_el) if want_S else None
+        S0, tsp, tab = np.zeros(n_el), np.zeros(n_ln), np.zeros(n_ln)
         self._ck(self.lib.b200rt_get_solution(self.h, e, _ptr(S), _ptr(S0), _ptr(tsp), _ptr(tab)))
         return dict(S=S, S0=S0, tau_species_ss=tsp, tau_absorber_ss=tab)
 
     def influence_matrix(self, e, layout=ROW_MAJOR):
-        K = np.zeros((self.n_vox, self.n_vox))
+        m = getattr(self, "mult", None)
+        n_el = self.n_vox * (m.n_upper if m else 1)
+        K = np.zeros((n_el, n_el))
         self._ck(self.lib.b200rt_get_influence(self.h, e, layout, K))
         return K
 
@@ -221,7 +266,7 @@ class Context:
     def brightness(self, los, n_subsamples=10):
         """host buffers in, host buffers out: the reference-facing call (brightness_gpu)."""
         n = len(los[0])
-        out = [np.zeros((self.n_em, n)) for _ in range(4)]
+        out = [np.zeros((r, n)) for r in self._out_rows()]
         self._ck(self.lib.b200rt_brightness(self.h, n, *los, n_subsamples, *[_ptr(o) for o in out]))
         self.n_los = n
         return dict(brightness=out[0], tau_species_final=out[1], tau_absorber_final=out[2], species_col_dens=out[3])
@@ -233,8 +278,12 @@ class Context:
     def brightness_resident(self, n_subsamples=10):
         self._ck(self.lib.b200rt_brightness_resident(self.h, n_subsamples))
 
+    def _out_rows(self):
+        m = getattr(self, "mult", None)
+        return (m.n_lines, m.n_lines, m.n_lines, m.n_lower) if m else (self.n_em,) * 4
+
     def los_download(self):
-        out = [np.zeros((self.n_em, self.n_los)) for _ in range(4)]
+        out = [np.zeros((r, self.n_los)) for r in self._out_rows()]
         self._ck(self.lib.b200rt_los_download(self.h, *[_ptr(o) for o in out]))
         return dict(brightness=out[0], tau_species_final=out[1], tau_absorber_final=out[2], species_col_dens=out[3])
 
@@ -381,3 +430,85 @@ class GpuModel:
         r = self.ctx.brightness(los, n_subsamples)
         out = np.stack([r["brightness"], r["tau_species_final"], r["tau_absorber_final"], r["species_col_dens"]], axis=1)
         return self.ctx.kernel_ms(PH_BRIGHTNESS)[0] * 1e-3, out
+
+
+def define_multiplet_tables(scn, precision=F64):
+    """Host restatement of O_1026_emission::define (reference emission/O_1026.hpp:134-217: Boltzmann populations of
+    the three J levels of the O I ground term) and H_lyman_multiplet::define (emission/H_lyman_multiplet.hpp:160-217),
+    evaluated in the arithmetic of `precision`."""
+    rt = np.float64 if precision == F64 else np.float32
+    n_avg, n_pt, T_avg, T_pt, a_avg, a_pt = (scn.vox_in[k].astype(rt) for k in range(6))
+    if scn.kind == 0:
+        kB, erg_per_eV = rt(1.38e-16), rt(1.60218e-12)
+        E = [rt(0.0281416) * erg_per_eV, rt(0.0196224) * erg_per_eV, rt(0.0) * erg_per_eV]   # O_1026_tracker.hpp:103-110
+        gw = [rt(1), rt(3), rt(5)]
+
+        def pops(T, bulk):
+            fr = [gw[l] * np.exp(-E[l] / kB / T) for l in range(3)]
+            tot = fr[0] + fr[1] + fr[2]
+            return np.stack([(fr[l] / tot) * bulk for l in range(3)])
+        dens, dens_pt = pops(T_avg, n_avg), pops(T_pt, n_pt)
+    else:
+        dens, dens_pt = n_avg[None, :], n_pt[None, :]
+    tabs = dict(species_density=dens, species_density_pt=dens_pt, species_T=T_avg, species_T_pt=T_pt,
+                absorber_density=a_avg, absorber_density_pt=a_pt)
+    return {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in tabs.items()}
+
+
+class GpuMultiplet:
+    """One MultipletScenario (synth.py) on one GPU, with the vocabulary of oracle/multbind.py."""
+
+    def __init__(self, scn, precision="f64", device=0):
+        self.scn = scn
+        self.prec = F64 if precision == "f64" else F32
+        self.ctx = Context(device, self.prec)
+        self.g = self.ctx.make_grid(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.rb, scn.szamethod, scn.raymethod)
+        self.ctx.set_grid(self.g)
+        self.desc = self.ctx.multiplet_desc(scn.kind, scn.solar)
+        self.tabs = define_multiplet_tables(scn, self.prec)
+        self.ctx.set_multiplet(self.desc, self.tabs)
+        d = self.desc
+        self.n_vox, self.n_rays = self.ctx.n_vox, self.ctx.n_rays
+        self.n_lines, self.n_mult, self.n_lower, self.n_upper, self.n_lambda = (d.n_lines, d.n_multiplets, d.n_lower,
+                                                                                  d.n_upper, d.n_lambda)
+        self.n_el = self.n_vox * self.n_upper
+
+    def constants(self):
+        d, NL = self.desc, self.desc.n_lines
+        a = lambda f, dt=np.float64, n=NL: np.array(list(f)[:n], dtype=dt)
+        return dict(multiplet_index=a(d.multiplet_index, np.int32), lower_level_index=a(d.lower_level_index, np.int32),
+                    upper_level_index=a(d.upper_level_index, np.int32), line_sigma_total=a(d.line_sigma_total),
+                    line_A=a(d.line_A), absorber_xsec=a(d.absorber_xsec),
+                    upper_state_decay_rate=a(d.upper_state_decay_rate, n=d.n_upper), offset=a(d.offset), norm=a(d.norm),
+                    weight=a(d.weight))
+
+    def arrays(self):
+        t, out = self.tabs, {}
+        for l in range(self.n_lower):
+            out[f"species_density_{l}"], out[f"species_density_pt_{l}"] = t["species_density"][l], t["species_density_pt"][l]
+        out.update(species_T=t["species_T"], species_T_pt=t["species_T_pt"], absorber_density=t["absorber_density"],
+                   absorber_density_pt=t["absorber_density_pt"])
+        return out
+
+    def build_rows(self, v0=0, v1=None):
+        self.ctx.influence(v0, v1)
+        return self.ctx.kernel_ms(PH_INFLUENCE)[0] * 1e-3, self.ctx.last_step_count()
+
+    def solve(self):
+        self.ctx.solve()
+        return self.ctx.residual(0)
+
+    def K(self):
+        return self.ctx.influence_matrix(0)
+
+    def vectors(self, want_S=True):
+        r = self.ctx.solution(0, want_S)
+        if r["S"] is None:
+            r["S"] = np.zeros(self.n_el)
+        return r
+
+    def set_sourcefn(self, S):
+        self.ctx.set_sourcefn(0, S)
+
+    def brightness(self, locs, dirs, n_subsamples=10):
+        return self.ctx.brightness(self.ctx.los_from_MSO(locs, dirs), n_subsamples)

@@ -410,6 +410,223 @@ int set_singlet_impl(b200rt_ctx *c, int e, const double *const arr[8]) {
 
 bool is64(const b200rt_ctx *c) { return c->precision == B200RT_F64; }
 
+// ------------------------------------------------------------------ multiplet emission
+template <class Real>
+MultView<Real> mult_view(b200rt_ctx *c) {
+  Multiplet &M = c->mult;
+  const size_t n = c->hg.n_vox;
+  Real *t = M.tabs.as<Real>();
+  MultView<Real> v;
+  v.T = t; v.T_pt = t + n; v.nabs = t + 2 * n; v.nabs_pt = t + 3 * n;
+  for (int l = 0; l < MULT_MAX_LOWER; l++) { v.n[l] = t + (4 + l) * n; v.n_pt[l] = t + (7 + l) * n; }
+  v.rec_step = M.rec_step.as<Real>(); v.rec_org = M.rec_org.as<Real>(); v.rec_w0 = M.rec_w0.as<Real>();
+  v.tsv = M.tsv.as<Real>(); v.tav = M.tav.as<Real>();
+  v.S = M.S_real.as<Real>();
+  v.rec_pt = M.rec_pt.as<Real>(); v.rec_avg = M.rec_avg.as<Real>();
+  return v;
+}
+
+template <class Real>
+int set_multiplet_impl(b200rt_ctx *c, const double *const arr[6]) {
+  Multiplet &M = c->mult;
+  const b200rt_multiplet_desc &d = M.d;
+  const size_t n = c->hg.n_vox, ne = n * d.n_upper;
+  const size_t nlp = (d.n_lambda + MULT_LPR - 1) / MULT_LPR, slots = n * MULT_LPR * nlp;
+  B200RT_CUDA(c, M.tabs.ensure(10 * n * sizeof(Real)));
+  B200RT_CUDA(c, cudaMemsetAsync(M.tabs.p, 0, 10 * n * sizeof(Real), c->stream));
+  B200RT_CUDA(c, M.rec_step.ensure(slots * (d.n_multiplets + d.n_lines) * sizeof(Real)));
+  B200RT_CUDA(c, M.rec_org.ensure(slots * d.n_lines * sizeof(Real)));
+  B200RT_CUDA(c, M.rec_w0.ensure(slots * d.n_lines * sizeof(Real)));
+  B200RT_CUDA(c, M.tsv.ensure(n * d.n_lines * sizeof(Real)));
+  B200RT_CUDA(c, M.tav.ensure(n * d.n_lines * sizeof(Real)));
+  B200RT_CUDA(c, M.K.ensure(ne * ne * sizeof(double)));
+  B200RT_CUDA(c, M.S0.ensure(ne * sizeof(double)));
+  B200RT_CUDA(c, M.S.ensure(ne * sizeof(double)));
+  B200RT_CUDA(c, M.S_real.ensure(ne * sizeof(Real)));
+  B200RT_CUDA(c, M.tau_sp.ensure(n * d.n_lines * sizeof(double)));
+  B200RT_CUDA(c, M.tau_abs.ensure(n * d.n_lines * sizeof(double)));
+  B200RT_CUDA(c, M.rec_pt.ensure(n * MULT_REC * sizeof(Real)));
+  B200RT_CUDA(c, M.rec_avg.ensure(n * MULT_REC * sizeof(Real)));
+  Real *t = M.tabs.as<Real>();
+  DevBuf stage;
+  int rc = B200RT_OK;
+  // arr: species_density [n_lower][n], species_density_pt, T, T_pt, absorber, absorber_pt
+  for (int l = 0; l < d.n_lower && rc == B200RT_OK; l++) {
+    rc = upload_real<Real>(c, arr[0] + (size_t) l * n, t + (4 + l) * n, n, stage);
+    if (rc == B200RT_OK) rc = upload_real<Real>(c, arr[1] + (size_t) l * n, t + (7 + l) * n, n, stage);
+  }
+  for (int a = 0; a < 4 && rc == B200RT_OK; a++) rc = upload_real<Real>(c, arr[2 + a], t + (size_t) a * n, n, stage);
+  if (rc == B200RT_OK) {
+    cudaError_t er = launch_mult_tables<Real>(d, mult_view<Real>(c), (int) n, c->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(c->stream);
+    if (er != cudaSuccess) rc = fail(c, B200RT_ERR_CUDA, cudaGetErrorString(er));
+  }
+  stage.release();
+  return rc;
+}
+
+template <class Real>
+int mult_influence_impl(b200rt_ctx *c, int v_begin, int v_end) {
+  GridView<Real> &g = gv<Real>(c);
+  Multiplet &M = c->mult;
+  const b200rt_multiplet_desc &d = M.d;
+  const int n_vox = g.n_vox;
+  const size_t ne = (size_t) n_vox * d.n_upper;
+  PhaseTimer::reset(c);
+  B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  B200RT_CUDA(c, cudaMemsetAsync(c->step_counter.p, 0, sizeof(unsigned long long), c->stream));
+  if (v_end > v_begin)
+    B200RT_CUDA(c, cudaMemsetAsync(M.K.as<double>() + (size_t) v_begin * d.n_upper * ne, 0,
+                                   (size_t) (v_end - v_begin) * d.n_upper * ne * sizeof(double), c->stream));
+  const long long cap_rays = batch_capacity(c, sizeof(Real));
+  const int vox_per_batch = (int) std::max<long long>(1, std::min<long long>(cap_rays / g.n_rays, v_end - v_begin));
+  ListView<Real> lv;
+  const long long need = std::max<long long>((long long) vox_per_batch * g.n_rays, n_vox);
+  if (int rc = ensure_lists<Real>(c, need, &lv)) return rc;
+  int *overflow = c->work_counter.as<int>() + 1;
+  MultView<Real> mv = mult_view<Real>(c);
+  for (int vb = v_begin; vb < v_end; vb += vox_per_batch) {
+    const int ve = std::min(v_end, vb + vox_per_batch);
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_voxel_rays<Real>(g, vb, ve, lv, overflow, c->stream));
+      t.stop(1);
+    }
+    {
+      PhaseTimer t(c, PH_INFLUENCE);
+      B200RT_CUDA(c, launch_mult_influence<Real>(d, g, mv, vb, ve, lv, M.K.as<double>(), c->work_counter.as<int>(),
+                                                 c->step_counter.as<unsigned long long>(), c->stream));
+      t.stop(1);
+      DBG(c, "multiplet influence march");
+    }
+  }
+  {
+    const Real *sp = c->sun_rays.as<Real>();
+    RayList<Real> rl;
+    rl.r = sp + 0 * (size_t) n_vox; rl.z = sp + 1 * (size_t) n_vox; rl.t = sp + 2 * (size_t) n_vox;
+    rl.cost = sp + 3 * (size_t) n_vox; rl.lz = sp + 4 * (size_t) n_vox;
+    const int *ip = reinterpret_cast<const int *>(sp + 5 * (size_t) n_vox);
+    rl.i_voxel = ip;
+    const int *shadow = ip + n_vox;
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, n_vox, lv, overflow, c->stream));
+      t.stop(1);
+    }
+    {
+      PhaseTimer t(c, PH_INFLUENCE);
+      B200RT_CUDA(c, cudaMemsetAsync(M.S0.p, 0, ne * sizeof(double), c->stream));
+      B200RT_CUDA(c, launch_mult_single_scattering<Real>(d, g, mv, lv, shadow, M.S0.as<double>(), M.tau_sp.as<double>(),
+                                                         M.tau_abs.as<double>(), c->work_counter.as<int>(), c->stream));
+      t.stop(1);
+      DBG(c, "multiplet single scattering");
+    }
+  }
+  unsigned long long steps = 0;
+  B200RT_CUDA(c, cudaMemcpyAsync(&steps, c->step_counter.p, sizeof(steps), cudaMemcpyDeviceToHost, c->stream));
+  if (int rc = check_overflow(c)) return rc;
+  PhaseTimer::collect(c);
+  c->last_steps = (long long) steps;
+  M.have_K = true; M.have_S = false;
+  return B200RT_OK;
+}
+
+int mult_solve_impl(b200rt_ctx *c, bool reset_timer) {
+  Multiplet &M = c->mult;
+  const int ne = c->hg.n_vox * M.d.n_upper;
+  if (reset_timer) PhaseTimer::reset(c);
+  if (!M.have_K) return fail(c, B200RT_ERR_STATE, "b200rt_solve: influence matrix not built");
+  PhaseTimer t(c, PH_SOLVE);
+  SolveResult r = {0, 0, 0};
+  // multiplet_CFR_emission::pre_solve is empty: kernel = I - K (multiplet_CFR_emission.hpp:408; emission_voxels.hpp:170-176)
+  if (int rc = solve_dense(c, ne, M.K.as<double>(), 1.0, M.S0.as<double>(), M.S.as<double>(), &r)) return rc;
+  t.stop(r.launches);
+  M.residual = r.residual;
+  if (c->precision == B200RT_F64) B200RT_CUDA(c, launch_convert<double>(M.S.as<double>(), M.S_real.as<double>(), ne, c->stream));
+  else B200RT_CUDA(c, launch_convert<float>(M.S.as<double>(), M.S_real.as<float>(), ne, c->stream));
+  M.have_S = true;
+  M.rec_dirty = true;
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  PhaseTimer::collect(c);
+  return B200RT_OK;
+}
+
+template <class Real>
+int mult_brightness_impl(b200rt_ctx *c, int n_subsamples) {
+  Multiplet &M = c->mult;
+  const b200rt_multiplet_desc &d = M.d;
+  if (n_subsamples == 1 || n_subsamples < 0)
+    return fail(c, B200RT_ERR_ARG, "n_subsamples must be 0 or > 1 (RT_grid.hpp:237)");
+  if (c->n_los <= 0) return fail(c, B200RT_ERR_STATE, "no lines of sight uploaded");
+  if (c->hg.pp)
+    return fail(c, B200RT_ERR_STATE, "interp_weights not implemented in grid_plane_parallel (grid_plane_parallel.hpp:304-311)");
+  if (!M.have_S) return fail(c, B200RT_ERR_STATE, "source function not available (solve or set_sourcefn first)");
+  GridView<Real> &g = gv<Real>(c);
+  PhaseTimer::reset(c);
+  B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  const long long n = c->n_los;
+  const long long per_batch = std::min<long long>(batch_capacity(c, sizeof(Real)), n);
+  ListView<Real> lv;
+  if (int rc = ensure_lists<Real>(c, per_batch, &lv)) return rc;
+  const size_t n_out = 3 * d.n_lines + d.n_lower;
+  B200RT_CUDA(c, c->los_out.ensure(n_out * n * sizeof(Real)));
+  const Real *li = c->los_in.as<Real>();
+  MultView<Real> mv = mult_view<Real>(c);
+  if (M.rec_dirty) {
+    B200RT_CUDA(c, launch_mult_pack<Real>(d, mv, g.n_vox, c->stream));
+    M.rec_dirty = false;
+  }
+  int *overflow = c->work_counter.as<int>() + 1;
+  for (long long first = 0; first < n; first += per_batch) {
+    const long long count = std::min(per_batch, n - first);
+    RayList<Real> rl;
+    rl.r = li + 3 * n + first; rl.z = li + 2 * n + first; rl.t = li + 4 * n + first;
+    rl.cost = li + 8 * n + first; rl.lz = li + 7 * n + first; rl.i_voxel = nullptr;
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, count, lv, overflow, c->stream));
+      t.stop(1);
+    }
+    {
+      PhaseTimer t(c, PH_BRIGHTNESS);
+      B200RT_CUDA(c, launch_mult_brightness<Real>(d, g, mv, li, n, first, count, lv, n_subsamples, c->los_out.as<Real>(), n,
+                                                  c->work_counter.as<int>(), c->stream));
+      t.stop(1);
+    }
+  }
+  if (int rc = check_overflow(c)) return rc;
+  PhaseTimer::collect(c);
+  c->los_done = true;
+  return B200RT_OK;
+}
+
+// multiplet outputs [3 n_lines + n_lower][n_los] -> brightness, tau_species_final, tau_absorber_final [n_lines][n],
+// species_col_dens [n_lower][n]
+template <class Real>
+int mult_los_download_impl(b200rt_ctx *c, double *const dst[4]) {
+  const long long n = c->n_los;
+  const b200rt_multiplet_desc &d = c->mult.d;
+  const Real *o = c->los_out.as<Real>();
+  const int rows[4] = {d.n_lines, d.n_lines, d.n_lines, d.n_lower};
+  size_t off = 0;
+  for (int q = 0; q < 4; q++) {
+    const size_t cnt = (size_t) rows[q] * n;
+    if (dst[q]) {
+      if (sizeof(Real) == sizeof(double)) {
+        B200RT_CUDA(c, cudaMemcpyAsync(dst[q], o + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      } else {
+        std::vector<float> tmp(cnt);
+        B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), o + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < cnt; i++) dst[q][i] = tmp[i];
+      }
+    }
+    off += cnt;
+  }
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return B200RT_OK;
+}
+
 } // namespace
 
 // ====================================================================== C ABI
@@ -452,6 +669,12 @@ int b200rt_destroy(b200rt_ctx *c) {
     Emission &E = c->em[e];
     DevBuf *eb[] = {&E.tabs, &E.phi, &E.mrec, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real, &E.rec_pt, &E.rec_avg};
     for (DevBuf *b : eb) b->release();
+  }
+  {
+    Multiplet &M = c->mult;
+    DevBuf *mb[] = {&M.tabs, &M.rec_step, &M.rec_org, &M.rec_w0, &M.tsv, &M.tav, &M.K, &M.S0, &M.tau_sp, &M.tau_abs, &M.S,
+                    &M.S_real, &M.rec_pt, &M.rec_avg};
+    for (DevBuf *b : mb) b->release();
   }
   if (c->grid_view) ::operator delete(c->grid_view);
   for (cudaEvent_t ev : c->lu_events) cudaEventDestroy(ev);
@@ -497,6 +720,7 @@ int b200rt_set_grid_sph(b200rt_ctx *c, int n_rb, int n_sb, int n_rays, const dou
   c->have_grid = true;
   c->n_em = 0;
   for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
+  c->mult.defined = c->mult.have_K = c->mult.have_S = false;
   return B200RT_OK;
 }
 
@@ -528,6 +752,7 @@ int b200rt_set_grid_pp(b200rt_ctx *c, int n_rb, int n_rays, const double *rb, co
   c->have_grid = true;
   c->n_em = 0;
   for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
+  c->mult.defined = c->mult.have_K = c->mult.have_S = false;
   return B200RT_OK;
 }
 
@@ -542,11 +767,38 @@ int b200rt_set_singlet(b200rt_ctx *c, int e, int n_em, double branching, double 
   for (auto p : arr) if (!p) return fail(c, B200RT_ERR_ARG, "null emission table");
   cudaSetDevice(c->device);
   c->n_em = n_em;
+  c->mult.defined = false;
   Emission &E = c->em[e];
   E.branching = branching; E.T_ref = T_ref; E.sigma_ref = sigma_ref; E.g_factor = g;
   int rc = is64(c) ? set_singlet_impl<double>(c, e, arr) : set_singlet_impl<float>(c, e, arr);
   if (rc) return rc;
   E.defined = true; E.have_K = false; E.have_S = false; E.residual = -1;
+  return B200RT_OK;
+}
+
+int b200rt_multiplet_desc_init(int kind, int precision, b200rt_multiplet_desc *d) {
+  if (!d || (precision != B200RT_F64 && precision != B200RT_F32)) return B200RT_ERR_ARG;
+  return precision == B200RT_F64 ? multiplet_desc_init<double>(kind, d) : multiplet_desc_init<float>(kind, d);
+}
+
+int b200rt_set_multiplet(b200rt_ctx *c, const b200rt_multiplet_desc *d, const double *species_density,
+                         const double *species_density_pt, const double *species_T, const double *species_T_pt,
+                         const double *absorber_density, const double *absorber_density_pt) {
+  if (!c) return B200RT_ERR_ARG;
+  if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "set the grid before the emissions");
+  const double *arr[6] = {species_density, species_density_pt, species_T, species_T_pt, absorber_density, absorber_density_pt};
+  for (auto p : arr) if (!p) return fail(c, B200RT_ERR_ARG, "null emission table");
+  if (!d || mult_check_desc(*d))
+    return fail(c, B200RT_ERR_ARG, "multiplet descriptor does not match the line / level tables of its kind");
+  cudaSetDevice(c->device);
+  c->n_em = 0;
+  for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
+  Multiplet &M = c->mult;
+  M.d = *d;
+  M.defined = false;
+  int rc = is64(c) ? set_multiplet_impl<double>(c, arr) : set_multiplet_impl<float>(c, arr);
+  if (rc) return rc;
+  M.defined = true; M.have_K = false; M.have_S = false; M.residual = -1; M.rec_dirty = true;
   return B200RT_OK;
 }
 
@@ -558,15 +810,17 @@ int b200rt_set_g_factor(b200rt_ctx *c, int e, double g) {
 
 int b200rt_influence(b200rt_ctx *c, int v_begin, int v_end) {
   if (!c) return B200RT_ERR_ARG;
-  if (!c->have_grid || c->n_em < 1) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
+  if (!c->have_grid || (c->n_em < 1 && !c->mult.defined)) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
   if (v_begin < 0 || v_end > c->hg.n_vox || v_begin > v_end) return fail(c, B200RT_ERR_ARG, "bad voxel range");
   cudaSetDevice(c->device);
+  if (c->mult.defined) return is64(c) ? mult_influence_impl<double>(c, v_begin, v_end) : mult_influence_impl<float>(c, v_begin, v_end);
   return is64(c) ? influence_impl<double>(c, v_begin, v_end) : influence_impl<float>(c, v_begin, v_end);
 }
 
 int b200rt_solve(b200rt_ctx *c) {
   if (!c) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
+  if (c->mult.defined) return mult_solve_impl(c, true);
   return solve_impl(c, true);
 }
 
@@ -574,6 +828,7 @@ int b200rt_generate_S(b200rt_ctx *c) {
   if (!c) return B200RT_ERR_ARG;
   int rc = b200rt_influence(c, 0, c->hg.n_vox);
   if (rc) return rc;
+  if (c->mult.defined) return mult_solve_impl(c, false);
   return solve_impl(c, false);
 }
 
@@ -584,7 +839,24 @@ int b200rt_last_step_count(b200rt_ctx *c, long long *n) {
 }
 
 int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp, double *tab) {
-  if (!c || e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
+  if (!c) return B200RT_ERR_ARG;
+  if (c->mult.defined) {
+    if (e != 0) return B200RT_ERR_ARG;
+    cudaSetDevice(c->device);
+    Multiplet &M = c->mult;
+    const size_t ne = (size_t) c->hg.n_vox * M.d.n_upper * sizeof(double), nl = (size_t) c->hg.n_vox * M.d.n_lines * sizeof(double);
+    if (S) {
+      if (!M.have_S) return fail(c, B200RT_ERR_STATE, "source function not solved");
+      B200RT_CUDA(c, cudaMemcpyAsync(S, M.S.p, ne, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if ((S0 || tsp || tab) && !M.have_K) return fail(c, B200RT_ERR_STATE, "influence pass not run");
+    if (S0) B200RT_CUDA(c, cudaMemcpyAsync(S0, M.S0.p, ne, cudaMemcpyDeviceToHost, c->stream));
+    if (tsp) B200RT_CUDA(c, cudaMemcpyAsync(tsp, M.tau_sp.p, nl, cudaMemcpyDeviceToHost, c->stream));
+    if (tab) B200RT_CUDA(c, cudaMemcpyAsync(tab, M.tau_abs.p, nl, cudaMemcpyDeviceToHost, c->stream));
+    B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return B200RT_OK;
+  }
+  if (e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
   Emission &E = c->em[e];
   const size_t nb = (size_t) c->hg.n_vox * sizeof(double);
@@ -601,17 +873,19 @@ int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp
 }
 
 int b200rt_get_influence(b200rt_ctx *c, int e, int layout, double *K) {
-  if (!c || e < 0 || e >= c->n_em || !K) return B200RT_ERR_ARG;
+  if (!c || !K) return B200RT_ERR_ARG;
+  const bool mm = c->mult.defined;
+  if (mm ? e != 0 : (e < 0 || e >= c->n_em)) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
-  Emission &E = c->em[e];
-  if (!E.have_K) return fail(c, B200RT_ERR_STATE, "influence matrix not built");
-  const size_t n = c->hg.n_vox;
+  if (!(mm ? c->mult.have_K : c->em[e].have_K)) return fail(c, B200RT_ERR_STATE, "influence matrix not built");
+  const size_t n = mm ? (size_t) c->hg.n_vox * c->mult.d.n_upper : (size_t) c->hg.n_vox;
+  const void *Kdev = mm ? c->mult.K.p : c->em[e].K.p;
   if (layout == B200RT_ROW_MAJOR) {
-    B200RT_CUDA(c, cudaMemcpyAsync(K, E.K.p, n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    B200RT_CUDA(c, cudaMemcpyAsync(K, Kdev, n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
   } else {
     std::vector<double> tmp(n * n);
-    B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), E.K.p, n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), Kdev, n * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < n; i++) for (size_t j = 0; j < n; j++) K[j * n + i] = tmp[i * n + j];
   }
@@ -619,7 +893,21 @@ int b200rt_get_influence(b200rt_ctx *c, int e, int layout, double *K) {
 }
 
 int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
-  if (!c || e < 0 || e >= c->n_em || !S) return B200RT_ERR_ARG;
+  if (!c || !S) return B200RT_ERR_ARG;
+  if (c->mult.defined) {
+    if (e != 0) return B200RT_ERR_ARG;
+    cudaSetDevice(c->device);
+    Multiplet &M = c->mult;
+    const int ne = c->hg.n_vox * M.d.n_upper;
+    B200RT_CUDA(c, cudaMemcpyAsync(M.S.p, S, ne * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (is64(c)) B200RT_CUDA(c, launch_convert<double>(M.S.as<double>(), M.S_real.as<double>(), ne, c->stream));
+    else B200RT_CUDA(c, launch_convert<float>(M.S.as<double>(), M.S_real.as<float>(), ne, c->stream));
+    B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    M.have_S = true;
+    M.rec_dirty = true;
+    return B200RT_OK;
+  }
+  if (e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
   Emission &E = c->em[e];
   if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
@@ -634,13 +922,26 @@ int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
 }
 
 int b200rt_last_residual(b200rt_ctx *c, int e, double *r) {
-  if (!c || e < 0 || e >= c->n_em || !r) return B200RT_ERR_ARG;
+  if (!c || !r) return B200RT_ERR_ARG;
+  if (c->mult.defined) { *r = c->mult.residual; return e == 0 ? B200RT_OK : B200RT_ERR_ARG; }
+  if (e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
   *r = c->em[e].residual;
   return B200RT_OK;
 }
 
 int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, void **tab) {
-  if (!c || e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
+  if (!c) return B200RT_ERR_ARG;
+  if (c->mult.defined) {
+    if (e != 0) return B200RT_ERR_ARG;
+    Multiplet &M = c->mult;
+    if (K) *K = M.K.p;
+    if (S0) *S0 = M.S0.p;
+    if (tsp) *tsp = M.tau_sp.p;
+    if (tab) *tab = M.tau_abs.p;
+    M.have_K = true;
+    return B200RT_OK;
+  }
+  if (e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
   Emission &E = c->em[e];
   if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
   if (K) *K = E.K.p;
@@ -652,6 +953,7 @@ int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, 
 }
 
 int b200rt_sourcefn_dev(b200rt_ctx *c, int e, void **S) {
+  if (c && S && c->mult.defined && e == 0) { *S = c->mult.S.p; return B200RT_OK; }
   if (!c || e < 0 || e >= c->n_em || !S) return B200RT_ERR_ARG;
   *S = c->em[e].S.p;
   return B200RT_OK;
@@ -677,8 +979,9 @@ int b200rt_los_upload(b200rt_ctx *c, int n, const double *x, const double *y, co
 
 int b200rt_brightness_resident(b200rt_ctx *c, int n_subsamples) {
   if (!c) return B200RT_ERR_ARG;
-  if (!c->have_grid || c->n_em < 1) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
+  if (!c->have_grid || (c->n_em < 1 && !c->mult.defined)) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
   cudaSetDevice(c->device);
+  if (c->mult.defined) return is64(c) ? mult_brightness_impl<double>(c, n_subsamples) : mult_brightness_impl<float>(c, n_subsamples);
   return is64(c) ? brightness_impl<double>(c, n_subsamples) : brightness_impl<float>(c, n_subsamples);
 }
 
@@ -687,6 +990,7 @@ int b200rt_los_download(b200rt_ctx *c, double *B, double *tsp, double *tab, doub
   if (!c->los_done) return fail(c, B200RT_ERR_STATE, "no brightness result to download");
   cudaSetDevice(c->device);
   double *dst[4] = {B, tsp, tab, col};
+  if (c->mult.defined) return is64(c) ? mult_los_download_impl<double>(c, dst) : mult_los_download_impl<float>(c, dst);
   return is64(c) ? los_download_impl<double>(c, dst) : los_download_impl<float>(c, dst);
 }
 

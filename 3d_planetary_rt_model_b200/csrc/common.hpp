@@ -108,6 +108,42 @@ struct Emission {
   bool rec_dirty = true;    // tables or S changed since the records were packed
 };
 
+// ------------------------------------------------------------------ multiplet CFR emission (multiplet.cu)
+constexpr int MULT_MAX_LINES = B200RT_MAX_LINES, MULT_MAX_LOWER = 3, MULT_MAX_UPPER = 4;
+constexpr int MULT_LPR = 8;      // lanes per ray / line of sight in the multiplet kernels
+constexpr int MULT_REC = 12;     // Reals per voxel record of the multiplet brightness kernel: T, n_abs, n[3], S[4], pad
+
+// numeric line parameters as the kernels take them (by value)
+template <class Real>
+struct MultParams {
+  Real sigma[MULT_MAX_LINES], A[MULT_MAX_LINES], xsec[MULT_MAX_LINES], decay[MULT_MAX_UPPER];
+  Real offset[MULT_MAX_LINES], norm[MULT_MAX_LINES], weight[MULT_MAX_LINES], solar[MULT_MAX_LINES];
+  int pumped[MULT_MAX_LINES];
+  Real T_ref, lambda_max, delta_lambda;
+};
+
+template <class Real>
+struct MultView {
+  const Real *T, *T_pt, *nabs, *nabs_pt;          // [n_vox]
+  const Real *n[MULT_MAX_LOWER], *n_pt[MULT_MAX_LOWER];
+  Real *rec_step;   // [n_vox][8][NLP][n_mult + n_lines]: kappa[m], weight*lineshape/kappa per line (voxel averages)
+  Real *rec_org;    // [n_vox][8][NLP][n_lines]: sigma n0 / decay * lineshape(T0)   (origin factors of G)
+  Real *rec_w0;     // [n_vox][8][NLP][n_lines]: weight * lineshape(T0)             (holstein_T_final)
+  Real *tsv, *tav;  // [n_vox][n_lines]: line-centre optical depths per unit path
+  const Real *S;    // [n_vox * n_upper] source function in Real
+  Real *rec_pt, *rec_avg;   // [n_vox][MULT_REC] brightness records
+};
+
+struct Multiplet {
+  bool defined = false, have_K = false, have_S = false, rec_dirty = true;
+  b200rt_multiplet_desc d;
+  double residual = -1;
+  DevBuf tabs;                       // 10 * n_vox Real: T, T_pt, nabs, nabs_pt, n[3], n_pt[3]
+  DevBuf rec_step, rec_org, rec_w0, tsv, tav;
+  DevBuf K, S0, tau_sp, tau_abs, S;  // double: [n_el][n_el], [n_el], [n_vox*n_lines] x2, [n_el]
+  DevBuf S_real, rec_pt, rec_avg;
+};
+
 enum Phase { PH_TRAVERSE = 0, PH_INFLUENCE = 1, PH_SOLVE = 2, PH_BRIGHTNESS = 3, PH_IPH = 4, PH_COUNT = 5 };
 
 // Quemerais IPH model: tables and the constants of BACKGROUND (ipbackgroundCFR_fun.f:176-235), iph.cu
@@ -137,6 +173,7 @@ struct b200rt_ctx {
 
   int n_em = 0;
   b200rt::Emission em[b200rt::MAX_EMISSIONS];
+  b200rt::Multiplet mult;           // set by b200rt_set_multiplet: the context then carries ONE multiplet emission
 
   // traversal scratch (one batch of rays)
   b200rt::DevBuf list_dist, list_ent, list_len, list_flag;
@@ -221,6 +258,31 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
                               long long n_los_total, int *queue, cudaStream_t s);
 template <class Real>
 cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *rec_pt, Real *rec_avg, cudaStream_t s);
+
+// ---- multiplet.cu
+template <class Real>
+MultParams<Real> mult_params(const b200rt_multiplet_desc &d);
+int mult_check_desc(const b200rt_multiplet_desc &d);     // 0 if the index tables match the kind's compiled-in ones
+template <class Real>
+cudaError_t launch_mult_tables(const b200rt_multiplet_desc &d, MultView<Real> mv, int n_vox, cudaStream_t s);
+template <class Real>
+cudaError_t launch_mult_influence(const b200rt_multiplet_desc &d, const GridView<Real> &g, MultView<Real> mv, int v_begin,
+                                  int v_end, ListView<Real> lists, double *K, int *work_counter,
+                                  unsigned long long *step_counter, cudaStream_t s);
+template <class Real>
+cudaError_t launch_mult_single_scattering(const b200rt_multiplet_desc &d, const GridView<Real> &g, MultView<Real> mv,
+                                          ListView<Real> lists, const int *shadow, double *S0, double *tau_sp,
+                                          double *tau_abs, int *work_counter, cudaStream_t s);
+template <class Real>
+cudaError_t launch_mult_pack(const b200rt_multiplet_desc &d, MultView<Real> mv, int n_vox, cudaStream_t s);
+template <class Real>
+cudaError_t launch_mult_brightness(const b200rt_multiplet_desc &d, const GridView<Real> &g, MultView<Real> mv,
+                                   const Real *los_in, long long los_stride, long long first, long long count,
+                                   ListView<Real> lists, int n_subsamples, Real *out, long long n_los_total, int *queue,
+                                   cudaStream_t s);
+// ---- grid_host.cpp: tracker constants of the reference (O_1026_tracker.hpp, H_multiplet_tracker*.hpp) in Real
+template <class Real>
+int multiplet_desc_init(int kind, b200rt_multiplet_desc *d);
 
 // ---- iph.cu  (compiled with -fmad=false)
 int iph_set_table(b200rt_ctx *c, int kmax, int lmax, int ninf, float temp, const float *alt_au, const float *ang,

@@ -266,6 +266,110 @@ void make_grid_pp(int n_rb, int n_theta, const double *rb_in, double *pts_r, dou
 template void make_grid_pp<double>(int, int, const double *, double *, double *, double *);
 template void make_grid_pp<float>(int, int, const double *, double *, double *, double *);
 
+// ---------------------------------------------------------------- multiplet tracker constants
+// The reference keeps these as constexpr members of its trackers, evaluated by the compiler in Real
+// (O_1026_tracker.hpp:17-216; H_multiplet_tracker.hpp:17-173; H_multiplet_tracker_test.hpp:17-158; constants.hpp:14-22;
+// constexpr_sqrt Real.hpp:63-82).  Restated in the same arithmetic so that a float build sees the float values.
+namespace {
+template <class Real>
+Real newton_sqrt(Real x) {            // Detail::sqrtNewtonRaphson: iterate 0.5*(c + x/c) until it stops changing
+  Real curr = x, prev = 0;
+  while (curr != prev) {
+    const Real next = 0.5 * (curr + x / curr);
+    prev = curr;
+    curr = next;
+  }
+  return curr;
+}
+template <class Real>
+struct Doppler { Real wave, freq, norm; };
+template <class Real>
+Doppler<Real> doppler_block(Real ref_lambda_nm, Real ref_velocity) {
+  const Real clight = 3e10;
+  const Real one_over_sqrt_pi = ((Real) M_2_SQRTPI) / 2.0;
+  Doppler<Real> d;
+  d.wave = ref_lambda_nm * ref_velocity / clight;               // nm
+  d.freq = 1.0 / (ref_lambda_nm * 1e-7) * ref_velocity;         // Hz (double expression, rounded to Real)
+  d.norm = one_over_sqrt_pi / d.freq;                           // 1/Hz
+  return d;
+}
+} // namespace
+
+template <class Real>
+int multiplet_desc_init(int kind, b200rt_multiplet_desc *d) {
+  std::memset(d, 0, sizeof(*d));
+  const Real kB = 1.38e-16, mH = 1.673e-24, line_f_coeff = 2.647e-2;
+  const Real T_ref = 200, lambda_max = 4.0;
+  d->kind = kind;
+  d->T_ref = T_ref;
+  d->lambda_max = lambda_max;
+  if (kind == B200RT_MULT_O1026) {
+    static const int mi[6] = {0, 1, 1, 2, 2, 2}, li[6] = {0, 1, 1, 2, 2, 2}, ui[6] = {0, 0, 1, 0, 1, 2}, lowJ[6] = {0, 1, 1, 2, 2, 2};
+    static const double off[6] = {0.0, 4e-5, -4e-5, 8e-5, 1e-5, -9e-5};
+    static const double A[6] = {4.22e7, 3.17e7, 5.71e7, 2.11e6, 1.91e7, 7.66e7};
+    static const double f[6] = {2.01e-2, 5.02e-3, 1.51e-2, 2.00e-4, 3.01e-3, 1.69e-2};
+    d->n_lines = 6; d->n_multiplets = 3; d->n_lower = 3; d->n_upper = 3; d->n_lambda = 21;
+    const Real vel = newton_sqrt<Real>(2 * kB * T_ref / (16 * mH));
+    const Doppler<Real> dw = doppler_block<Real>((Real) 102.57616, vel);
+    const Real delta_lambda = 2 * lambda_max / (d->n_lambda - 1);
+    for (int l = 0; l < 6; l++) {
+      d->multiplet_index[l] = mi[l]; d->lower_level_index[l] = li[l]; d->upper_level_index[l] = ui[l];
+      d->line_A[l] = (Real) A[l];
+      d->line_sigma_total[l] = line_f_coeff * (Real) f[l];
+      d->absorber_xsec[l] = (Real) 3.53e-17;
+      d->offset[l] = (Real) ((Real) off[l] / dw.wave);
+      d->norm[l] = dw.norm;
+      d->weight[l] = (Real) (delta_lambda * dw.freq);
+      d->pumped[l] = (lowJ[l] == 2);
+    }
+    d->upper_state_decay_rate[0] = (Real) (2.11e6 + 3.17e7 + 4.22e7 + 1.29e7 + 8.6e5 + 1.72e7);
+    d->upper_state_decay_rate[1] = (Real) (1.91e7 + 5.71e7 + 2.32e7 + 7.74e6);
+    d->upper_state_decay_rate[2] = (Real) (7.66e7 + 3.09e7);
+    return B200RT_OK;
+  }
+  if (kind != B200RT_MULT_H_LYMAN && kind != B200RT_MULT_H_SINGLET) return B200RT_ERR_ARG;
+  const bool single = (kind == B200RT_MULT_H_SINGLET);
+  static const double off4[4] = {-2.70365e-4, 2.70365e-4, -5.703e-5, 5.703e-5};
+  static const double A4[4] = {6.2648e8, 6.2649e8, 1.6725e8, 1.6725e8};
+  static const double f4[4] = {0.2776, 0.13881, 5.2761e-2, 2.6381e-2};
+  static const double x4[4] = {6.3e-20, 6.3e-20, 3.53e-17, 3.52e-17};
+  d->n_lines = single ? 2 : 4; d->n_multiplets = 2; d->n_lower = 1; d->n_upper = single ? 2 : 4; d->n_lambda = 41;
+  const Real vel = newton_sqrt<Real>(2 * kB * T_ref / mH);
+  Doppler<Real> dw[2];
+  if (single) {   // line_wavelength = {lyman_alpha_lambda*1e7, lyman_beta_lambda*1e7}: Real * double, rounded to Real
+    const Real la = (Real) 121.6e-7, lb = (Real) 102.6e-7;
+    dw[0] = doppler_block<Real>((Real) (la * 1e7), vel);
+    dw[1] = doppler_block<Real>((Real) (lb * 1e7), vel);
+  } else {
+    dw[0] = doppler_block<Real>((Real) 121.5668237310, vel);
+    dw[1] = doppler_block<Real>((Real) 102.572182505, vel);
+  }
+  const Real delta_lambda = 2 * lambda_max / (d->n_lambda - 1);
+  for (int l = 0; l < d->n_lines; l++) {
+    const int gi = single ? l : (l < 2 ? 0 : 1);   // Lyman alpha or beta
+    d->multiplet_index[l] = gi; d->lower_level_index[l] = 0; d->upper_level_index[l] = l;
+    if (single) {
+      d->line_A[l] = (Real) (l == 0 ? 6.2648e8 : 1.6725e8);
+      d->line_sigma_total[l] = line_f_coeff * (Real) (l == 0 ? 0.2776 + 0.13881 : 5.2761e-2 + 2.6381e-2);
+      d->absorber_xsec[l] = (Real) (l == 0 ? 6.3e-20 : 3.52e-17);
+      d->offset[l] = (Real) ((Real) 0.0 / dw[gi].wave);
+      d->upper_state_decay_rate[l] = (Real) (l == 0 ? 6.2648e8 : 1.6725e8 + 2.2449e7);
+    } else {
+      d->line_A[l] = (Real) A4[l];
+      d->line_sigma_total[l] = line_f_coeff * (Real) f4[l];
+      d->absorber_xsec[l] = (Real) x4[l];
+      d->offset[l] = (Real) ((Real) off4[l] / dw[gi].wave);
+      d->upper_state_decay_rate[l] = (Real) (l == 0 ? 6.2648e8 : l == 1 ? 6.2649e8 : 1.6725e8 + 2.2449e7);
+    }
+    d->norm[l] = dw[gi].norm;
+    d->weight[l] = (Real) (delta_lambda * dw[gi].freq);
+    d->pumped[l] = 1;
+  }
+  return B200RT_OK;
+}
+template int multiplet_desc_init<double>(int, b200rt_multiplet_desc *);
+template int multiplet_desc_init<float>(int, b200rt_multiplet_desc *);
+
 // observation::add_MSO_observation (observation.hpp:46-65): model = (MSO_z, -MSO_y, MSO_x);
 // atmo_point::xyz (atmo_vec.cpp:51-61); atmo_vector::ptxyz (atmo_vec.cpp:256-290).
 template <class Real>

@@ -348,6 +348,27 @@ __global__ void residual_kernel(const double *__restrict__ K, int n, double w, c
   if (lane == 0) rabs[row] = fabs(S0[row] - (S[row] - w * s));
 }
 
+// ---- y_out = w K y_in (one warp per row) and the smallest entry of the row: the M-matrix certificate below
+__global__ void kmatvec_kernel(const double *__restrict__ K, int n, double w, const double *__restrict__ y_in,
+                               double *__restrict__ y_out, double *__restrict__ row_min) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double *Kr = K + (size_t) row * n;
+  double s = 0, mn = 0;
+  for (int j = lane; j < n; j += 32) {
+    const double k = Kr[j];
+    s += k * y_in[j];
+    mn = fmin(mn, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if (lane == 0) { y_out[row] = w * s; if (row_min) row_min[row] = mn; }
+}
+
 template <class Real>
 __global__ void convert_kernel(const double *__restrict__ src, Real *__restrict__ dst, long long n) {
   const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,10 +411,45 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   double min_margin = 1e300;
   for (int i = 0; i < n; i++) min_margin = std::min(min_margin, hm[i]);
   if (res) res->min_margin = min_margin;
-  if (!(min_margin > 0.0))
-    return fail(c, B200RT_ERR_NOT_DOMINANT,
-                "I - w*K is not strictly row diagonally dominant (min margin " + std::to_string(min_margin) +
-                    "): the influence matrix rows are not scattering probabilities");
+  if (!(min_margin > 0.0)) {
+    // Not row dominant as it stands (the multiplet emissions: K[(v0,iu),(v,ju)] carries the ORIGIN voxel's lower-state
+    // density, multiplet_CFR_emission.hpp:264-271, so its rows are probabilities only after a diagonal rescaling).
+    // Certificate instead: K >= 0 and max_i (w K)^m 1 < 1 for some m  =>  rho(w K) < 1  =>  I - w K is a nonsingular
+    // M-matrix: every Schur complement is again one, all pivots are positive, and elimination without row exchanges
+    // is componentwise backward stable (its error bound is invariant under the diagonal rescaling that makes the
+    // matrix row dominant).  x / rabs / margin are free at this point and serve as scratch.
+    bool certified = false;
+    double kmin = 0, ymax = 1e300;
+    std::vector<double> hy(n, 1.0);
+    B200RT_CUDA(c, cudaMemcpyAsync(x, hy.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    double *ya = x, *yb = rabs;
+    const int max_iter = 2048;
+    for (int it = 0; it < max_iter && !certified; it++) {
+      kmatvec_kernel<<<(n + 7) / 8, 256, 0, st>>>(K, n, branching, ya, yb, it == 0 ? margin : nullptr);
+      launches++;
+      std::swap(ya, yb);
+      if (it == 0) {
+        B200RT_CUDA(c, cudaMemcpyAsync(hm.data(), margin, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        B200RT_CUDA(c, cudaStreamSynchronize(st));
+        for (int i = 0; i < n; i++) kmin = std::min(kmin, hm[i]);
+        if (kmin < 0.0 || branching < 0.0) break;
+      }
+      if ((it & 7) == 7 || it == 0) {
+        B200RT_CUDA(c, cudaMemcpyAsync(hy.data(), ya, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        B200RT_CUDA(c, cudaStreamSynchronize(st));
+        ymax = 0;
+        for (int i = 0; i < n; i++) ymax = std::max(ymax, hy[i]);
+        if (ymax < 1.0) certified = true;
+        if (!(ymax < 1e200)) break;    // diverging
+      }
+    }
+    B200RT_CUDA(c, cudaGetLastError());
+    if (!certified)
+      return fail(c, B200RT_ERR_NOT_DOMINANT,
+                  "I - w*K is neither strictly row diagonally dominant (min margin " + std::to_string(min_margin) +
+                      ") nor certifiably an M-matrix (min K entry " + std::to_string(kmin) + ", max (wK)^m 1 = " +
+                      std::to_string(ymax) + "): elimination without row exchanges is not safe");
+  }
 
   const size_t gemm_smem = (size_t) STAGES * (TM * SA + KC * (TN + 4)) * sizeof(double);        // 128x128 tiles
   const size_t gemm_smem_h = (size_t) STAGES * (TM * SA + KC * (TN / 2 + 4)) * sizeof(double);  // 128x64 tiles

@@ -32,7 +32,8 @@ typedef enum {
   B200RT_ERR_STATE = 3,         /* call order: grid / emission / source function not set */
   B200RT_ERR_CAPACITY = 4,      /* a ray produced more boundary crossings than 2*n_rb+n_sb
                                    (boundary_set::append only asserts, boundaries.hpp:153-158) */
-  B200RT_ERR_NOT_DOMINANT = 5,  /* I - w K is not strictly row diagonally dominant */
+  B200RT_ERR_NOT_DOMINANT = 5,  /* I - w K is neither strictly row diagonally dominant nor certifiably an M-matrix
+                                   (K >= 0, rho(w K) < 1): elimination without row exchanges would be unsafe */
   B200RT_ERR_NOMEM = 6
 } b200rt_status;
 
@@ -95,6 +96,46 @@ int b200rt_set_singlet(b200rt_ctx *ctx, int i_emission, int n_emissions,
                        const double *dtau_species_pt, const double *dtau_absorber_pt);
 /* singlet_CFR::set_emission_g_factor, singlet_CFR.hpp:282-284 */
 int b200rt_set_g_factor(b200rt_ctx *ctx, int i_emission, double g);
+
+/* ---- multiplet emissions -----------------------------------------------------------
+ * replaces multiplet_CFR_emission::copy_to_device_influence / copy_to_device_brightness
+ * (emission/multiplet_CFR_emission.hpp:472-512) for the three multiplet emission types of the reference:
+ *   B200RT_MULT_O1026     O_1026_emission      (emission/O_1026.hpp, O_1026_tracker.hpp)   6 lines, 3 multiplets
+ *   B200RT_MULT_H_LYMAN   H_lyman_multiplet    (emission/H_lyman_multiplet.hpp, H_multiplet_tracker.hpp)  4 lines
+ *   B200RT_MULT_H_SINGLET H_lyman_singlet      (emission/H_lyman_multiplet_test.hpp)       2 lines
+ * The descriptor carries the tracker's static tables (CUDA_STATIC_ARRAY_MEMBERs and the constexpr Doppler-width
+ * block, O_1026_tracker.hpp:17-216): b200rt_multiplet_desc_init fills it for `kind` in the arithmetic of
+ * `precision`; offset = line_wavelength_offset / doppler_width_wavelength_reference, norm = line_shape_normalization
+ * at T_ref, weight = tracker.weight().  solar_flux[line] / pumped[line]: compute_single_scattering assigns
+ * singlescat(voxel, upper(line)) = flux n_lower sigma / decay * holstein_T_final[line] for pumped lines
+ * (O_1026.hpp:111-129: the J=2 lines; H_lyman_multiplet.hpp:148-155: every line).
+ * A context carries ONE multiplet emission (the reference's oxygen_RT / ly_multiplet_RT are RT_grid<., 1, .>,
+ * observation_fit.hpp:93-125); b200rt_set_multiplet replaces any singlet emissions.  Per-voxel arrays are the
+ * protected members multiplet_CFR_emission::define fills (:60-66): species_density[_pt] as [n_lower][n_vox].
+ * In multiplet mode the shared entry points keep their meaning with these shapes (n_el = n_vox * n_upper, element
+ * = voxel * n_upper + state, emission_voxels.hpp:32; voxel_vector.hpp:19-21):
+ *   b200rt_get_solution: sourcefn, singlescat [n_el]; tau_*_single_scattering [n_vox * n_lines] (voxel major)
+ *   b200rt_get_influence: [n_el][n_el];  b200rt_set_sourcefn: [n_el]
+ *   b200rt_brightness / b200rt_los_download: brightness, tau_species_final, tau_absorber_final [n_lines][n_los];
+ *                        species_col_dens [n_lower][n_los]   (O_1026_tracker.hpp:163-179) */
+#define B200RT_MAX_LINES 6
+enum { B200RT_MULT_O1026 = 0, B200RT_MULT_H_LYMAN = 1, B200RT_MULT_H_SINGLET = 2 };
+typedef struct {
+  int kind;
+  int n_lines, n_multiplets, n_lower, n_upper, n_lambda;
+  int multiplet_index[B200RT_MAX_LINES], lower_level_index[B200RT_MAX_LINES], upper_level_index[B200RT_MAX_LINES];
+  double line_sigma_total[B200RT_MAX_LINES], line_A[B200RT_MAX_LINES], absorber_xsec[B200RT_MAX_LINES];
+  double upper_state_decay_rate[B200RT_MAX_LINES];   /* indexed by upper state */
+  double offset[B200RT_MAX_LINES], norm[B200RT_MAX_LINES], weight[B200RT_MAX_LINES];
+  double T_ref, lambda_max;
+  double solar_flux[B200RT_MAX_LINES];
+  int pumped[B200RT_MAX_LINES];
+} b200rt_multiplet_desc;
+int b200rt_multiplet_desc_init(int kind, int precision, b200rt_multiplet_desc *desc);
+int b200rt_set_multiplet(b200rt_ctx *ctx, const b200rt_multiplet_desc *desc,
+                         const double *species_density, const double *species_density_pt,
+                         const double *species_T, const double *species_T_pt,
+                         const double *absorber_density, const double *absorber_density_pt);
 
 /* ---- source function ------------------------------------------------------------
  * b200rt_generate_S replaces RT_grid::generate_S_gpu() (RT_gpu.cu:255-309): influence

@@ -111,7 +111,7 @@ class _Common:
         self._f("get_K")(self.h, out)
         return out
 
-    def vectors(self):
+    def vectors(self, want_S=True):
         S0, S = np.zeros(self.n_el), np.zeros(self.n_el)
         tsp, tab = np.zeros(self.n_vox * self.n_lines), np.zeros(self.n_vox * self.n_lines)
         self._f("get_vectors")(self.h, S0, tsp, tab, S)

@@ -128,7 +128,7 @@ def check_golden(M, z, prec, exact):
         floor = 1e-290 if prec == "f64" else 1e-30
         assert np.array_equal(np.abs(K) > floor, np.abs(z["K"]) > floor)
         assert rel_err(np.where(np.abs(K) > floor, K, 0), np.where(np.abs(z["K"]) > floor, z["K"], 0)) < tol
-    v = M.vectors()
+    v = M.vectors(want_S=False)
     for k in ("S0", "tau_species_ss", "tau_absorber_ss"):
         assert same_bits(v[k], z["vec_" + k]) if exact else rel_err(v[k], z["vec_" + k]) < tol, k
     M.solve()
@@ -151,3 +151,103 @@ def check_golden(M, z, prec, exact):
 def test_oracle_reproduces_golden(synth, multbind, kind, prec):
     scn, z = load_golden(synth, kind, prec)
     check_golden(multbind.OracleMultiplet(scn, prec), z, prec, exact=True)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("kind", KINDS)
+def test_product_descriptor_equals_tracker_constants(synth, binding, multbind, kind, prec):
+    """b200rt_multiplet_desc_init (host helper of the product, no GPU needed) restates the trackers' constexpr
+    constants: bit-identical to the oracle's, which is pinned bit for bit to the reference build above"""
+    lib = binding.load()
+    d = binding.MultipletDesc()
+    assert lib.b200rt_multiplet_desc_init(kind, binding.F64 if prec == "f64" else binding.F32, __import__("ctypes").byref(d)) == 0
+    scn = synth.make_multiplet_scenario(kind, 8, 6, 4, 4)
+    O = multbind.OracleMultiplet(scn, prec)
+    c = O.constants()
+    assert (d.n_lines, d.n_multiplets, d.n_lower, d.n_upper, d.n_lambda) == synth.MULT_DIMS[kind]
+    NL = d.n_lines
+    for name, field in (("multiplet_index", d.multiplet_index), ("lower_level_index", d.lower_level_index),
+                        ("upper_level_index", d.upper_level_index)):
+        assert list(field)[:NL] == list(c[name]), name
+    for name, field in (("line_sigma_total", d.line_sigma_total), ("line_A", d.line_A), ("absorber_xsec", d.absorber_xsec),
+                        ("offset", d.offset), ("norm", d.norm), ("weight", d.weight)):
+        assert same_bits(np.array(list(field)[:NL]), c[name]), name
+    assert same_bits(np.array(list(d.upper_state_decay_rate)[:d.n_upper]), c["upper_state_decay_rate"])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_product_define_equals_reference_define(synth, binding, multbind, prec):
+    """binding.define_multiplet_tables (host, numpy) against O_1026_emission::define of the oracle (Boltzmann levels)"""
+    scn = synth.make_multiplet_scenario(0, 12, 8, 5, 6, sza_T_contrast=0.1)
+    t = binding.define_multiplet_tables(scn, binding.F64 if prec == "f64" else binding.F32)
+    a = multbind.OracleMultiplet(scn, prec).arrays()
+    for l in range(3):
+        assert rel_err(t["species_density"][l], a[f"species_density_{l}"]) < (1e-14 if prec == "f64" else 1e-6)
+        assert rel_err(t["species_density_pt"][l], a[f"species_density_pt_{l}"]) < (1e-14 if prec == "f64" else 1e-6)
+
+
+# ------------------------------------------------------------------ CUDA path
+def compare_gpu(synth, O, G, prec, los_sets):
+    tol = TOL[prec]
+    _, ns_o = O.build_rows()
+    _, ns_g = G.build_rows()
+    assert ns_o == ns_g
+    Ko, Kg = O.K(), G.K()
+    floor = 1e-290 if prec == "f64" else 1e-30
+    assert np.array_equal(np.abs(Ko) > floor, np.abs(Kg) > floor)
+    assert rel_err(np.where(np.abs(Ko) > floor, Ko, 0), np.where(np.abs(Kg) > floor, Kg, 0)) < tol
+    vo, vg = O.vectors(), G.vectors(want_S=False)
+    for k in ("S0", "tau_species_ss", "tau_absorber_ss"):
+        assert rel_err(vo[k], vg[k]) < tol, k
+    O.solve()
+    assert G.solve() < 1e-12
+    So = O.vectors()["S"]
+    fl = 1e-30 if prec == "f64" else float(np.abs(So).max())
+    assert rel_err(So, G.vectors()["S"], floor=fl) < tol
+    G.set_sourcefn(So)
+    for locs, dirs in los_sets:
+        for nsub in (10, 0, 4):
+            bo, bg = O.brightness(locs, dirs, nsub), G.brightness(locs, dirs, nsub)
+            for k in bo:
+                assert np.array_equal(bo[k] == -1, bg[k] == -1), (nsub, k)
+                assert rel_err(bo[k], bg[k], floor=1e-300) < (tol if k == "brightness" else 2 * tol), (nsub, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("shape", [(8, 6, 4, 4), (12, 8, 5, 6)])
+def test_cuda_matches_oracle(synth, binding, multbind, prec, kind, shape):
+    scn = synth.make_multiplet_scenario(kind, *shape, sza_T_contrast=0.1)
+    compare_gpu(synth, multbind.OracleMultiplet(scn, prec), binding.GpuMultiplet(scn, prec), prec,
+                [synth.fake_image(30 * synth.rMars, 30, 16), synth.random_los(500)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [0, 1])
+def test_cuda_matches_oracle_default_grid(synth, binding, multbind, kind):
+    """BASELINE.json configs[4] (ii)/(iii): O I 102.6 and the H Lyman multiplet on the reference default grid"""
+    scn = synth.make_multiplet_scenario(kind, 40, 20, 7, 12)
+    compare_gpu(synth, multbind.OracleMultiplet(scn), binding.GpuMultiplet(scn), "f64",
+                [synth.fake_image(30 * synth.rMars, 30, 24)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,prec", GOLDEN)
+def test_cuda_reproduces_golden(synth, binding, kind, prec):
+    scn, z = load_golden(synth, kind, prec)
+    check_golden(binding.GpuMultiplet(scn, prec), z, prec, exact=False)
+
+
+@pytest.mark.gpu
+def test_multiplet_then_singlet_on_one_context(synth, binding, oraclebind):
+    """set_singlet after set_multiplet returns the context to singlet shapes"""
+    scn_m = synth.make_multiplet_scenario(2, 8, 6, 4, 4)
+    G = binding.GpuMultiplet(scn_m)
+    G.build_rows()
+    scn = synth.make_scenario(8, 6, 4, 4, n_em=1)
+    G.ctx.set_singlet(0, 1, *(float(x) for x in scn.em_scalars[0]), binding.define_singlet_tables(scn, 0))
+    G.ctx.influence()
+    O = oraclebind.OracleModel(scn)
+    O.build_rows()
+    assert rel_err(O.K(0), G.ctx.influence_matrix(0)) < 1e-6
