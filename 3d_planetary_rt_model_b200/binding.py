@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200rt_influence": (C.c_int, [_vp, C.c_int, C.c_int]),
     "b200rt_solve": (C.c_int, [_vp]),
     "b200rt_last_step_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
+    "b200rt_last_substep_count": (C.c_int, [_vp, C.POINTER(C.c_longlong)]),
     "b200rt_get_solution": (C.c_int, [_vp] + [C.c_int] + [_vp] * 4),
     "b200rt_get_influence": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "b200rt_set_sourcefn": (C.c_int, [_vp, C.c_int, _dp]),
@@ -222,6 +223,11 @@ class Context:
     def last_step_count(self):
         n = C.c_longlong(0)
         self._ck(self.lib.b200rt_last_step_count(self.h, C.byref(n)))
+        return n.value
+
+    def last_substep_count(self):
+        n = C.c_longlong(0)
+        self._ck(self.lib.b200rt_last_substep_count(self.h, C.byref(n)))
         return n.value
 
     def solution(self, e, want_S=True):

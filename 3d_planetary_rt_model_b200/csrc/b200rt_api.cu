@@ -228,6 +228,7 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
   GridView<Real> &g = gv<Real>(c);
   PhaseTimer::reset(c);
   B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  B200RT_CUDA(c, cudaMemsetAsync(c->step_counter.p, 0, sizeof(unsigned long long), c->stream));
   const long long n = c->n_los;
   const long long per_batch = std::min<long long>(batch_capacity(c, sizeof(Real)), n);
   ListView<Real> lv;
@@ -257,12 +258,16 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
     {
       PhaseTimer t(c, PH_BRIGHTNESS);
       B200RT_CUDA(c, launch_brightness<Real>(g, ev, c->n_em, li, n, first, count, lv, n_subsamples,
-                                             c->los_out.as<Real>(), n, c->work_counter.as<int>(), c->stream));
+                                             c->los_out.as<Real>(), n, c->work_counter.as<int>(),
+                                             c->step_counter.as<unsigned long long>(), c->stream));
       t.stop(1);
     }
   }
+  unsigned long long substeps = 0;
+  B200RT_CUDA(c, cudaMemcpyAsync(&substeps, c->step_counter.p, sizeof(substeps), cudaMemcpyDeviceToHost, c->stream));
   if (int rc = check_overflow(c)) return rc;
   PhaseTimer::collect(c);
+  c->last_substeps = (long long) substeps;
   c->los_done = true;
   return B200RT_OK;
 }
@@ -835,6 +840,12 @@ int b200rt_generate_S(b200rt_ctx *c) {
 int b200rt_last_step_count(b200rt_ctx *c, long long *n) {
   if (!c || !n) return B200RT_ERR_ARG;
   *n = c->last_steps;
+  return B200RT_OK;
+}
+
+int b200rt_last_substep_count(b200rt_ctx *c, long long *n) {
+  if (!c || !n) return B200RT_ERR_ARG;
+  *n = c->last_substeps;
   return B200RT_OK;
 }
 

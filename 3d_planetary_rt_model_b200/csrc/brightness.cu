@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128, (NEM == 2 && sizeof(Real) == 8) ? 3 : 4)
 brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> em1,
                   const Real *__restrict__ los_in, long long los_stride, long long first, long long count,
                   ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total,
-                  int *queue) {
+                  int *queue, unsigned long long *substep_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_rb = g.n_rb, n_sb = g.n_sb, n_sb1 = n_sb - 1;
   Real *s_rb = reinterpret_cast<Real *>(smem_raw);   // [n_rb]
@@ -166,6 +166,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
   const int *el = nullptr;
   Real px = 0, py = 0, pz = 0, lx = 0, ly = 0, lz = 0;   // px, py, pz already divided by the 1e9 scale
   Real P[NEM][NLL], acc_B[NEM], acc_tsp[NEM], acc_tab[NEM], acc_col[NEM];
+  unsigned long long my_substeps = 0;
 
   while (true) {
     // ---- groups without work pull the next line of sight
@@ -186,6 +187,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
         continue;
       }
       total = (len - 1) * nss;
+      if (sub == 0) my_substeps += (unsigned long long) total;
       flagbits = lists.flag[t];
       dl = lists.dist + (size_t) t * lists.cap;
       el = lists.ent + (size_t) t * lists.cap;
@@ -296,6 +298,11 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       have = false;
     }
   }
+  if (substep_counter) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_substeps += __shfl_xor_sync(0xffffffffu, my_substeps, o);
+    if (lane == 0 && my_substeps) atomicAdd(substep_counter, my_substeps);
+  }
 }
 
 } // namespace
@@ -313,7 +320,8 @@ cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *r
 template <class Real>
 cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em, const Real *los_in,
                               long long los_stride, long long first, long long count, ListView<Real> lists,
-                              int n_subsamples, Real *out, long long n_los_total, int *queue, cudaStream_t s) {
+                              int n_subsamples, Real *out, long long n_los_total, int *queue,
+                              unsigned long long *substep_counter, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
@@ -327,21 +335,21 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
     e = cudaFuncSetAttribute(brightness_kernel<Real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     brightness_kernel<Real, 1><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[0], los_in, los_stride, first, count,
-                                                                        lists, n_subsamples, out, n_los_total, queue);
+                                                                        lists, n_subsamples, out, n_los_total, queue, substep_counter);
   } else {
     e = cudaFuncSetAttribute(brightness_kernel<Real, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     brightness_kernel<Real, 2><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[1], los_in, los_stride, first, count,
-                                                                        lists, n_subsamples, out, n_los_total, queue);
+                                                                        lists, n_subsamples, out, n_los_total, queue, substep_counter);
   }
   return cudaGetLastError();
 }
 template cudaError_t launch_brightness<double>(const GridView<double> &, const EmissionView<double> *, int,
                                                const double *, long long, long long, long long, ListView<double>, int,
-                                               double *, long long, int *, cudaStream_t);
+                                               double *, long long, int *, unsigned long long *, cudaStream_t);
 template cudaError_t launch_brightness<float>(const GridView<float> &, const EmissionView<float> *, int, const float *,
                                               long long, long long, long long, ListView<float>, int, float *,
-                                              long long, int *, cudaStream_t);
+                                              long long, int *, unsigned long long *, cudaStream_t);
 template cudaError_t launch_pack_records<double>(const EmissionView<double> &, int, double *, double *, cudaStream_t);
 template cudaError_t launch_pack_records<float>(const EmissionView<float> &, int, float *, float *, cudaStream_t);
 

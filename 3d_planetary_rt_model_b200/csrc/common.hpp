@@ -181,6 +181,7 @@ struct b200rt_ctx {
   b200rt::DevBuf work_counter;      // 2 ints: dynamic work index, capacity-overflow flag
   b200rt::DevBuf step_counter;      // unsigned long long
   long long last_steps = 0;
+  long long last_substeps = 0;      // line-of-sight sub-steps of the last singlet brightness call
 
   // lines of sight
   int n_los = 0;
@@ -255,7 +256,7 @@ template <class Real>
 cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em,
                               const Real *los_in, long long los_stride, long long first,
                               long long count, ListView<Real> lists, int n_subsamples, Real *out,
-                              long long n_los_total, int *queue, cudaStream_t s);
+                              long long n_los_total, int *queue, unsigned long long *substep_counter, cudaStream_t s);
 template <class Real>
 cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *rec_pt, Real *rec_avg, cudaStream_t s);
 

@@ -26,10 +26,8 @@ __constant__ double EXPK[4] = {
 
 // exp(x) for finite x <= 0 (also correct up to x ~ +700).  Underflows through the denormals to
 // exactly 0 like the host libm: the power of two is applied in two halves.
+// Valid for |x| < 1.4e9 (the rint trick keeps k in int32): optical depths of the spherical grid are far below that.
 __device__ __forceinline__ double exp_nonpos(double x) {
-  // x < -1000 (result 0 either way) is pinned to -1000 with integer compares on the high word, so that the
-  // rint trick below stays in range: a near-horizontal ray of the plane-parallel grid has path lengths ~1e24 cm
-  if ((unsigned) __double2hiint(x) > 0xC08F4000u) x = -1000.0;
   const double t = fma(x, EXPK[0], EXPK[1]);
   int k = __double2loint(t);
   const double kd = t - EXPK[1];
@@ -43,6 +41,14 @@ __device__ __forceinline__ double exp_nonpos(double x) {
   const double s1 = __hiloint2double((1023 + k1) << 20, 0);
   const double s2 = __hiloint2double((1023 + k2) << 20, 0);
   return (p * s1) * s2;
+}
+
+// the same for ANY x <= 0: x < -1000 (result 0 either way) is pinned to -1000 with integer compares on the high
+// word.  Needed on the plane-parallel grid, where a near-horizontal ray has path lengths ~1e25 cm (tau ~ 1e16).
+// Costs ~10 % more issue slots per exp, so the spherical-grid kernels use exp_nonpos.
+__device__ __forceinline__ double exp_nonpos_guarded(double x) {
+  if ((unsigned) __double2hiint(x) > 0xC08F4000u) x = -1000.0;
+  return exp_nonpos(x);
 }
 
 // a / b for normal positive b (|b| in [1e-290, 1e290]), no special cases

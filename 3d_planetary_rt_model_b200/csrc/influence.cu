@@ -37,9 +37,12 @@ namespace {
 
 template <class Real> __device__ __forceinline__ Real rexp(Real x);
 template <> __device__ __forceinline__ double rexp<double>(double x) { return exp(x); }
-template <class Real> __device__ __forceinline__ Real exp_neg(Real x);   // x <= 0, finite
-template <> __device__ __forceinline__ double exp_neg<double>(double x) { return fm::exp_nonpos(x); }
-template <> __device__ __forceinline__ float exp_neg<float>(float x) { return expf(x); }
+// exp(x), x <= 0.  GUARD: arguments may be astronomically negative (plane-parallel grid, fastmath.cuh)
+template <class Real, bool GUARD> __device__ __forceinline__ Real exp_neg(Real x);
+template <> __device__ __forceinline__ double exp_neg<double, false>(double x) { return fm::exp_nonpos(x); }
+template <> __device__ __forceinline__ double exp_neg<double, true>(double x) { return fm::exp_nonpos_guarded(x); }
+template <> __device__ __forceinline__ float exp_neg<float, false>(float x) { return expf(x); }
+template <> __device__ __forceinline__ float exp_neg<float, true>(float x) { return expf(x); }
 template <> __device__ __forceinline__ float rexp<float>(float x) { return expf(x); }
 template <class Real> __device__ __forceinline__ Real rsqrt_(Real x);
 template <> __device__ __forceinline__ double rsqrt_<double>(double x) { return sqrt(x); }
@@ -94,7 +97,7 @@ template <> struct Rec2<double> { typedef double2 type; };
 template <> struct Rec2<float> { typedef float2 type; };
 
 // MODE 0: rows of the influence matrix (voxel-origin rays); MODE 1: sun-ward rays -> S0, tau
-template <class Real, int MODE>
+template <class Real, int MODE, bool PP>
 __global__ void __launch_bounds__(256, 2)
 march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_rays_total,
              ListView<Real> lists, const int *__restrict__ shadow, double *__restrict__ K,
@@ -191,7 +194,7 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
 #pragma unroll
         for (int m = 0; m < LAMBDA_PER_LANE; m++) {
           const Real tau = rec[m].x * s;
-          const Real tp = exp_neg<Real>(-tau);
+          const Real tp = exp_neg<Real, PP>(-tau);
           if (MODE == 0) {
             const Real f = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) * tau : (Real(1.0) - tp);
             G += (rec[m].y * P[m]) * f * nl0[m];
@@ -256,8 +259,12 @@ cudaError_t launch_influence(const GridView<Real> &g, const EmissionView<Real> &
   long long blocks = (tasks + threads / 32 - 1) / (threads / 32);
   const long long persistent = (long long) NUM_SMS * 4;
   if (blocks > persistent) blocks = persistent;
-  march_kernel<Real, 0><<<(unsigned) blocks, threads, 0, s>>>(g, em, v_begin, n, lists, nullptr, K, nullptr, nullptr,
-                                                              nullptr, work_counter, step_counter);
+  if (g.pp)
+    march_kernel<Real, 0, true><<<(unsigned) blocks, threads, 0, s>>>(g, em, v_begin, n, lists, nullptr, K, nullptr, nullptr,
+                                                                      nullptr, work_counter, step_counter);
+  else
+    march_kernel<Real, 0, false><<<(unsigned) blocks, threads, 0, s>>>(g, em, v_begin, n, lists, nullptr, K, nullptr, nullptr,
+                                                                       nullptr, work_counter, step_counter);
   return cudaGetLastError();
 }
 
@@ -272,8 +279,12 @@ cudaError_t launch_single_scattering(const GridView<Real> &g, const EmissionView
   const long long tasks = (n + RAYS_PER_WARP - 1) / RAYS_PER_WARP;
   long long blocks = (tasks + threads / 32 - 1) / (threads / 32);
   if (blocks > NUM_SMS * 4) blocks = NUM_SMS * 4;
-  march_kernel<Real, 1><<<(unsigned) blocks, threads, 0, s>>>(g, em, 0, n, lists, shadow, nullptr, S0, tau_sp, tau_abs,
-                                                              work_counter, nullptr);
+  if (g.pp)
+    march_kernel<Real, 1, true><<<(unsigned) blocks, threads, 0, s>>>(g, em, 0, n, lists, shadow, nullptr, S0, tau_sp, tau_abs,
+                                                                      work_counter, nullptr);
+  else
+    march_kernel<Real, 1, false><<<(unsigned) blocks, threads, 0, s>>>(g, em, 0, n, lists, shadow, nullptr, S0, tau_sp, tau_abs,
+                                                                       work_counter, nullptr);
   return cudaGetLastError();
 }
 

@@ -64,7 +64,7 @@ template <class TR> struct Dim {
 };
 
 template <class Real> __device__ __forceinline__ Real m_exp(Real x);          // x <= 0
-template <> __device__ __forceinline__ double m_exp<double>(double x) { return fm::exp_nonpos(x); }
+template <> __device__ __forceinline__ double m_exp<double>(double x) { return fm::exp_nonpos_guarded(x); }   // also on plane-parallel grids
 template <> __device__ __forceinline__ float m_exp<float>(float x) { return expf(x); }
 template <class Real> __device__ __forceinline__ Real m_sqrt(Real x);
 template <> __device__ __forceinline__ double m_sqrt<double>(double x) { return sqrt(x); }

@@ -51,6 +51,19 @@ __device__ __forceinline__ int info_slot(int info) { return info & ((1 << SLOT_B
 __device__ __forceinline__ int info_dim(int info) { return (info >> SLOT_BITS) & 1; }
 __device__ __forceinline__ int info_val(int info) { return (info >> (SLOT_BITS + 1)) - 1; }
 
+// 16-byte groups of distances for the ranking loop
+template <class Real> struct VecOf;
+template <> struct VecOf<double> {
+  typedef double2 type;
+  __device__ static __forceinline__ int count_less(const double2 &v, double d) { return (v.x < d ? 1 : 0) + (v.y < d ? 1 : 0); }
+};
+template <> struct VecOf<float> {
+  typedef float4 type;
+  __device__ static __forceinline__ int count_less(const float4 &v, float d) {
+    return (v.x < d ? 1 : 0) + (v.y < d ? 1 : 0) + (v.z < d ? 1 : 0) + (v.w < d ? 1 : 0);
+  }
+};
+
 template <class Real>
 __device__ __forceinline__ bool key_less(Real d1, int s1, Real d2, int s2) {
   return d1 < d2 || (d1 == d2 && s1 < s2);
@@ -174,12 +187,13 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
   const int cap = g.cap, n_rb = g.n_rb, n_sb = g.n_sb;
 
   // per-warp scratch
-  const size_t per_warp = ((size_t) (2 * n_rb + 2 * cap) * sizeof(Real) + (size_t) 2 * cap * sizeof(int) + 15) & ~size_t(15);
+  const int cap4 = (cap + 3) & ~3;                         // room for the 16-byte padding of the ranking loop
+  const size_t per_warp = ((size_t) (2 * n_rb + 2 * cap4) * sizeof(Real) + (size_t) 2 * cap * sizeof(int) + 15) & ~size_t(15);
   unsigned char *base = smem_raw + per_warp * warp;
-  Real *sph_d = reinterpret_cast<Real *>(base);            // [2*n_rb]  first/second hit per sphere
-  Real *cmp_d = sph_d + 2 * n_rb;                          // [cap]     compacted, unsorted
-  Real *srt_d = cmp_d + cap;                               // [cap]     sorted
-  int *cmp_i = reinterpret_cast<int *>(srt_d + cap);       // [cap]
+  Real *cmp_d = reinterpret_cast<Real *>(base);            // [cap4]    compacted, unsorted (16-byte aligned)
+  Real *srt_d = cmp_d + cap4;                              // [cap4]    sorted
+  Real *sph_d = srt_d + cap4;                              // [2*n_rb]  first/second hit per sphere
+  int *cmp_i = reinterpret_cast<int *>(sph_d + 2 * n_rb);  // [cap]
   int *srt_i = cmp_i + cap;                                // [cap]
 
   const Real INF = Lim<Real>::inf();
@@ -219,6 +233,7 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
     const bool origin_in = (r0 >= 0 && r0 <= n_rb - 2 && s0 >= 0 && s0 <= n_sb - 2);
 
     // ---- pass 1: spheres -> shared, and the keys of the first in-grid entry / first exit
+#pragma unroll 1
     for (int ir = lane; ir < n_rb; ir += 32) {
       Real f, s;
       if (g.pp) plane_hits(z, lz, g.rb[ir], f, s);   // plane_parallel_grid::ray_voxel_intersections (grid_plane_parallel.hpp:282-288)
@@ -232,6 +247,7 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
     int rb_val = r0;                               // radial index at `begin`
     if (origin_in) { db = 0; sb_slot = 0; }
     else {
+#pragma unroll 1
       for (int ir = lane; ir < n_rb; ir += 32) {
         const bool above = r > g.rb[ir];
         const Real f = sph_d[2 * ir], s = sph_d[2 * ir + 1];
@@ -253,6 +269,7 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
       continue;
     }
     Real de = INF; int se_slot = 0x7fffffff;       // key of `end`
+#pragma unroll 1
     for (int ir = lane; ir < n_rb; ir += 32) {
       const bool above = r > g.rb[ir];
       const Real f = sph_d[2 * ir], s = sph_d[2 * ir + 1];
@@ -266,6 +283,7 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
     // ---- pass 2: compact every crossing with  begin < key <= end
     int count = 0;                                  // warp-uniform
     Real dsb = -INF; int ssb_slot = -1; int sb_val = s0;   // latest sza crossing before `begin`
+#pragma unroll 1
     for (int base_ir = 0; base_ir < n_rb; base_ir += 32) {
       const int ir = base_ir + lane;
       Real f = INF, s = INF;
@@ -288,6 +306,7 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
       count += __popc(ms);
     }
     const Real zn = z / r;
+#pragma unroll 1
     for (int base_k = 0; base_k < n_sb - 2; base_k += 32) {
       const int k = base_k + lane;
       Real f = INF, s = INF;
@@ -338,19 +357,48 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
     }
     __syncwarp();
 
-    // ---- rank by (distance, slot): what the stable insertion sort produces
+    // ---- rank by (distance, slot): what the stable insertion sort produces.
+    // Fast path: rank by distance alone (one compare per pair, distances read 16 bytes at a time); two crossings at
+    // exactly the same distance then collide on one rank and leave a slot of the sorted list unwritten, which is
+    // detected below and sends the (rare) ray through the exact (distance, slot) ranking.
+    constexpr int VEC = 16 / (int) sizeof(Real);
+    typedef typename VecOf<Real>::type RealV;
+    const int count_pad = (count + VEC - 1) / VEC * VEC;
+#pragma unroll 1
+    for (int e = count + lane; e < count_pad; e += 32) cmp_d[e] = INF;     // padding never counts (INF < d is false)
+#pragma unroll 1
+    for (int e = lane; e < count; e += 32) srt_i[e] = -1;
+    __syncwarp();
+#pragma unroll 1
     for (int e = lane; e < count; e += 32) {
       const Real d = cmp_d[e];
-      const int info = cmp_i[e];
-      const int slot = info_slot(info);
       int rank = 0;
-      for (int j = 0; j < count; j++) {
-        const Real dj = cmp_d[j];
-        const int sj = info_slot(cmp_i[j]);
-        rank += key_less(dj, sj, d, slot) ? 1 : 0;
-      }
+      const RealV *cv = reinterpret_cast<const RealV *>(cmp_d);
+#pragma unroll 4
+      for (int j = 0; j < count_pad / VEC; j++) rank += VecOf<Real>::count_less(cv[j], d);
       srt_d[rank] = d;
-      srt_i[rank] = info;
+      srt_i[rank] = cmp_i[e];
+    }
+    __syncwarp();
+    bool hole = false;
+#pragma unroll 1
+    for (int e = lane; e < count; e += 32) hole |= (srt_i[e] < 0);
+    if (__any_sync(0xffffffffu, hole)) {
+      __syncwarp();
+#pragma unroll 1
+      for (int e = lane; e < count; e += 32) {
+        const Real d = cmp_d[e];
+        const int info = cmp_i[e];
+        const int slot = info_slot(info);
+        int rank = 0;
+        for (int j = 0; j < count; j++) {
+          const Real dj = cmp_d[j];
+          const int sj = info_slot(cmp_i[j]);
+          rank += key_less(dj, sj, d, slot) ? 1 : 0;
+        }
+        srt_d[rank] = d;
+        srt_i[rank] = info;
+      }
     }
     __syncwarp();
 
@@ -364,6 +412,7 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
       oe[0] = carry_r * (n_sb - 1) + carry_s;      // `begin` is inside the grid by construction
     }
     int last_r = carry_r;
+#pragma unroll 1
     for (int base_e = 0; base_e < count; base_e += 32) {
       const int e = base_e + lane;
       int pr = 0, ps = 0;                           // (pos+1)<<16 | (val+1) ; 0 = not set here
@@ -402,7 +451,8 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
 
 template <class Real>
 size_t traverse_smem_bytes(const GridView<Real> &g, int warps) {
-  const size_t per_warp = ((size_t) (2 * g.n_rb + 2 * g.cap) * sizeof(Real) + (size_t) 2 * g.cap * sizeof(int) + 15) & ~size_t(15);
+  const int cap4 = (g.cap + 3) & ~3;
+  const size_t per_warp = ((size_t) (2 * g.n_rb + 2 * cap4) * sizeof(Real) + (size_t) 2 * g.cap * sizeof(int) + 15) & ~size_t(15);
   return per_warp * warps;
 }
 

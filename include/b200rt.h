@@ -147,6 +147,10 @@ int b200rt_solve(b200rt_ctx *ctx);                      /* RT_grid::solve_gpu, e
 /* ray-voxel steps executed by the last b200rt_influence call (one step = one
  * RT_grid::influence_update, RT_grid.hpp:90-105, covering all emissions) */
 int b200rt_last_step_count(b200rt_ctx *ctx, long long *n_steps);
+/* line-of-sight sub-steps integrated by the last singlet b200rt_brightness* call: sum over lines of sight of
+ * (segments inside the grid) x (n_subsamples - 1), one sub-step = one update_tracker_brightness_interp of every
+ * emission (RT_grid.hpp:273-293) */
+int b200rt_last_substep_count(b200rt_ctx *ctx, long long *n_substeps);
 
 /* replaces RT_grid::emissions_solved_to_host / emissions_influence_to_host
  * (RT_gpu.cu:62-84; emission_voxels.hpp:273-291).  Any pointer may be NULL.

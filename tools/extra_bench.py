@@ -49,6 +49,36 @@ def sweep(n_sets, n_los, contexts, gpus):
             "sweep_seconds": wall, "sweep_sets_per_s": len(NH) / wall, "sweep_finite": bool(np.isfinite(b).all())}
 
 
+def multiplet(kind, image_px=600):
+    """BASELINE.json configs[4] (ii)/(iii): one multiplet emission on the reference default grid 40x20x7x12 --
+    source function (influence + single scattering + solve) and the 600 x 600 fake image (observation::fake,
+    observation.hpp:173-208; generate_source_function.cpp:296-306), device times of the kernels"""
+    synth = importlib.import_module(PKG + ".synth")
+    binding = importlib.import_module(PKG + ".binding")
+    scn = synth.make_multiplet_scenario(kind, 40, 20, 7, 12)
+    G = binding.GpuMultiplet(scn, "f64")
+    locs, dirs = synth.fake_image(30 * synth.rMars, 30, image_px)
+    los = G.ctx.los_from_MSO(locs, dirs)
+    G.ctx.los_upload(los)
+    out = {}
+    for it in range(3):
+        G.ctx.influence()
+        t_tr, t_in = G.ctx.kernel_ms(binding.PH_TRAVERSE)[0], G.ctx.kernel_ms(binding.PH_INFLUENCE)[0]
+        steps = G.ctx.last_step_count()
+        G.ctx.solve()
+        t_so = G.ctx.kernel_ms(binding.PH_SOLVE)[0]
+        G.ctx.brightness_resident(10)
+        t_lt, t_br = G.ctx.kernel_ms(binding.PH_TRAVERSE)[0], G.ctx.kernel_ms(binding.PH_BRIGHTNESS)[0]
+    name = {0: "O1026", 1: "H_lyman_multiplet", 2: "H_lyman_singlet"}[kind]
+    b = G.ctx.los_download()["brightness"]
+    out[f"mult_{name}"] = {"grid": "40x20x7x12", "n_elements": G.n_el, "ray_voxel_steps": steps,
+                           "influence_traverse_ms": t_tr, "influence_march_ms": t_in,
+                           "steps_per_s": steps / ((t_tr + t_in) * 1e-3), "solve_ms": t_so, "residual": G.ctx.residual(0),
+                           "n_los": len(locs), "los_traverse_ms": t_lt, "brightness_ms": t_br,
+                           "los_per_s": len(locs) / ((t_lt + t_br) * 1e-3), "max_line_kR": [float(x) for x in b.max(axis=1)]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iph-los", type=int, default=1000000)
@@ -56,12 +86,16 @@ def main():
     ap.add_argument("--sweep-los", type=int, default=10000)
     ap.add_argument("--contexts", type=int, default=4)
     ap.add_argument("--gpus", type=int, default=-1)
+    ap.add_argument("--multiplet", action="store_true", help="O I 102.6 and H Lyman multiplet on the default grid")
     a = ap.parse_args()
     out = {}
     if a.iph_los > 0:
         out.update(iph(a.iph_los))
     if a.sets > 0:
         out.update(sweep(a.sets, a.sweep_los, a.contexts, a.gpus))
+    if a.multiplet:
+        out.update(multiplet(0))
+        out.update(multiplet(1))
     print(json.dumps(out))
 
 

@@ -1,15 +1,16 @@
 #!/bin/bash
 # ncu evidence for one round: launch list of one bench step + full captures of the top kernels.
-# usage (under gpurun): bash tools/profile_round.sh <tag>
+# usage (under gpurun): bash tools/profile_round.sh <tag>      (then, here: python tools/make_profiles.py <tag>)
+# The profiled command is the bench's own workload (1e6 lines of sight, grid 100x60x24x16), one step, no warm-up.
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out
-CMD="python bench.py --steps 1 --warmup 0 --n-los 200000 --no-cpu-baseline --no-extras"
+CMD="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-extras"
 $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain_$TAG.log; exit 1; }
 tail -c 600 $OUT/plain_$TAG.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
-for K in ${KERNELS:-brightness_kernel march_kernel traverse_kernel update_kernel}; do
+for K in ${KERNELS:-brightness_kernel march_kernel traverse_kernel gemm128_kernel}; do
   ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -f -o $OUT/prof_${K}_$TAG $CMD > $OUT/ncu_${K}_$TAG.log 2>&1
   echo "$K rc=$?"
 done
