@@ -270,7 +270,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
             const Real lineshape = phi[m];
             const Real tau = (dta + dts * lineshape) * s;
             const Real tp = MathB<Real>::exp_(-tau);
-            Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::div_(Real(1.0) - tp, tau);
+            Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::divq_(Real(1.0) - tp, tau);
             c *= (wgt[m] * lineshape * P[e][m]) * common;
             T_int += c;
             P[e][m] *= tp;

@@ -11,6 +11,7 @@ template <class Real> struct MathB;
 template <> struct MathB<double> {
   __device__ static double exp_(double x) { return fm::exp_nonpos(x); }   // arguments are <= 0 and finite
   __device__ static double div_(double a, double b) { return fm::div_approx(a, b); }   // b >= 1e-3 where it is used
+  __device__ static double divq_(double a, double b) { return fm::div_fast(a, b); }    // 1e-12: inside the wavelength loops
   __device__ static double divc_(double a, double b, double rb) { return fm::div_by(a, b, rb); }   // rb = 1/b precomputed
   __device__ static double rcp_(double b) { return 1.0 / b; }
   __device__ static double log_(double x) { return log(x); }
@@ -23,6 +24,7 @@ template <> struct MathB<double> {
 template <> struct MathB<float> {
   __device__ static float exp_(float x) { return expf(x); }
   __device__ static float div_(float a, float b) { return a / b; }
+  __device__ static float divq_(float a, float b) { return a / b; }
   __device__ static float divc_(float a, float b, float) { return a / b; }
   __device__ static float rcp_(float b) { return 1.0f / b; }
   // std::log(float) of the host libm is (nearly) correctly rounded; CUDA logf is not (1 ulp), and one ulp of

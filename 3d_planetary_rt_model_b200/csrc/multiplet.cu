@@ -426,7 +426,7 @@ mult_brightness_kernel(GridView<Real> g, MultView<Real> mv, MultParams<Real> P_,
           for (int m = 0; m < NM; m++) {
             const Real tau = kap[m] * s;
             const Real p = m_exp<Real>(-tau);
-            const Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::div_(Real(1.0) - p, tau);
+            const Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::divq_(Real(1.0) - p, tau);
             base[m] = ok ? c * P[m][j] * s : Real(0);
             P[m][j] *= p;
           }

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from golden_util import GOLDEN, load_golden
-from util import TOL, TOL_AUX, assert_lists_equal, rel_err, same_bits
+from util import TOL, UNDERFLOW, TOL_AUX, assert_lists_equal, rel_err, same_bits
 
 
 def check_against_golden(M, scn, z, prec, exact):
@@ -22,14 +22,18 @@ def check_against_golden(M, scn, z, prec, exact):
         if exact:
             assert same_bits(K, z[f"K{e}"])
         else:
-            assert np.array_equal(K != 0, z[f"K{e}"] != 0)
-            assert rel_err(K, z[f"K{e}"]) < tol
+            # entries at the underflow edge of Real (< 1e-290 / 1e-30, against row sums of order 1) are compared as
+            # zeros: the device's exp does not walk through the denormals (fastmath.cuh), same rule as test_gpu_parity
+            floor = 1e-290 if prec == "f64" else 1e-30
+            Kz = z[f"K{e}"]
+            assert np.array_equal(np.abs(K) > floor, np.abs(Kz) > floor)
+            assert rel_err(np.where(np.abs(K) > floor, K, 0.0), np.where(np.abs(Kz) > floor, Kz, 0.0)) < tol
         v = M.vectors(e, want_S=False) if not exact else M.vectors(e)
         for k in ("S0", "tau_species_ss", "tau_absorber_ss"):
             if exact:
                 assert same_bits(v[k], z[f"vec{e}_{k}"]), k
             else:
-                assert rel_err(v[k], z[f"vec{e}_{k}"]) < tol, k
+                assert rel_err(v[k], z[f"vec{e}_{k}"], floor=UNDERFLOW[prec]) < tol, k
     M.solve()
     for e in range(2):
         Sg = z[f"vec{e}_S"]

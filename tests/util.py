@@ -33,3 +33,9 @@ def assert_lists_equal(a, b):
     assert np.array_equal(a[1], b[1]), "exits_bottom flags differ"
     assert np.array_equal(a[2], b[2]), "entering voxel indices differ"
     assert same_bits(a[3], b[3]), "crossing distances differ in their IEEE bits"
+
+
+# Results below this magnitude are compared as zeros: quantities of order 1 (transmissions, probabilities) that have
+# underflowed through ~700 e-foldings.  The host libm walks through the denormals to exactly 0; the device's exp
+# (fastmath.cuh) bottoms out at ~1e-301 instead.
+UNDERFLOW = {"f64": 1e-290, "f32": 1e-30}
