@@ -683,6 +683,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   }
   if (c->grid_view) ::operator delete(c->grid_view);
   for (cudaEvent_t ev : c->lu_events) cudaEventDestroy(ev);
+  if (c->lu_graph) cudaGraphExecDestroy(c->lu_graph);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;

@@ -193,6 +193,9 @@ struct b200rt_ctx {
   b200rt::DevBuf lu, lu_dinv, lu_flag;
   cudaStream_t stream2 = nullptr;            // look-ahead stream of the LU
   std::vector<cudaEvent_t> lu_events;
+  cudaGraphExec_t lu_graph = nullptr;        // the factorisation + back substitution of one (np, workspace), replayed
+  int lu_graph_np = 0, lu_graph_launches = 0;
+  const void *lu_graph_A = nullptr, *lu_graph_dinv = nullptr;
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 #include "common.hpp"
 
@@ -80,9 +81,17 @@ __global__ void prepare_kernel(const double *__restrict__ K, int n, int np, doub
   }
 }
 
-// ---- (1) diagonal block: in-place Gauss-Jordan inverse, no pivoting.
-// 256 threads = 16 x 16, thread (ty, tx) owns rows ty*8.., columns tx*8.. in registers.  The inner
-// 8 steps are unrolled so that every register index is static.
+// ---- (1) diagonal block: in-place BLOCK Gauss-Jordan inverse, 4 pivots per step, no pivoting.
+// With J the 4 pivot indices of a step, P = A[J,J] and R the other 124 indices, one step is
+//     A[R,R] -= A[R,J] P^-1 A[J,R];   A[J,R] <- P^-1 A[J,R];   A[R,J] <- -A[R,J] P^-1;   A[J,J] <- P^-1
+// (the scalar in-place Gauss-Jordan step with a 4x4 pivot).  The rank-4 update of the whole block is exactly
+// m8n8k4-shaped, so it runs on the FP64 tensor pipe: 512 threads = 16 warps in a 4 x 4 arrangement, each warp keeps
+// a 32 x 32 piece of the block in DMMA accumulator layout (16 tiles, 32 registers per thread) for all 32 steps.
+// Per step: the owners publish rows J and columns J through shared memory (double-buffered: ONE barrier per step,
+// 32 barriers per inverse where the scalar version needed 128), every thread inverts the 4x4 pivot itself (cheaper
+// than a second barrier), forms its B fragments (P^-1 A[J,R])[k = tq][column g] with 4 FMAs per tile column, issues 16
+// DMMAs, and the owners overwrite the pivot rows / columns.  Measured: 67 us (scalar, 8x8 register tiles, DFMA) ->
+// see profiles/ for the current figure; the inverse is the critical path of the last ~27 block columns.
 __device__ __forceinline__ double rcp_fast(double b) {   // 1/b for normal b, <= 1 ulp
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
@@ -93,62 +102,191 @@ __device__ __forceinline__ double rcp_fast(double b) {   // 1/b for normal b, <=
   e = fma(-b, r, 1.0);
   return fma(r, e, r);
 }
-constexpr int TB = 128;   // block size of the factorisation
-__global__ void __launch_bounds__(256)
-gj128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ dinv) {
-  __shared__ __align__(16) double prow[2][TB], pcol[2][TB];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const double *Akk = A + ((size_t) KB * TB) * np + (size_t) KB * TB;
-  double a[8][8];
+__device__ __forceinline__ double sel4(double a0, double a1, double a2, double a3, int i) {
+  const double lo = (i & 1) ? a1 : a0, hi = (i & 1) ? a3 : a2;
+  return (i & 2) ? hi : lo;
+}
+// in-place inverse of a 4x4 matrix with a safely non-zero diagonal at every step (principal block of an M-matrix)
+__device__ __forceinline__ void inv4(double (&m)[4][4]) {
 #pragma unroll
-  for (int rr = 0; rr < 8; rr++)
+  for (int j = 0; j < 4; j++) {
+    const double p = rcp_fast(m[j][j]);
 #pragma unroll
-    for (int c2 = 0; c2 < 4; c2++) {
-      const double2 v = *reinterpret_cast<const double2 *>(Akk + (size_t) (ty * 8 + rr) * np + tx * 8 + 2 * c2);
-      a[rr][2 * c2] = v.x;
-      a[rr][2 * c2 + 1] = v.y;
+    for (int c = 0; c < 4; c++) m[j][c] = (c == j) ? p : m[j][c] * p;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (i == j) continue;
+      const double f = m[i][j];
+#pragma unroll
+      for (int c = 0; c < 4; c++) m[i][c] = (c == j) ? -f * p : fma(-f, m[j][c], m[i][c]);
     }
-  for (int jb = 0; jb < 16; jb++) {
+  }
+}
+constexpr int TB = 128;   // block size of the factorisation
+constexpr int GJ_THREADS = 512;
+__global__ void __launch_bounds__(GJ_THREADS)
+gj128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ dinv) {
+  __shared__ __align__(16) double prow[2][4][TB];   // rows J of the step
+  __shared__ __align__(16) double pcol[2][TB][4];   // columns J of the step
+  __shared__ __align__(16) double pinv[2][4][4];    // P^-1 of the step
+  __shared__ __align__(16) double praw[4][4];       // the next pivot block on its way to its inverse (owner warp only)
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int wr = w >> 2, wc = w & 3, wm = wr * 32, wn = wc * 32;
+  const double *Akk = A + ((size_t) KB * TB) * np + (size_t) KB * TB;
+  double acc[4][4][2];   // element (wm + 8 mt + g, wn + 8 nt + 2 tq + c)
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-      const int j = jb * 8 + jj, buf = jj & 1;
-      if (ty == jb) {
+  for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-        for (int cc = 0; cc < 8; cc++) prow[buf][tx * 8 + cc] = a[jj][cc];
+    for (int nt = 0; nt < 4; nt++) {
+      const double2 v = *reinterpret_cast<const double2 *>(Akk + (size_t) (wm + 8 * mt + g) * np + wn + 8 * nt + 2 * tq);
+      acc[mt][nt][0] = v.x;
+      acc[mt][nt][1] = v.y;
+    }
+  // what the step after the current one needs, written into buffer `nb`: the inverse of its pivot block (formed by the
+  // one warp that holds it, while the other warps are still in their DMMAs) and its pivot rows / columns.
+  // band = 32-wide band of the pivots, tJ = tile index inside the band, half = which 4 of the tile's 8 indices.
+  // (tJ is a compile-time constant at every call once the step loop is unrolled; the `t == tJ` loops keep the register
+  // indices static)
+  auto invert_next_pivot = [&](int band, int tJ, int half, int nb) {
+    if (wr == band && wc == band) {               // warp-uniform
+      if ((g >> 2) == half && (tq >> 1) == half) {
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (t == tJ) *reinterpret_cast<double2 *>(&praw[g & 3][(2 * tq) & 3]) = make_double2(acc[t][t][0], acc[t][t][1]);
       }
-      if (tx == jb) {
+      __syncwarp();
+      double m[4][4];
 #pragma unroll
-        for (int rr = 0; rr < 8; rr++) pcol[buf][ty * 8 + rr] = a[rr][jj];
+      for (int q = 0; q < 4; q++) {
+        const double2 a = *reinterpret_cast<const double2 *>(&praw[q][0]);
+        const double2 b = *reinterpret_cast<const double2 *>(&praw[q][2]);
+        m[q][0] = a.x; m[q][1] = a.y; m[q][2] = b.x; m[q][3] = b.y;
       }
+      __syncwarp();
+      inv4(m);
+      if (lane < 4) {
+        *reinterpret_cast<double2 *>(&pinv[nb][lane][0]) =
+            make_double2(sel4(m[0][0], m[1][0], m[2][0], m[3][0], lane), sel4(m[0][1], m[1][1], m[2][1], m[3][1], lane));
+        *reinterpret_cast<double2 *>(&pinv[nb][lane][2]) =
+            make_double2(sel4(m[0][2], m[1][2], m[2][2], m[3][2], lane), sel4(m[0][3], m[1][3], m[2][3], m[3][3], lane));
+      }
+    }
+  };
+  auto publish = [&](int band, int tJ, int half, int nb) {
+    if (wr == band && (g >> 2) == half) {
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        if (t == tJ) {
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++)
+            *reinterpret_cast<double2 *>(&prow[nb][g & 3][wn + 8 * nt + 2 * tq]) = make_double2(acc[t][nt][0], acc[t][nt][1]);
+        }
+    }
+    if (wc == band && (tq >> 1) == half) {
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        if (t == tJ) {
+#pragma unroll
+          for (int mt = 0; mt < 4; mt++)
+            *reinterpret_cast<double2 *>(&pcol[nb][wm + 8 * mt + g][(2 * tq) & 3]) = make_double2(acc[mt][t][0], acc[mt][t][1]);
+        }
+    }
+  };
+  invert_next_pivot(0, 0, 0, 0);
+  publish(0, 0, 0, 0);
+  __syncthreads();
+  for (int kk = 0; kk < 4; kk++) {         // 32-wide band holding the pivots
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {       // step within the band: tile index ks >> 1, half of the tile ks & 1
+      const int tJ = ks >> 1, half = ks & 1, buf = ks & 1;
+      const int tJn = ((ks + 1) & 7) >> 1, halfn = (ks + 1) & 1, kkn = kk + (ks == 7 ? 1 : 0);   // the step after
+      const bool own_rows = (wr == kk) && ((g >> 2) == half);
+      const bool own_cols = (wc == kk) && ((tq >> 1) == half);
+      // B fragments of the update: (P^-1 A[J,:])[tq][wn + 8 nt + g]
+      double pk[4], spb[4], fa[4];
+      {
+        const double2 a = *reinterpret_cast<const double2 *>(&pinv[buf][tq][0]);
+        const double2 b = *reinterpret_cast<const double2 *>(&pinv[buf][tq][2]);
+        pk[0] = a.x; pk[1] = a.y; pk[2] = b.x; pk[3] = b.y;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const int col = wn + 8 * nt + g;
+        spb[nt] = pk[0] * prow[buf][0][col];
+        spb[nt] = fma(pk[1], prow[buf][1][col], spb[nt]);
+        spb[nt] = fma(pk[2], prow[buf][2][col], spb[nt]);
+        spb[nt] = fma(pk[3], prow[buf][3][col], spb[nt]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) fa[mt] = -pcol[buf][wm + 8 * mt + g][tq];
+      // DMMA order: the tile holding the next pivot block first (its owner inverts it while the other DMMAs drain), then
+      // the rest of that tile row / column (what the next step's publication reads), then the other nine tiles.
+      dmma8x8x4(acc[tJn][tJn][0], acc[tJn][tJn][1], fa[tJn], spb[tJn]);
+      if (kkn < 4) invert_next_pivot(kkn, tJn, halfn, buf ^ 1);
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+        if (t != tJn) {
+          dmma8x8x4(acc[tJn][t][0], acc[tJn][t][1], fa[tJn], spb[t]);
+          dmma8x8x4(acc[t][tJn][0], acc[t][tJn][1], fa[t], spb[tJn]);
+        }
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+          if (mt != tJn && nt != tJn) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], fa[mt], spb[nt]);
+      // the pivot rows / columns are then overwritten with their new values
+      if (own_rows) {      // A[J,:] <- P^-1 A[J,:]
+        double pr[4];
+        {
+          const double2 a = *reinterpret_cast<const double2 *>(&pinv[buf][g & 3][0]);
+          const double2 b = *reinterpret_cast<const double2 *>(&pinv[buf][g & 3][2]);
+          pr[0] = a.x; pr[1] = a.y; pr[2] = b.x; pr[3] = b.y;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          double c0 = 0, c1 = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double2 r = *reinterpret_cast<const double2 *>(&prow[buf][q][wn + 8 * nt + 2 * tq]);
+            c0 = fma(pr[q], r.x, c0);
+            c1 = fma(pr[q], r.y, c1);
+          }
+          acc[tJ][nt][0] = c0;
+          acc[tJ][nt][1] = c1;
+        }
+      }
+      if (own_cols) {      // A[:,J] <- -A[:,J] P^-1, and the pivot block itself <- P^-1
+        const int cq = (2 * tq) & 3;   // 0 or 2: this lane's two columns of J
+        double pc0[4], pc1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double2 a = *reinterpret_cast<const double2 *>(&pinv[buf][q][cq]);
+          pc0[q] = a.x;
+          pc1[q] = a.y;
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+          const double2 f01 = *reinterpret_cast<const double2 *>(&pcol[buf][wm + 8 * mt + g][0]);
+          const double2 f23 = *reinterpret_cast<const double2 *>(&pcol[buf][wm + 8 * mt + g][2]);
+          acc[mt][tJ][0] = -fma(f23.y, pc0[3], fma(f23.x, pc0[2], fma(f01.y, pc0[1], f01.x * pc0[0])));
+          acc[mt][tJ][1] = -fma(f23.y, pc1[3], fma(f23.x, pc1[2], fma(f01.y, pc1[1], f01.x * pc1[0])));
+        }
+        if (own_rows) {
+          acc[tJ][tJ][0] = sel4(pc0[0], pc0[1], pc0[2], pc0[3], g & 3);
+          acc[tJ][tJ][1] = sel4(pc1[0], pc1[1], pc1[2], pc1[3], g & 3);
+        }
+      }
+      if (kkn < 4) publish(kkn, tJn, halfn, buf ^ 1);
       __syncthreads();
-      const double p = rcp_fast(prow[buf][j]);
-      double sp[8], f[8];
-#pragma unroll
-      for (int cc = 0; cc < 8; cc++) sp[cc] = prow[buf][tx * 8 + cc] * p;
-#pragma unroll
-      for (int rr = 0; rr < 8; rr++) f[rr] = pcol[buf][ty * 8 + rr];
-#pragma unroll
-      for (int rr = 0; rr < 8; rr++)
-#pragma unroll
-        for (int cc = 0; cc < 8; cc++) a[rr][cc] = fma(-f[rr], sp[cc], a[rr][cc]);
-      if (ty == jb) {
-#pragma unroll
-        for (int cc = 0; cc < 8; cc++) a[jj][cc] = sp[cc];
-      }
-      if (tx == jb) {
-#pragma unroll
-        for (int rr = 0; rr < 8; rr++) a[rr][jj] = -f[rr] * p;
-        if (ty == jb) a[jj][jj] = p;
-      }
     }
   }
   double *out = dinv + (size_t) KB * TB * TB;
 #pragma unroll
-  for (int rr = 0; rr < 8; rr++)
+  for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-    for (int c2 = 0; c2 < 4; c2++)
-      *reinterpret_cast<double2 *>(out + (size_t) (ty * 8 + rr) * TB + tx * 8 + 2 * c2) =
-          make_double2(a[rr][2 * c2], a[rr][2 * c2 + 1]);
+    for (int nt = 0; nt < 4; nt++)
+      *reinterpret_cast<double2 *>(out + (size_t) (wm + 8 * mt + g) * TB + wn + 8 * nt + 2 * tq) =
+          make_double2(acc[mt][nt][0], acc[mt][nt][1]);
 }
 
 // ---- rhs: b[r] -= L21[r][block column KB] . b_KB for every row below (one warp per row)
@@ -169,9 +307,10 @@ rhs128_kernel(const double *__restrict__ Lbuf, int np, int KB, double *__restric
 
 // ---- 128x128x128 tile products on the FP64 tensor pipe
 constexpr int TM = 128, TN = 128, TK = 128;
-constexpr int KC = 16;                 // k-chunk per pipeline stage
-constexpr int STAGES = 4;
-constexpr int SA = KC + 4;             // 20: (row*20 + col) mod 16 distinct for row, col < 4  (conflict-free LDS.64)
+constexpr int KC_DEFAULT = 16;         // k-chunk per pipeline stage
+constexpr int STAGES_DEFAULT = 4;
+constexpr int KC_BULK = 8, STAGES_BULK = 4;
+constexpr size_t gemm_smem_bytes(int kc, int stages, int tn) { return (size_t) stages * (TM * (kc + 4) + kc * (tn + 4)) * sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
@@ -187,9 +326,14 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //         a double-buffered side array: the updates of block column KB read one half while chain KB+1 fills the other)
 // NT = DMMA n-tiles per warp: 8 -> 128x128 output tile per CTA (bulk update), 4 -> 128x64 (the two
 // kernels on the critical path run as twice as many CTAs with half the latency; blockIdx.y picks the half).
-template <int MODE, int NT>
-__global__ void __launch_bounds__(256)
+// KC = k-chunk per pipeline stage, STAGES = cp.async stages.  The bulk update runs <1, 4, 8, 4>: 128x64 tiles (64
+// accumulator registers per thread) and 66 kB of shared memory per CTA, so TWO CTAs are resident per SM and one's
+// C-tile prologue / epilogue overlaps the other's DMMA stream (a lone 128x128 CTA per SM left the tensor pipe idle
+// ~40 % of each tile: 26.5 us per tile against 16.7 us of DMMA issue).
+template <int MODE, int NT, int KC = KC_DEFAULT, int STAGES = STAGES_DEFAULT>
+__global__ void __launch_bounds__(256, (MODE == 1) ? 2 : 1)
 gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict__ dinv, double *__restrict__ Lbuf) {
+  constexpr int SA = KC + 4;             // 20 / 12: (row*SA + col) mod 16 distinct for row, col < 4  (conflict-free LDS.64)
   constexpr int TNc = 16 * NT;           // output tile width of this CTA
   constexpr int SBc = TNc + 4;           // 132 / 68: (k*SB + n) mod 16 distinct for k, n < 4
   constexpr int STAGE = TM * SA + KC * SBc;
@@ -221,9 +365,10 @@ gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict_
     double *As = sm + (chunk % STAGES) * STAGE;
     double *Bs = As + TM * SA;
     const int k0 = chunk * KC;
+    constexpr int PA = KC / 2;          // 16-byte pieces per A row: the chunk is 128 rows x KC doubles
 #pragma unroll
-    for (int i = 0; i < 4; i++) {       // A chunk: 128 rows x 16 doubles = 1024 x 16 B
-      const int r = (tid >> 3) + 32 * i, p = tid & 7;
+    for (int i = 0; i < TM * PA / 256; i++) {
+      const int e = tid + 256 * i, r = e / PA, p = e % PA;
       cp_async16(As + r * SA + 2 * p, Lg + (size_t) r * ldl + k0 + 2 * p);
     }
     constexpr int PPR = TNc / 2;        // 16-byte pieces per B row
@@ -451,10 +596,10 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
                       std::to_string(ymax) + "): elimination without row exchanges is not safe");
   }
 
-  const size_t gemm_smem = (size_t) STAGES * (TM * SA + KC * (TN + 4)) * sizeof(double);        // 128x128 tiles
-  const size_t gemm_smem_h = (size_t) STAGES * (TM * SA + KC * (TN / 2 + 4)) * sizeof(double);  // 128x64 tiles
+  const size_t gemm_smem = gemm_smem_bytes(KC_BULK, STAGES_BULK, TN / 2);             // 128x64 tiles, bulk update
+  const size_t gemm_smem_h = gemm_smem_bytes(KC_DEFAULT, STAGES_DEFAULT, TN / 2);     // 128x64 tiles
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1, 4, KC_BULK, STAGES_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
 
   // second stream + events for the look-ahead
@@ -469,6 +614,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     c->lu_events.push_back(ev);
   }
   cudaStream_t sB = c->stream2;
+  const int launches_before = launches;
   // B200RT_SOLVE_TRACE=1: timestamp every chain / update of the factorisation (development aid)
   static const bool trace = getenv("B200RT_SOLVE_TRACE") != nullptr;
   struct Mark { const char *what; int KB; cudaEvent_t ev; };
@@ -482,7 +628,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   };
   auto chain = [&](int KB, cudaStream_t s) {       // invert the diagonal block, form L21, forward-substitute
     const int m1 = nK - KB - 1;
-    gj128_kernel<<<1, 256, 0, s>>>(A, np, KB, dinv);
+    gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
     launches++;
     if (m1 > 0) {
       gemm128_kernel<2, 4><<<dim3(m1, 2), 256, gemm_smem_h, s>>>(A, np, KB, dinv, Lbuf(KB));
@@ -490,42 +636,76 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       launches += 2;
     }
   };
-  cudaEvent_t ev_start = c->lu_events[2 * nK];
-  B200RT_CUDA(c, cudaEventRecord(ev_start, st));
-  B200RT_CUDA(c, cudaStreamWaitEvent(sB, ev_start, 0));
-  mark("start", 0, st);
-  mark("chain_begin", 0, sB);
-  chain(0, sB);
-  mark("chain_end", 0, sB);
-  B200RT_CUDA(c, cudaEventRecord(c->lu_events[0], sB));            // evP[0]
-  for (int KB = 0; KB < nK; KB++) {
-    B200RT_CUDA(c, cudaStreamWaitEvent(st, c->lu_events[2 * KB], 0)); // block column KB factored
-    const int m1 = nK - KB - 1;                                       // block columns after KB
-    if (m1 > 0) {
-      mark("ui_begin", KB, st);
-      gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
-      mark("ui_end", KB, st);
-      launches++;
-      B200RT_CUDA(c, cudaEventRecord(c->lu_events[2 * KB + 1], st));  // evU[KB]
-      B200RT_CUDA(c, cudaStreamWaitEvent(sB, c->lu_events[2 * KB + 1], 0));
-      mark("chain_begin", KB + 1, sB);
-      chain(KB + 1, sB);
-      mark("chain_end", KB + 1, sB);
-      B200RT_CUDA(c, cudaEventRecord(c->lu_events[2 * KB + 2], sB));  // evP[KB+1]
-      const int m2 = m1 - 1;
-      if (m2 > 0) {
-        gemm128_kernel<1, 8><<<m2 * m2, 256, gemm_smem, st>>>(A, np, KB, dinv, Lbuf(KB));
-        mark("uii_end", KB, st);
+  // The ~280 launches of the factorisation and back substitution (two streams, ~140 event dependencies) are captured
+  // once per (np, workspace) into a CUDA graph and replayed: on the last ~27 block columns the critical path is a chain
+  // of short kernels, and the graph removes the host launch gaps between them.
+  auto record = [&]() -> cudaError_t {
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+    cudaEvent_t ev_start = c->lu_events[2 * nK];
+    CK(cudaEventRecord(ev_start, st));
+    CK(cudaStreamWaitEvent(sB, ev_start, 0));
+    mark("start", 0, st);
+    mark("chain_begin", 0, sB);
+    chain(0, sB);
+    mark("chain_end", 0, sB);
+    CK(cudaEventRecord(c->lu_events[0], sB));            // evP[0]
+    for (int KB = 0; KB < nK; KB++) {
+      CK(cudaStreamWaitEvent(st, c->lu_events[2 * KB], 0)); // block column KB factored
+      const int m1 = nK - KB - 1;                                       // block columns after KB
+      if (m1 > 0) {
+        mark("ui_begin", KB, st);
+        gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
+        mark("ui_end", KB, st);
         launches++;
+        CK(cudaEventRecord(c->lu_events[2 * KB + 1], st));  // evU[KB]
+        CK(cudaStreamWaitEvent(sB, c->lu_events[2 * KB + 1], 0));
+        mark("chain_begin", KB + 1, sB);
+        chain(KB + 1, sB);
+        mark("chain_end", KB + 1, sB);
+        CK(cudaEventRecord(c->lu_events[2 * KB + 2], sB));  // evP[KB+1]
+        const int m2 = m1 - 1;
+        if (m2 > 0) {
+          gemm128_kernel<1, 4, KC_BULK, STAGES_BULK><<<dim3(m2 * m2, 2), 256, gemm_smem, st>>>(A, np, KB, dinv, Lbuf(KB));
+          mark("uii_end", KB, st);
+          launches++;
+        }
       }
     }
+    mark("factor_end", 0, st);
+    for (int KB = nK - 1; KB >= 0; KB--) {
+      backsolve128_kernel<<<KB + 1, 512, 0, st>>>(A, np, KB, dinv, b, x);
+      launches++;
+    }
+    mark("backsolve_end", 0, st);
+  return cudaGetLastError();
+#undef CK
+  };
+  if (trace) {
+    B200RT_CUDA(c, record());
+  } else {
+    if (c->lu_graph && (c->lu_graph_np != np || c->lu_graph_A != A || c->lu_graph_dinv != dinv)) {
+      cudaGraphExecDestroy(c->lu_graph);
+      c->lu_graph = nullptr;
+    }
+    if (!c->lu_graph) {
+      cudaGraph_t graph = nullptr;
+      launches = 0;
+      B200RT_CUDA(c, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const cudaError_t e_rec = record();
+      const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
+      if (e_rec != cudaSuccess || e_end != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        B200RT_CUDA(c, e_rec != cudaSuccess ? e_rec : e_end);
+      }
+      const cudaError_t e_inst = cudaGraphInstantiate(&c->lu_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      B200RT_CUDA(c, e_inst);
+      c->lu_graph_np = np; c->lu_graph_A = A; c->lu_graph_dinv = dinv; c->lu_graph_launches = launches;
+      launches = launches_before;
+    }
+    B200RT_CUDA(c, cudaGraphLaunch(c->lu_graph, st));
+    launches += c->lu_graph_launches;
   }
-  mark("factor_end", 0, st);
-  for (int KB = nK - 1; KB >= 0; KB--) {
-    backsolve128_kernel<<<KB + 1, 512, 0, st>>>(A, np, KB, dinv, b, x);
-    launches++;
-  }
-  mark("backsolve_end", 0, st);
   B200RT_CUDA(c, cudaGetLastError());
   B200RT_CUDA(c, cudaMemcpyAsync(S, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
   residual_kernel<<<(n + 7) / 8, 256, 0, st>>>(K, n, branching, S0, S, rabs);
