@@ -3,6 +3,7 @@
 #include <csignal>
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 #include <execinfo.h>
 #include <unistd.h>
 #include <string>
@@ -67,6 +68,8 @@ int obsfit_set_use_CO2_absorption(void *h, int use) { return guard([&] { static_
 int obsfit_set_CO2_exobase_density(void *h, double n) { return guard([&] { static_cast<observation_fit *>(h)->set_CO2_exobase_density(n); }); }
 int obsfit_save_influence_matrix(void *h, const char *fname) { return guard([&] { static_cast<observation_fit *>(h)->save_influence_matrix(fname); }); }
 // which: 0 brightness, 1 species_col_dens, 2 tau_species_final, 3 tau_absorber_final, 4 iph observed, 5 iph unextincted
+// [2][n_obs];  6 D_brightness, 7 D_col_dens, 8 tau_D_final [2][n_obs];  9 O_1026_brightness [6][n_obs];
+// 10 lyman_multiplet_brightness, 11 lyman_singlet_brightness [2][n_obs]
 int obsfit_get(void *h, int which, double *out) {
   return guard([&] {
     auto *o = static_cast<observation_fit *>(h);
@@ -76,8 +79,100 @@ int obsfit_get(void *h, int which, double *out) {
       case 2: flatten(o->tau_species_final(), out); break;
       case 3: flatten(o->tau_absorber_final(), out); break;
       case 4: flatten(o->iph_brightness_observed(), out); break;
-      default: flatten(o->iph_brightness_unextincted(), out); break;
+      case 5: flatten(o->iph_brightness_unextincted(), out); break;
+      case 6: flatten(o->D_brightness(), out); break;
+      case 7: flatten(o->D_col_dens(), out); break;
+      case 8: flatten(o->tau_D_final(), out); break;
+      case 9: flatten(o->O_1026_brightness(), out); break;
+      case 10: flatten(o->lyman_multiplet_brightness(), out); break;
+      case 11: flatten(o->lyman_singlet_brightness(), out); break;
+      default: throw std::invalid_argument("obsfit_get: unknown quantity");
     }
+  });
+}
+// ---- the other generate_source_function* members (names as observation_fit's)
+static std::string str(const char *p) { return p ? p : ""; }
+int obsfit_generate_source_function_ex(void *h, double nH, double T, const char *atmosphere_fname, const char *sourcefn_fname,
+                                       int plane_parallel, int deuterium) {
+  return guard([&] { static_cast<observation_fit *>(h)->generate_source_function(nH, T, str(atmosphere_fname), str(sourcefn_fname), plane_parallel != 0, deuterium != 0); });
+}
+int obsfit_generate_source_function_lc(void *h, double nH, double lc, int plane_parallel, int deuterium) {
+  return guard([&] { static_cast<observation_fit *>(h)->generate_source_function_lc(nH, lc, "", "", plane_parallel != 0, deuterium != 0); });
+}
+int obsfit_generate_source_function_effv(void *h, double nH, double effv, int plane_parallel, int deuterium) {
+  return guard([&] { static_cast<observation_fit *>(h)->generate_source_function_effv(nH, effv, "", "", plane_parallel != 0, deuterium != 0); });
+}
+int obsfit_generate_source_function_variable_thermosphere(void *h, double nH, double T, double nCO2rmin, double rexo, double rmin,
+                                                          double rmax, double rmindiffusion, double T_tropo, double r_tropo,
+                                                          double shape_parameter, int plane_parallel, int deuterium) {
+  return guard([&] {
+    static_cast<observation_fit *>(h)->generate_source_function_variable_thermosphere(nH, T, nCO2rmin, rexo, rmin, rmax, rmindiffusion, T_tropo,
+                                                                                      r_tropo, shape_parameter, "", "", plane_parallel != 0,
+                                                                                      deuterium != 0);
+  });
+}
+int obsfit_generate_source_function_nH_asym(void *h, double nH, double T, double asym, int deuterium) {
+  return guard([&] { static_cast<observation_fit *>(h)->generate_source_function_nH_asym(nH, T, asym, "", deuterium != 0); });
+}
+int obsfit_generate_source_function_temp_asym(void *h, double nHavg, double Tnoon, double Tmidnight, int deuterium) {
+  return guard([&] { static_cast<observation_fit *>(h)->generate_source_function_temp_asym(nHavg, Tnoon, Tmidnight, "", deuterium != 0); });
+}
+int obsfit_generate_source_function_tabular_atmosphere(void *h, double rmin, double rexo, double rmax, int n_nH, const double *alt_nH,
+                                                       const double *log_nH, int n_nCO2, const double *alt_nCO2, const double *log_nCO2,
+                                                       int n_T, const double *alt_T, const double *T, int compute_exosphere,
+                                                       int plane_parallel, int deuterium) {
+  return guard([&] {
+    typedef std::vector<double> V;
+    static_cast<observation_fit *>(h)->generate_source_function_tabular_atmosphere(
+        rmin, rexo, rmax, V(alt_nH, alt_nH + n_nH), V(log_nH, log_nH + n_nH), V(alt_nCO2, alt_nCO2 + n_nCO2), V(log_nCO2, log_nCO2 + n_nCO2),
+        V(alt_T, alt_T + n_T), V(T, T + n_T), compute_exosphere != 0, plane_parallel != 0, deuterium != 0, "");
+  });
+}
+int obsfit_O_1026_generate_source_function(void *h, double nO, double T, double solar_lyman_beta, const char *sourcefn_fname) {
+  return guard([&] { static_cast<observation_fit *>(h)->O_1026_generate_source_function(nO, T, solar_lyman_beta, "", str(sourcefn_fname)); });
+}
+int obsfit_lyman_multiplet_generate_source_function(void *h, double nH, double T, const char *sourcefn_fname) {
+  return guard([&] { static_cast<observation_fit *>(h)->lyman_multiplet_generate_source_function(nH, T, "", str(sourcefn_fname)); });
+}
+int obsfit_lyman_singlet_generate_source_function(void *h, double nH, double T, const char *sourcefn_fname) {
+  return guard([&] { static_cast<observation_fit *>(h)->lyman_singlet_generate_source_function(nH, T, "", str(sourcefn_fname)); });
+}
+int obsfit_save_influence_matrix_O_1026(void *h, const char *fname) { return guard([&] { static_cast<observation_fit *>(h)->save_influence_matrix_O_1026(fname); }); }
+// options
+int obsfit_set_use_temp_dependent_sH(void *h, int use, double constant_temp) { return guard([&] { static_cast<observation_fit *>(h)->set_use_temp_dependent_sH(use != 0, constant_temp); }); }
+int obsfit_set_sza_method(void *h, int uniform_cos) {
+  return guard([&] { uniform_cos ? static_cast<observation_fit *>(h)->set_sza_method_uniform_cos() : static_cast<observation_fit *>(h)->set_sza_method_uniform(); });
+}
+// kind 0: species density, 1: species temperature (set_H_density_tweak[_values], set_H_temp_tweak[_values])
+int obsfit_set_tweak(void *h, int kind, int on, int n, const int *voxels, double factor) {
+  return guard([&] {
+    auto *o = static_cast<observation_fit *>(h);
+    std::vector<int> v(voxels, voxels + n);
+    if (kind == 0) { o->set_H_density_tweak(on != 0); o->set_H_density_tweak_values(v, factor); }
+    else { o->set_H_temp_tweak(on != 0); o->set_H_temp_tweak_values(v, factor); }
+  });
+}
+// which 0: lc_from_T, 1: eff_from_T, 2: T_from_lc, 3: T_from_eff  (observation_fit::Tconv)
+int obsfit_Tconv(void *h, int which, double x, double *out) {
+  return guard([&] {
+    auto &t = static_cast<observation_fit *>(h)->Tconv;
+    *out = which == 0 ? t.lc_from_T(x) : which == 1 ? t.eff_from_T(x) : which == 2 ? t.T_from_lc(x) : t.T_from_eff(x);
+  });
+}
+// source function / radial boundaries of model `which` (0 H, 1 D, 2 plane-parallel H, 3 plane-parallel D)
+int obsfit_source_function_ex(void *h, int e, int which, double *out) {
+  return guard([&] { auto s = static_cast<observation_fit *>(h)->source_function(e, which); std::memcpy(out, s.data(), s.size() * sizeof(double)); });
+}
+int obsfit_radial_boundaries_ex(void *h, int which, double *out) {
+  return guard([&] { auto s = static_cast<observation_fit *>(h)->radial_boundaries(which); std::memcpy(out, s.data(), s.size() * sizeof(double)); });
+}
+// model 0: O I 102.6 (n = 741*3), 1: Lyman multiplet (741*4), 2: Lyman singlet (741*2); returns the length in *n
+int obsfit_multiplet_source_function(void *h, int model, double *out, int capacity, int *n) {
+  return guard([&] {
+    auto s = static_cast<observation_fit *>(h)->multiplet_source_function(model);
+    if ((int) s.size() > capacity) throw std::invalid_argument("obsfit_multiplet_source_function: buffer too small");
+    std::memcpy(out, s.data(), s.size() * sizeof(double));
+    if (n) *n = (int) s.size();
   });
 }
 int obsfit_source_function(void *h, int e, double *out) {

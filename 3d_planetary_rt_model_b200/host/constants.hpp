@@ -1,6 +1,7 @@
 // constants.hpp -- physical constants of the host facade; values as the reference's src/constants.hpp:9-63
 #pragma once
 #include <cmath>
+#include <string>
 
 namespace b200rt_host {
 
@@ -16,6 +17,7 @@ constexpr Real mCO2 = 44 * mH;
 constexpr Real line_f_coeff = 2.647e-2;        // cm^2 Hz
 constexpr Real aMars_typical = 1.41;           // AU
 constexpr Real pi = M_PI;
+constexpr Real rexo_typical = rMars + 200e5;   // typical exobase altitude (constants.hpp:12)
 
 constexpr Real lyman_alpha_lambda = 121.6e-7;  // cm
 constexpr Real lyman_alpha_f = 0.41641;

@@ -1,7 +1,8 @@
 """ctypes binding of the C handles over the C++ observation_fit facade (host/capi.cpp, libb200rt_host.so).
 
-The class below has the method names of the reference's Cython class Pyobservation_fit
-(python/py_corona_sim.pyx:176-562) for the H Lyman alpha / beta path, plus brightness_batch."""
+The class below has the method names and argument lists of the reference's Cython class Pyobservation_fit
+(python/py_corona_sim.pyx:176-562), plus brightness_batch and accessors for the solutions.  (The reference's own
+.pyx also compiles unchanged against the facade: oracle/build_pyx.py.)"""
 from __future__ import annotations
 
 import ctypes as C
@@ -30,7 +31,27 @@ SIGNATURES = {
     "obsfit_radial_boundaries": (C.c_int, [_vp, _dp]),
     "obsfit_brightness_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_double)]),
     "obsfit_atmosphere_tables": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "obsfit_generate_source_function_ex": (C.c_int, [_vp, C.c_double, C.c_double, C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
+    "obsfit_generate_source_function_lc": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "obsfit_generate_source_function_effv": (C.c_int, [_vp, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "obsfit_generate_source_function_variable_thermosphere": (C.c_int, [_vp] + [C.c_double] * 10 + [C.c_int, C.c_int]),
+    "obsfit_generate_source_function_nH_asym": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "obsfit_generate_source_function_temp_asym": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "obsfit_generate_source_function_tabular_atmosphere": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp,
+                                                                     C.c_int, _dp, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_int]),
+    "obsfit_O_1026_generate_source_function": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, C.c_char_p]),
+    "obsfit_lyman_multiplet_generate_source_function": (C.c_int, [_vp, C.c_double, C.c_double, C.c_char_p]),
+    "obsfit_lyman_singlet_generate_source_function": (C.c_int, [_vp, C.c_double, C.c_double, C.c_char_p]),
+    "obsfit_save_influence_matrix_O_1026": (C.c_int, [_vp, C.c_char_p]),
+    "obsfit_set_use_temp_dependent_sH": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "obsfit_set_sza_method": (C.c_int, [_vp, C.c_int]),
+    "obsfit_set_tweak": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"), C.c_double]),
+    "obsfit_Tconv": (C.c_int, [_vp, C.c_int, C.c_double, C.POINTER(C.c_double)]),
+    "obsfit_source_function_ex": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
+    "obsfit_radial_boundaries_ex": (C.c_int, [_vp, C.c_int, _dp]),
+    "obsfit_multiplet_source_function": (C.c_int, [_vp, C.c_int, _dp, C.c_int, C.POINTER(C.c_int)]),
 }
+MODEL_H, MODEL_D, MODEL_H_PP, MODEL_D_PP = 0, 1, 2, 3
 _lib = None
 
 
@@ -92,8 +113,78 @@ class Pyobservation_fit:
                                                         len(ra), np.ascontiguousarray(ra, dtype=np.float64),
                                                         np.ascontiguousarray(dec, dtype=np.float64)))
 
-    def generate_source_function(self, nH, T, sourcefn_fname=""):
-        self._ck(self.lib.obsfit_generate_source_function(self.h, nH, T, os.fsencode(sourcefn_fname)))
+    def generate_source_function(self, nH, T, atmosphere_fname="", sourcefn_fname="", plane_parallel=False, deuterium=False):
+        self._ck(self.lib.obsfit_generate_source_function_ex(self.h, nH, T, os.fsencode(atmosphere_fname), os.fsencode(sourcefn_fname),
+                                                             int(plane_parallel), int(deuterium)))
+
+    def generate_source_function_lc(self, nH, lc, plane_parallel=False, deuterium=False):
+        self._ck(self.lib.obsfit_generate_source_function_lc(self.h, nH, lc, int(plane_parallel), int(deuterium)))
+
+    def generate_source_function_effv(self, nH, effv, plane_parallel=False, deuterium=False):
+        self._ck(self.lib.obsfit_generate_source_function_effv(self.h, nH, effv, int(plane_parallel), int(deuterium)))
+
+    def generate_source_function_variable_thermosphere(self, nHexo, Texo, nCO2rmin, rexo, rmin, rmax, rmindiffusion, T_tropo,
+                                                       r_tropo, shape_parameter, plane_parallel=False, deuterium=False):
+        self._ck(self.lib.obsfit_generate_source_function_variable_thermosphere(
+            self.h, nHexo, Texo, nCO2rmin, rexo, rmin, rmax, rmindiffusion, T_tropo, r_tropo, shape_parameter,
+            int(plane_parallel), int(deuterium)))
+
+    def generate_source_function_nH_asym(self, nH, Texo, asym, deuterium=False):
+        self._ck(self.lib.obsfit_generate_source_function_nH_asym(self.h, nH, Texo, asym, int(deuterium)))
+
+    def generate_source_function_temp_asym(self, nHavg, Tnoon, Tmidnight, deuterium=False):
+        self._ck(self.lib.obsfit_generate_source_function_temp_asym(self.h, nHavg, Tnoon, Tmidnight, int(deuterium)))
+
+    def generate_source_function_tabular_atmosphere(self, atm_dict, compute_exosphere=False, plane_parallel=False, deuterium=False):
+        a = {k: np.ascontiguousarray(atm_dict[k], dtype=np.float64) for k in ("alt_nH", "log_nH", "alt_nCO2", "log_nCO2", "alt_Temp", "Temp")}
+        self._ck(self.lib.obsfit_generate_source_function_tabular_atmosphere(
+            self.h, atm_dict["rmin"], atm_dict["rexo"], atm_dict["rmax"], len(a["alt_nH"]), a["alt_nH"], a["log_nH"],
+            len(a["alt_nCO2"]), a["alt_nCO2"], a["log_nCO2"], len(a["alt_Temp"]), a["alt_Temp"], a["Temp"],
+            int(compute_exosphere), int(plane_parallel), int(deuterium)))
+
+    def O_1026_generate_source_function(self, nO, T, solar_brightness_lyman_beta, sourcefn_fname=""):
+        self._ck(self.lib.obsfit_O_1026_generate_source_function(self.h, nO, T, solar_brightness_lyman_beta, os.fsencode(sourcefn_fname)))
+
+    def lyman_multiplet_generate_source_function(self, nH, T, sourcefn_fname=""):
+        self._ck(self.lib.obsfit_lyman_multiplet_generate_source_function(self.h, nH, T, os.fsencode(sourcefn_fname)))
+
+    def lyman_singlet_generate_source_function(self, nH, T, sourcefn_fname=""):
+        self._ck(self.lib.obsfit_lyman_singlet_generate_source_function(self.h, nH, T, os.fsencode(sourcefn_fname)))
+
+    def save_influence_matrix_O_1026(self, fname):
+        self._ck(self.lib.obsfit_save_influence_matrix_O_1026(self.h, os.fsencode(fname)))
+
+    def set_use_temp_dependent_sH(self, use=True, constant_temp_sH=-1.0):
+        self._ck(self.lib.obsfit_set_use_temp_dependent_sH(self.h, int(use), constant_temp_sH))
+
+    def set_sza_method_uniform(self):
+        self._ck(self.lib.obsfit_set_sza_method(self.h, 0))
+
+    def set_sza_method_uniform_cos(self):
+        self._ck(self.lib.obsfit_set_sza_method(self.h, 1))
+
+    def set_H_density_tweak(self, on, voxels=(), factor=1.0):
+        self._ck(self.lib.obsfit_set_tweak(self.h, 0, int(on), len(voxels), np.ascontiguousarray(voxels, dtype=np.int32), factor))
+
+    def set_H_temp_tweak(self, on, voxels=(), factor=1.0):
+        self._ck(self.lib.obsfit_set_tweak(self.h, 1, int(on), len(voxels), np.ascontiguousarray(voxels, dtype=np.int32), factor))
+
+    def _tconv(self, which, x):
+        out = C.c_double(0)
+        self._ck(self.lib.obsfit_Tconv(self.h, which, float(x), C.byref(out)))
+        return out.value
+
+    def lc_from_T(self, T):
+        return self._tconv(0, T)
+
+    def eff_from_T(self, T):
+        return self._tconv(1, T)
+
+    def T_from_lc(self, lc):
+        return self._tconv(2, lc)
+
+    def T_from_eff(self, eff):
+        return self._tconv(3, eff)
 
     def set_use_CO2_absorption(self, use=True):
         self._ck(self.lib.obsfit_set_use_CO2_absorption(self.h, int(use)))
@@ -104,10 +195,34 @@ class Pyobservation_fit:
     def save_influence_matrix(self, fname):
         self._ck(self.lib.obsfit_save_influence_matrix(self.h, os.fsencode(fname)))
 
-    def _get(self, which):
-        out = np.zeros((self.n_emissions, self.n_obs))
+    def _get(self, which, rows=None):
+        out = np.zeros((rows or self.n_emissions, self.n_obs))
         self._ck(self.lib.obsfit_get(self.h, which, out))
         return out
+
+    def D_brightness(self):
+        return self._get(6)
+
+    def D_col_dens(self):
+        return self._get(7)
+
+    def tau_D_final(self):
+        return self._get(8)
+
+    def O_1026_brightness(self):
+        return self._get(9, 6)
+
+    def lyman_multiplet_brightness(self):
+        return self._get(10)
+
+    def lyman_singlet_brightness(self):
+        return self._get(11)
+
+    def multiplet_source_function(self, model):
+        out = np.zeros(self.n_vox * 4)
+        n = C.c_int(0)
+        self._ck(self.lib.obsfit_multiplet_source_function(self.h, model, out, len(out), C.byref(n)))
+        return out[:n.value].copy()
 
     def brightness(self):
         return self._get(0)
@@ -127,14 +242,14 @@ class Pyobservation_fit:
     def iph_brightness_unextincted(self):
         return self._get(5)
 
-    def source_function(self, e):
-        out = np.zeros(self.n_vox)
-        self._ck(self.lib.obsfit_source_function(self.h, e, out))
+    def source_function(self, e, which=MODEL_H):
+        out = np.zeros(self.n_vox if which < 2 else self.n_rb - 1)
+        self._ck(self.lib.obsfit_source_function_ex(self.h, e, which, out))
         return out
 
-    def radial_boundaries(self):
+    def radial_boundaries(self, which=MODEL_H):
         out = np.zeros(self.n_rb)
-        self._ck(self.lib.obsfit_radial_boundaries(self.h, out))
+        self._ck(self.lib.obsfit_radial_boundaries_ex(self.h, which, out))
         return out
 
     def brightness_batch(self, nH, T, contexts_per_gpu=4, n_gpus=-1):

@@ -47,7 +47,7 @@ def test_facade_matches_oracle_pipeline(synth, hb, oraclebind, tmp_path):
     F = hb.Pyobservation_fit()
     locs, dirs = synth.random_los(1500)
     F.add_observation(locs, dirs)
-    F.generate_source_function(nH, T, str(tmp_path / "S.dat"))
+    F.generate_source_function(nH, T, sourcefn_fname=str(tmp_path / "S.dat"))
     b = F.brightness()
     scn = synth.make_scenario(40, 20, 7, 12, n_em=2, nH_exo=nH, T_exo=T)
     O = oraclebind.OracleModel(scn, "f64")
