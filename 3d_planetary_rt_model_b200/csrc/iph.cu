@@ -48,28 +48,37 @@ __device__ __forceinline__ float asin_core(float a) {   // 0 <= a <= 0.5
   p = p * z + 1.6666752422E-1f;
   return p * z * a + a;
 }
+// one evaluation path for every lane (the three ranges of the CPU restatement folded into selects; the float
+// operations that produce the result are the same ones, so the value is bit-identical)
 __device__ __forceinline__ float acos_poly(float x) {
   const float PIO2 = 1.5707963267948966f, PI_F = 3.14159265358979f;
   if (x > 1.f) x = 1.f;
   if (x < -1.f) x = -1.f;
-  if (x > 0.5f) return 2.f * asin_core(sqrtf(0.5f * (1.f - x)));
-  if (x < -0.5f) return PI_F - 2.f * asin_core(sqrtf(0.5f * (1.f + x)));
-  if (x >= 0.f) return PIO2 - asin_core(x);
-  return PIO2 + asin_core(-x);
+  const float a = fabsf(x);
+  const bool big = a > 0.5f;
+  const float s = asin_core(big ? sqrtf(0.5f * (1.f - a)) : a);
+  const float two_s = 2.f * s;
+  const float r_big = (x > 0.f) ? two_s : PI_F - two_s;
+  const float r_small = (x >= 0.f) ? PIO2 - s : PIO2 + s;
+  return big ? r_big : r_small;
 }
 
 struct Tables {
   const float *alt, *ang, *dans, *so, *sn;   // shared memory
+  const float *dma;                           // dma[k] = (alt[k] - alt[k-1]) / 3 / UA: TOP's step limit (:473-476)
   int kmax, lmax;
 };
+// Where the previous look-up of this line of sight landed.  Consecutive look-ups are a fraction of a table cell
+// apart (TOP steps by a third of the altitude cell at most), so the lower-bound searches start from the previous
+// bracket and walk: 0-1 steps instead of the 5-6 halvings of a binary search.  The bracket found is the same.
+struct Hint { int alt, ang; };
 
 // first j with T <= ang[j]  (the Fortran's arithmetic-IF scan, :517-528)
-__device__ __forceinline__ void bracket_ang(const Tables &t, float T, int &ll, int &llp, float &dt) {
-  int lo = 0, hi = t.lmax;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (t.ang[mid] < T) lo = mid + 1; else hi = mid;
-  }
+__device__ __forceinline__ void bracket_ang(const Tables &t, float T, int &ll, int &llp, float &dt, Hint &h) {
+  int lo = h.ang;
+  while (lo > 0 && !(t.ang[lo - 1] < T)) lo--;
+  while (lo < t.lmax && t.ang[lo] < T) lo++;
+  h.ang = min(lo, t.lmax - 1);
   if (lo >= t.lmax) {
     ll = t.lmax - 2; llp = t.lmax - 1;
     dt = (T - t.ang[ll]) / (t.ang[llp] - t.ang[ll]);
@@ -82,12 +91,11 @@ __device__ __forceinline__ void bracket_ang(const Tables &t, float T, int &ll, i
     dt = (T - t.ang[ll]) / (t.ang[llp] - t.ang[ll]);
   }
 }
-__device__ __forceinline__ void bracket_alt(const Tables &t, float Z, int &kk, int &kkp, float &du) {
-  int lo = 0, hi = t.kmax;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (t.alt[mid] < Z) lo = mid + 1; else hi = mid;
-  }
+__device__ __forceinline__ void bracket_alt(const Tables &t, float Z, int &kk, int &kkp, float &du, Hint &h) {
+  int lo = h.alt;
+  while (lo > 0 && !(t.alt[lo - 1] < Z)) lo--;
+  while (lo < t.kmax && t.alt[lo] < Z) lo++;
+  h.alt = min(lo, t.kmax - 1);
   if (lo >= t.kmax) { kk = kkp = t.kmax - 1; du = 0.f; }
   else if (Z == t.alt[lo]) { kk = lo; kkp = (lo + 1 < t.kmax) ? lo + 1 : lo; du = 0.f; }
   else {
@@ -96,14 +104,14 @@ __device__ __forceinline__ void bracket_alt(const Tables &t, float Z, int &kk, i
   }
 }
 
-__device__ __forceinline__ float den(const Tables &t, float Z, float T, int &ko) {   // DEN :492-547
+__device__ __forceinline__ float den(const Tables &t, float Z, float T, int &ko, Hint &h) {   // DEN :492-547
   ko = 1;
   if (Z < t.alt[0]) return 0.f;
   if (Z > t.alt[t.kmax - 1]) Z = t.alt[t.kmax - 1];
   int ll, llp, kk, kkp;
   float dt, du;
-  bracket_ang(t, T, ll, llp, dt);
-  bracket_alt(t, Z, kk, kkp, du);
+  bracket_ang(t, T, ll, llp, dt, h);
+  bracket_alt(t, Z, kk, kkp, du, h);
   const float a = t.dans[kk * t.lmax + ll], b = t.dans[kkp * t.lmax + ll];
   const float c = t.dans[kk * t.lmax + llp], d = t.dans[kkp * t.lmax + llp];
   const float fl = a + du * (b - a);
@@ -139,7 +147,7 @@ __device__ __forceinline__ float holstein_T(float TO) {   // T :363-397
   return T;
 }
 
-__device__ float top(const Tables &t, const IphConst &c, float XF, float YF, float ZF, float XH, float YH, float ZH) {   // TOP :399-490
+__device__ float top(const Tables &t, const IphConst &c, float XF, float YF, float ZF, float XH, float YH, float ZH, Hint &h) {   // TOP :399-490
   const float UA = c.ua;
   float XA = XF / UA, XB = XH / UA, YA = YF / UA, YB = YH / UA, ZA = ZF / UA, ZB = ZH / UA;
   const float altp = t.alt[0] / UA;
@@ -160,10 +168,10 @@ __device__ float top(const Tables &t, const IphConst &c, float XF, float YF, flo
   const float DSA0 = NORME / 20.f;
   float TA = acos_poly(YA / RA) / c.dpi;
   int KP;
-  float DN1 = den(t, RA * UA, TA, KP);
+  float DN1 = den(t, RA * UA, TA, KP, h);
   DN1 = c.dinf_b * DN1;
   if (KP == t.kmax) KP = KP - 1;
-  float DMA = (t.alt[KP] - t.alt[KP - 1]) / 3.f / UA;
+  float DMA = t.dma[KP];
   float DSAB = fminf(DMA, DSA0);
   float SAB = 0.f, DT = 0.f;
   do {
@@ -173,12 +181,12 @@ __device__ float top(const Tables &t, const IphConst &c, float XF, float YF, flo
     SAB = SAB + DSAB;
     RA = sqrtf(XA * XA + YA * YA + ZA * ZA);
     TA = acos_poly(YA / RA) / c.dpi;
-    float DN = den(t, RA * UA, TA, KP);
+    float DN = den(t, RA * UA, TA, KP, h);
     DN = c.dinf_b * DN;
     DT = DT + (DN + DN1) * .5f * DSAB * c.sig * UA;
     DN1 = DN;
     if (KP == t.kmax) KP = KP - 1;
-    DMA = (t.alt[KP] - t.alt[KP - 1]) / 3.f / UA;
+    DMA = t.dma[KP];
     DSAB = fminf(DMA, DSA0);
   } while (SAB <= NORME);
   return DT;
@@ -192,13 +200,18 @@ iph_kernel(IphConst c, const float *__restrict__ g_alt, const float *__restrict_
   extern __shared__ float smf[];
   const int nt = c.kmax * c.lmax;
   float *s_alt = smf, *s_ang = s_alt + c.kmax, *s_dans = s_ang + c.lmax, *s_so = s_dans + nt, *s_sn = s_so + nt;
-  for (int i = threadIdx.x; i < c.kmax; i += blockDim.x) s_alt[i] = g_alt[i];
+  float *s_dma = s_sn + nt;
+  for (int i = threadIdx.x; i < c.kmax; i += blockDim.x) {
+    s_alt[i] = g_alt[i];
+    s_dma[i] = (i > 0) ? (g_alt[i] - g_alt[i - 1]) / 3.f / c.ua : 0.f;
+  }
   for (int i = threadIdx.x; i < c.lmax; i += blockDim.x) s_ang[i] = g_ang[i];
   for (int i = threadIdx.x; i < nt; i += blockDim.x) { s_dans[i] = g_dans[i]; s_so[i] = g_so[i]; s_sn[i] = g_sn[i]; }
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_los) return;
-  Tables t = {s_alt, s_ang, s_dans, s_so, s_sn, c.kmax, c.lmax};
+  Tables t = {s_alt, s_ang, s_dans, s_so, s_sn, s_dma, c.kmax, c.lmax};
+  Hint h = {c.kmax - 1, 0}, h_out = {c.kmax - 1, 0};   // inner march (TOP) and outer march keep their own brackets
 
   const float U = c.a11 * u1[i] + c.a12 * v1[i];                       // :297-299
   const float V = c.a21 * u1[i] + c.a22 * v1[i] + c.a23 * w1[i];
@@ -214,7 +227,7 @@ iph_kernel(IphConst c, const float *__restrict__ g_alt, const float *__restrict_
     for (;;) {
       const float TETA = acos_poly(YP / R) / c.dpi;
       int KO;
-      const float DNA = den(t, R, TETA, KO);
+      const float DNA = den(t, R, TETA, KO, h_out);
       float DN1 = c.dinf_b * DNA;
       if (DN1 == 0.f) DN1 = 1.f;
       float DP = c.dtap * 0.05f / DN1;
@@ -235,8 +248,8 @@ iph_kernel(IphConst c, const float *__restrict__ g_alt, const float *__restrict_
       if (!(R < t.alt[0] || R >= t.alt[t.kmax - 1])) {
         int ll, llp, kk, kkp;
         float dt, du;
-        bracket_ang(t, TETA2, ll, llp, dt);
-        bracket_alt(t, R, kk, kkp, du);
+        bracket_ang(t, TETA2, ll, llp, dt, h_out);
+        bracket_alt(t, R, kk, kkp, du, h_out);
         float fl = t.sn[kk * t.lmax + ll] + du * (t.sn[kkp * t.lmax + ll] - t.sn[kk * t.lmax + ll]);
         float flp = t.sn[kk * t.lmax + llp] + du * (t.sn[kkp * t.lmax + llp] - t.sn[kk * t.lmax + llp]);
         FN = fl + dt * (flp - fl);
@@ -244,7 +257,7 @@ iph_kernel(IphConst c, const float *__restrict__ g_alt, const float *__restrict_
         flp = t.so[kk * t.lmax + llp] + du * (t.so[kkp * t.lmax + llp] - t.so[kk * t.lmax + llp]);
         FOO = fl + dt * (flp - fl);
       }
-      const float DTT = top(t, c, XAV, YAV, ZAV, XP, YP, ZP);
+      const float DTT = top(t, c, XAV, YAV, ZAV, XP, YP, ZP, h);
       const float cosff = (U * XP + V * YP + W * ZP) / R;
       const float corec = 0.25f * cosff * cosff + (11.f / 12.f);
       TT = TT + DTT * c.dinf_o / c.dinf_b;
@@ -387,7 +400,7 @@ int iph_background(b200rt_ctx *c, float fs, float xpos, float ypos, float zpos, 
   B200RT_CUDA(c, cudaMemcpyAsync(d_w, w1, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   const int nt = T.kmax * T.lmax;
   const float *tab = T.dev.as<float>();
-  const size_t smem = (size_t) (T.kmax + T.lmax + 3 * nt) * sizeof(float);
+  const size_t smem = (size_t) (2 * T.kmax + T.lmax + 3 * nt) * sizeof(float);   // axes, step table, DANS, SO, SN
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, c->stream);
