@@ -73,35 +73,49 @@ struct Tables {
 // bracket and walk: 0-1 steps instead of the 5-6 halvings of a binary search.  The bracket found is the same.
 struct Hint { int alt, ang; };
 
-// first j with T <= ang[j]  (the Fortran's arithmetic-IF scan, :517-528)
-__device__ __forceinline__ void bracket_ang(const Tables &t, float T, int &ll, int &llp, float &dt, Hint &h) {
-  int lo = h.ang;
-  while (lo > 0 && !(t.ang[lo - 1] < T)) lo--;
-  while (lo < t.lmax && t.ang[lo] < T) lo++;
-  h.ang = min(lo, t.lmax - 1);
-  if (lo >= t.lmax) {
-    ll = t.lmax - 2; llp = t.lmax - 1;
-    dt = (T - t.ang[ll]) / (t.ang[llp] - t.ang[ll]);
-  } else if (T == t.ang[lo]) {
-    ll = lo; llp = (lo + 1 < t.lmax) ? lo + 1 : lo;
-    dt = 0.f;
-  } else {
-    ll = lo - 1; llp = lo;
-    if (lo == 0) { ll = 0; llp = 1; }
-    dt = (T - t.ang[ll]) / (t.ang[llp] - t.ang[ll]);
+// lower bound (first j with x <= ax[j]) starting from the previous bracket: the hint is right or off by one in all but
+// a handful of look-ups per line of sight, so one predicated correction + one check replace the search; the rare miss
+// (the first look-up, the jump from the end of one TOP segment to the next outer point) takes the binary search.
+// On return a_lo = ax[lo-1] (or ax[0]) and a_hi = ax[lo] (or ax[n-1]) are the values the interpolation needs.
+__device__ __forceinline__ int lower_bound_hint(const float *ax, int n, float x, int hint) {
+  int lo = hint;
+  const bool up = ax[lo] < x;
+  const bool down = (lo > 0) && !(ax[lo - 1] < x);
+  lo += (up ? 1 : 0) - (down ? 1 : 0);
+  const bool ok = (lo == 0 || ax[lo - 1] < x) && (lo >= n || !(ax[lo] < x));
+  if (!ok) {
+    int l = 0, hh = n;
+    while (l < hh) {
+      const int mid = (l + hh) >> 1;
+      if (ax[mid] < x) l = mid + 1; else hh = mid;
+    }
+    lo = l;
   }
+  return lo;
+}
+// first j with T <= ang[j]  (the Fortran's arithmetic-IF scan, :517-528) and the weight of the upper neighbour;
+// the case analysis of the scan (below the axis, on a node, beyond the axis) as selects
+__device__ __forceinline__ void bracket_ang(const Tables &t, float T, int &ll, int &llp, float &dt, Hint &h) {
+  const int lo = lower_bound_hint(t.ang, t.lmax, T, h.ang);
+  h.ang = min(lo, t.lmax - 1);
+  const bool on_node = (lo < t.lmax) && (T == t.ang[h.ang]);
+  ll = min(max(lo - 1, 0), t.lmax - 2);
+  llp = ll + 1;
+  const float a0 = t.ang[ll];
+  dt = (T - a0) / (t.ang[llp] - a0);
+  if (on_node) { ll = lo; llp = min(lo + 1, t.lmax - 1); dt = 0.f; }
 }
 __device__ __forceinline__ void bracket_alt(const Tables &t, float Z, int &kk, int &kkp, float &du, Hint &h) {
-  int lo = h.alt;
-  while (lo > 0 && !(t.alt[lo - 1] < Z)) lo--;
-  while (lo < t.kmax && t.alt[lo] < Z) lo++;
+  const int lo = lower_bound_hint(t.alt, t.kmax, Z, h.alt);
   h.alt = min(lo, t.kmax - 1);
-  if (lo >= t.kmax) { kk = kkp = t.kmax - 1; du = 0.f; }
-  else if (Z == t.alt[lo]) { kk = lo; kkp = (lo + 1 < t.kmax) ? lo + 1 : lo; du = 0.f; }
-  else {
-    kk = lo - 1; kkp = lo;
-    du = (Z - t.alt[kk]) / (t.alt[kkp] - t.alt[kk]);
-  }
+  const bool beyond = lo >= t.kmax;
+  const bool on_node = !beyond && (Z == t.alt[h.alt]);
+  kk = min(max(lo - 1, 0), t.kmax - 2);
+  kkp = kk + 1;
+  const float a0 = t.alt[kk];
+  du = (Z - a0) / (t.alt[kkp] - a0);
+  if (on_node) { kk = lo; kkp = min(lo + 1, t.kmax - 1); du = 0.f; }
+  if (beyond) { kk = kkp = t.kmax - 1; du = 0.f; }
 }
 
 __device__ __forceinline__ float den(const Tables &t, float Z, float T, int &ko, Hint &h) {   // DEN :492-547
