@@ -135,10 +135,12 @@ void atmosphere_model::voxel_tables(const std::vector<Real> &rb, const std::vect
                                     const std::vector<Real> &pts_s, std::vector<Real> (&out)[6]) const {
   const int n_r = (int) rb.size() - 1, n_s = (int) sb.size() - 1;
   for (auto &v : out) v.assign((size_t) n_r * n_s, 0.0);
+  const bool per_sza = sza_dependent();
   for (int i = 0; i < n_r; i++)
     for (int j = 0; j < n_s; j++) {
       Real vals[6];
-      voxel_values(rb[i], rb[i + 1], sb[j], sb[j + 1], pts_r[i], pts_s[j], vals);
+      if (per_sza || j == 0) voxel_values(rb[i], rb[i + 1], sb[j], sb[j + 1], pts_r[i], pts_s[j], vals);
+      else for (int q = 0; q < 6; q++) vals[q] = out[q][(size_t) i * n_s];
       for (int q = 0; q < 6; q++) out[q][(size_t) i * n_s + j] = vals[q];
     }
 }

@@ -78,6 +78,7 @@ public:
   // for the voxel [r0, r1] x [t0, t1] with point (pt_r, pt_t).  Default: the 1-D profile (no SZA dependence);
   // T is the constant temperature when temp_dependent_sH is off (chamb_diff_1d.cpp Temp_voxel_avg).
   virtual void voxel_values(Real r0, Real r1, Real t0, Real t1, Real pt_r, Real pt_t, Real (&out)[6]) const;
+  virtual bool sza_dependent() const { return false; }   // false: voxel_tables evaluates one SZA column and copies it
 
   // [6][n_vox] tables, voxel id = ir*(n_sb-1)+isza.  sb / pts_s = SZA boundaries / points of the grid
   // (n_sb = 2, sb = {0, pi} on the plane-parallel grid).
@@ -134,6 +135,7 @@ public:
   void set_asymmetry(Real a);
   Real theta_average_factor(Real t0, Real t1) const;
   void voxel_values(Real r0, Real r1, Real t0, Real t1, Real pt_r, Real pt_t, Real (&out)[6]) const override;
+  bool sza_dependent() const override { return true; }
 };
 
 // exobase temperature linear in SZA from T0 (noon) to T1 (midnight), exobase density A T^-Tpower with the sphere
@@ -154,6 +156,7 @@ public:
   Real r_from_n_species(Real n) const override { return atm_sza[0]->r_from_n_species(n); }
   Real at(int which, Real r, Real t) const;      // which: 0 species, 1 temperature, 2 absorber
   void voxel_values(Real r0, Real r1, Real t0, Real t1, Real pt_r, Real pt_t, Real (&out)[6]) const override;
+  bool sza_dependent() const override { return true; }
 
 private:
   std::vector<std::unique_ptr<chamb_diff_1d>> atm_sza;
