@@ -35,6 +35,12 @@ SIGNATURES = {
     "b200rt_make_grid_pp": (C.c_int, [C.c_int] * 3 + [_dp] * 4),
     "b200rt_set_singlet": (C.c_int, [_vp, C.c_int, C.c_int] + [C.c_double] * 4 + [_dp] * 8),
     "b200rt_set_g_factor": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "b200rt_influence_ranges": (C.c_int, [_vp, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS"),
+                                          np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]),
+    "b200rt_ipc_export_influence": (C.c_int, [_vp, C.c_int, C.c_char_p]),
+    "b200rt_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "b200rt_ipc_close": (C.c_int, [_vp, _vp]),
+    "b200rt_set_row_sink": (C.c_int, [_vp, C.c_int, _vp]),
     "b200rt_multiplet_desc_init": (C.c_int, [C.c_int, C.c_int, _vp]),
     "b200rt_set_multiplet": (C.c_int, [_vp, _vp] + [_dp] * 6),
     "b200rt_generate_S": (C.c_int, [_vp]),
@@ -258,6 +264,29 @@ class Context:
         p = [_vp() for _ in range(4)]
         self._ck(self.lib.b200rt_influence_dev(self.h, e, *[C.byref(x) for x in p]))
         return [x.value for x in p]
+
+    def influence_ranges(self, ranges):
+        """ranges: [(v_begin, v_end), ...] ascending and disjoint (multi.partition_interleaved)"""
+        a = np.ascontiguousarray([r[0] for r in ranges], dtype=np.int32)
+        b = np.ascontiguousarray([r[1] for r in ranges], dtype=np.int32)
+        self._ck(self.lib.b200rt_influence_ranges(self.h, len(a), a, b))
+
+    # ---- multi-GPU row exchange over peer memory (include/b200rt.h)
+    def ipc_export_influence(self, e=0) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.b200rt_ipc_export_influence(self.h, e, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._ck(self.lib.b200rt_ipc_open(self.h, handle, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._ck(self.lib.b200rt_ipc_close(self.h, ptr))
+
+    def set_row_sink(self, e, ptr):
+        self._ck(self.lib.b200rt_set_row_sink(self.h, e, ptr))
 
     # ---- observations
     def los_from_MSO(self, locs, dirs):

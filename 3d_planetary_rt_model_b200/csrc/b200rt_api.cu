@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <new>
+#include <utility>
 #include <vector>
 #include "common.hpp"
 
@@ -120,42 +121,87 @@ int upload_real<float>(b200rt_ctx *c, const double *src, float *dst, size_t n, D
 }
 
 // ------------------------------------------------------------------ influence
+// ranges: the source-voxel ranges [begin, end) this call builds rows for (one range for a single GPU or a contiguous
+// shard; several for the interleaved shards that balance the cost of low- and high-altitude rows across ranks)
 template <class Real>
-int influence_impl(b200rt_ctx *c, int v_begin, int v_end) {
+int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges) {
   GridView<Real> &g = gv<Real>(c);
   const int n_vox = g.n_vox;
   PhaseTimer::reset(c);
   B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
   B200RT_CUDA(c, cudaMemsetAsync(c->step_counter.p, 0, sizeof(unsigned long long), c->stream));
+  int n_rows = 0;
+  for (auto &r : ranges) n_rows += r.second - r.first;
   for (int e = 0; e < c->n_em; e++) {
     Emission &E = c->em[e];
     if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
-    if (v_end > v_begin)
-      B200RT_CUDA(c, cudaMemsetAsync(E.K.as<double>() + (size_t) v_begin * n_vox, 0,
-                                     (size_t) (v_end - v_begin) * n_vox * sizeof(double), c->stream));
+    for (auto &r : ranges)
+      if (r.second > r.first)
+        B200RT_CUDA(c, cudaMemsetAsync(E.K.as<double>() + (size_t) r.first * n_vox, 0,
+                                       (size_t) (r.second - r.first) * n_vox * sizeof(double), c->stream));
   }
+  // Local slots 0 .. n_rows-1 run over the ranges in order.  One range: slot i is voxel first + i.  Several ranges
+  // (interleaved multi-GPU shards): the slot -> voxel map goes to the device, so that a batch -- one traversal launch
+  // + one march launch -- spans shard boundaries and the launch count does not grow with the number of shards.
+  const bool mapped = ranges.size() > 1;
+  std::vector<int> vox_of;
+  if (mapped) {
+    vox_of.reserve(n_rows);
+    for (auto &r : ranges) for (int v = r.first; v < r.second; v++) vox_of.push_back(v);
+    B200RT_CUDA(c, c->vox_map.ensure((size_t) n_rows * sizeof(int)));
+    B200RT_CUDA(c, cudaMemcpyAsync(c->vox_map.p, vox_of.data(), (size_t) n_rows * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
+  const int first_voxel = ranges.empty() ? 0 : ranges[0].first;
   const long long cap_rays = batch_capacity(c, sizeof(Real));
-  const int vox_per_batch = (int) std::max<long long>(1, std::min<long long>(cap_rays / g.n_rays, v_end - v_begin));
+  int vox_per_batch = (int) std::max<long long>(1, std::min<long long>(cap_rays / g.n_rays, std::max(n_rows, 1)));
+  bool pushing = false;
+  for (int e = 0; e < c->n_em; e++) pushing = pushing || c->row_sink[e] != nullptr;
+  if (pushing && n_rows > 0) {     // several batches, so that the DMA of one overlaps the march of the next
+    if (const char *env = getenv("B200RT_ROW_PUSH_BATCHES")) c->row_push_batches = std::max(1, atoi(env));
+    vox_per_batch = std::max(1, std::min(vox_per_batch, (n_rows + c->row_push_batches - 1) / c->row_push_batches));
+    if (!c->copy_stream) B200RT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->ev_rows) B200RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_rows, cudaEventDisableTiming));
+  }
   ListView<Real> lv;
   const long long need = std::max<long long>((long long) vox_per_batch * g.n_rays, n_vox);
   if (int rc = ensure_lists<Real>(c, need, &lv)) return rc;
   int *overflow = c->work_counter.as<int>() + 1;
 
-  for (int vb = v_begin; vb < v_end; vb += vox_per_batch) {
-    const int ve = std::min(v_end, vb + vox_per_batch);
+  for (int lb = 0; lb < n_rows; lb += vox_per_batch) {
+    const int le = std::min(n_rows, lb + vox_per_batch);
+    GridView<Real> gb = g;
+    int vb = first_voxel + lb, ve = first_voxel + le;      // unmapped: the voxel range itself
+    if (mapped) { gb.vox_map = c->vox_map.as<int>() + lb; vb = 0; ve = le - lb; }
     {
       PhaseTimer t(c, PH_TRAVERSE);
-      B200RT_CUDA(c, launch_traverse_voxel_rays<Real>(g, vb, ve, lv, overflow, c->stream));
+      B200RT_CUDA(c, launch_traverse_voxel_rays<Real>(gb, vb, ve, lv, overflow, c->stream));
       t.stop(1);
       DBG(c, "traverse_voxel_rays");
     }
     for (int e = 0; e < c->n_em; e++) {
       PhaseTimer t(c, PH_INFLUENCE);
-      B200RT_CUDA(c, launch_influence<Real>(g, em_view<Real>(c, e), vb, ve, lv, c->em[e].K.as<double>(),
+      B200RT_CUDA(c, launch_influence<Real>(gb, em_view<Real>(c, e), vb, ve, lv, c->em[e].K.as<double>(),
                                             c->work_counter.as<int>(),
                                             e == 0 ? c->step_counter.as<unsigned long long>() : nullptr, c->stream));
       t.stop(1);
       DBG(c, "influence march");
+    }
+    if (pushing) {   // the rows of this batch are final: hand them to the solving GPU (peer memory, copy engine, NVLink)
+      B200RT_CUDA(c, cudaEventRecord(c->ev_rows, c->stream));
+      B200RT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rows, 0));
+      int run_lo = lb;                                      // contiguous runs of voxels inside the batch
+      while (run_lo < le) {
+        int run_hi = run_lo + 1;
+        const int v_lo = mapped ? vox_of[run_lo] : first_voxel + run_lo;
+        while (run_hi < le && (mapped ? vox_of[run_hi] : first_voxel + run_hi) == v_lo + (run_hi - run_lo)) run_hi++;
+        for (int e = 0; e < c->n_em; e++)
+          if (c->row_sink[e])
+            B200RT_CUDA(c, cudaMemcpyAsync(static_cast<double *>(c->row_sink[e]) + (size_t) v_lo * n_vox,
+                                           c->em[e].K.as<double>() + (size_t) v_lo * n_vox,
+                                           (size_t) (run_hi - run_lo) * n_vox * sizeof(double), cudaMemcpyDeviceToDevice,
+                                           c->copy_stream));
+        run_lo = run_hi;
+      }
     }
   }
   // single scattering: one sun-ward ray per voxel (every rank computes all of them: n_vox rays)
@@ -186,6 +232,7 @@ int influence_impl(b200rt_ctx *c, int v_begin, int v_end) {
   unsigned long long steps = 0;
   B200RT_CUDA(c, cudaMemcpyAsync(&steps, c->step_counter.p, sizeof(steps), cudaMemcpyDeviceToHost, c->stream));
   if (int rc = check_overflow(c)) return rc;   // synchronises
+  if (pushing) B200RT_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the rows have landed on the solving GPU
   PhaseTimer::collect(c);
   c->last_steps = (long long) steps;
   for (int e = 0; e < c->n_em; e++) { c->em[e].have_K = true; c->em[e].have_S = false; }
@@ -684,6 +731,8 @@ int b200rt_destroy(b200rt_ctx *c) {
   if (c->grid_view) ::operator delete(c->grid_view);
   for (cudaEvent_t ev : c->lu_events) cudaEventDestroy(ev);
   if (c->lu_graph) cudaGraphExecDestroy(c->lu_graph);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_rows) cudaEventDestroy(c->ev_rows);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -820,7 +869,24 @@ int b200rt_influence(b200rt_ctx *c, int v_begin, int v_end) {
   if (v_begin < 0 || v_end > c->hg.n_vox || v_begin > v_end) return fail(c, B200RT_ERR_ARG, "bad voxel range");
   cudaSetDevice(c->device);
   if (c->mult.defined) return is64(c) ? mult_influence_impl<double>(c, v_begin, v_end) : mult_influence_impl<float>(c, v_begin, v_end);
-  return is64(c) ? influence_impl<double>(c, v_begin, v_end) : influence_impl<float>(c, v_begin, v_end);
+  const std::vector<std::pair<int, int>> one = {{v_begin, v_end}};
+  return is64(c) ? influence_impl<double>(c, one) : influence_impl<float>(c, one);
+}
+
+int b200rt_influence_ranges(b200rt_ctx *c, int n_ranges, const int *v_begin, const int *v_end) {
+  if (!c || n_ranges < 0 || (n_ranges > 0 && (!v_begin || !v_end))) return B200RT_ERR_ARG;
+  if (!c->have_grid || c->n_em < 1) return fail(c, B200RT_ERR_STATE, "grid / singlet emissions not set");
+  if (c->mult.defined) return fail(c, B200RT_ERR_STATE, "b200rt_influence_ranges: singlet emissions only");
+  std::vector<std::pair<int, int>> r;
+  int last_end = 0;
+  for (int i = 0; i < n_ranges; i++) {
+    if (v_begin[i] < last_end || v_end[i] > c->hg.n_vox || v_begin[i] > v_end[i])
+      return fail(c, B200RT_ERR_ARG, "voxel ranges must be ascending, disjoint and inside the grid");
+    last_end = v_end[i];
+    r.emplace_back(v_begin[i], v_end[i]);
+  }
+  cudaSetDevice(c->device);
+  return is64(c) ? influence_impl<double>(c, r) : influence_impl<float>(c, r);
 }
 
 int b200rt_solve(b200rt_ctx *c) {
@@ -961,6 +1027,39 @@ int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, 
   if (tsp) *tsp = E.tau_sp.p;
   if (tab) *tab = E.tau_abs.p;
   E.have_K = true;   // the caller may fill rows from peers
+  return B200RT_OK;
+}
+
+// ---- peer-memory row exchange (one process per GPU): the solving rank exports its K, the others open it and
+// name it as the sink of their row batches
+int b200rt_ipc_export_influence(b200rt_ctx *c, int e, void *handle64) {
+  if (!c || !handle64 || e < 0 || e >= c->n_em || c->mult.defined) return B200RT_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaSetDevice(c->device);
+  cudaIpcMemHandle_t h;
+  B200RT_CUDA(c, cudaIpcGetMemHandle(&h, c->em[e].K.p));
+  std::memcpy(handle64, &h, sizeof h);
+  c->em[e].have_K = true;   // peers fill rows
+  return B200RT_OK;
+}
+int b200rt_ipc_open(b200rt_ctx *c, const void *handle64, void **peer_ptr) {
+  if (!c || !handle64 || !peer_ptr) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, sizeof h);
+  B200RT_CUDA(c, cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200RT_OK;
+}
+int b200rt_ipc_close(b200rt_ctx *c, void *peer_ptr) {
+  if (!c || !peer_ptr) return B200RT_ERR_ARG;
+  cudaSetDevice(c->device);
+  for (auto &sk : c->row_sink) if (sk == peer_ptr) sk = nullptr;
+  B200RT_CUDA(c, cudaIpcCloseMemHandle(peer_ptr));
+  return B200RT_OK;
+}
+int b200rt_set_row_sink(b200rt_ctx *c, int e, void *peer_K_dev) {
+  if (!c || e < 0 || e >= 2) return B200RT_ERR_ARG;
+  c->row_sink[e] = peer_K_dev;
   return B200RT_OK;
 }
 

@@ -38,6 +38,8 @@ template <class Real>
 struct GridView {
   int n_rb, n_sb, n_vox, n_rays, cap;
   int pp;                  // 1 = plane_parallel_grid: boundaries are the planes z = rb[i], n_sb = 2 (no cones)
+  const int *vox_map;      // voxel-origin rays: source voxel of local slot i is vox_map[i] (nullptr: v_begin + i);
+                           // lets one launch cover the interleaved voxel shards of a multi-GPU build
   const Real *rb;          // [n_rb]   radial boundaries
   const Real *sph_R2;      // [n_rb]   (rb/1e9)^2            sphere::set_radius
   const Real *sb;          // [n_sb]   sza boundaries
@@ -196,6 +198,14 @@ struct b200rt_ctx {
   cudaGraphExec_t lu_graph = nullptr;        // the factorisation + back substitution of one (np, workspace), replayed
   int lu_graph_np = 0, lu_graph_launches = 0;
   const void *lu_graph_A = nullptr, *lu_graph_dinv = nullptr;
+
+  // row sink (multi-GPU): peer-memory address of the solving GPU's K; finished row batches are DMA'd there over
+  // NVLink by the copy engines while the next batch is marched
+  b200rt::DevBuf vox_map;                    // source voxels of an interleaved shard, ascending
+  void *row_sink[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_rows = nullptr;
+  int row_push_batches = 4;                  // a rank's row range is marched in at least this many batches when a sink is set
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -125,6 +125,7 @@ int upload_grid(b200rt_ctx *c) {
   GridView<Real> *g = new GridView<Real>;
   char *base = static_cast<char *>(c->grid_tables.p);
   g->n_rb = n_rb; g->n_sb = n_sb; g->n_vox = n_vox; g->n_rays = n_rays; g->cap = h.cap; g->pp = h.pp ? 1 : 0;
+  g->vox_map = nullptr;
   g->rb = (const Real *) (base + o_rb);          g->sph_R2 = (const Real *) (base + o_R2);
   g->sb = (const Real *) (base + o_sb);          g->cone_cos = (const Real *) (base + o_cc);
   g->cone_cos2 = (const Real *) (base + o_cc2);  g->pts_r = (const Real *) (base + o_pr);

@@ -130,7 +130,11 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
     int len = 0, v0 = 0, ir = 0;
     if (valid) {
       len = lists.len[ray];
-      if (MODE == 0) { v0 = v_begin + (int) (ray / g.n_rays); ir = (int) (ray % g.n_rays); }
+      if (MODE == 0) {
+        v0 = v_begin + (int) (ray / g.n_rays);
+        if (g.vox_map) v0 = g.vox_map[v0];
+        ir = (int) (ray % g.n_rays);
+      }
       else { v0 = (int) ray; if (shadow[v0]) len = -1; }
     }
     const Real Tr0 = valid ? em.T_ratio[v0] : Real(1);

@@ -204,7 +204,8 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
     Real r, z, t, cost, lz;
     int i_voxel;
     if (VOXEL_RAYS) {
-      const int iv = v_begin + (int) (ray / g.n_rays);
+      int iv = v_begin + (int) (ray / g.n_rays);
+      if (g.vox_map) iv = g.vox_map[iv];
       const int ir = (int) (ray % g.n_rays);
       const int irad = iv / (n_sb - 1), isza = iv % (n_sb - 1);
       r = g.pts_r[irad];

@@ -21,8 +21,9 @@ roofline  = the dominant kernel against the roofline that binds it.  SURVEY.md 8
 cpu_baseline / --impl reference = the reference's own CPU (OpenMP) source built in place
             (oracle/_ref), on a bounded sample of the same workload.
 
-N > 1 (torchrun): influence rows are split by source voxel and gathered onto rank 0 with one grouped
-NCCL send/recv, rank 0 solves and broadcasts S, lines of sight are split per GPU (no communication).
+N > 1 (torchrun): influence rows are split by source voxel; each rank DMAs its finished row batches into rank 0's
+resident K over NVLink (peer memory through CUDA IPC, copy engines) while it marches the next batch; rank 0 solves and
+broadcasts S (NCCL, 47 kB), lines of sight are split per GPU (no communication).
 """
 import argparse
 import importlib
@@ -179,7 +180,9 @@ def run_ours(args):
     b_, T_, s_, g_ = (float(x) for x in scn.em_scalars[0])
     ctx.set_singlet(0, 1, b_, T_, s_, g_, tabs)
 
-    v0, v1 = partition(n_vox, world, rank)
+    multi = importlib.import_module(PKG + ".multi")
+    v_ranges = multi.partition_interleaved(n_vox, world, rank)   # cost-balanced shards of source voxels
+    n_rows_mine = sum(b - a for a, b in v_ranges)
     l0, l1 = partition(n_los, world, rank)
     los_all = ctx.los_from_MSO(locs, dirs)                      # host preparation (atmo_vector::ptxyz)
     los_mine = [np.ascontiguousarray(a[l0:l1]) for a in los_all]
@@ -198,28 +201,37 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    multi = importlib.import_module(PKG + ".multi")
+    peer_ptrs = multi.connect_row_sink(dist, ctx, rank, 0, 1) if world > 1 else []
 
     def gather_rows():
-        """the one exchange on the path: every rank's row block -> rank 0's resident K, one grouped NCCL
-        send/recv over NVLink (only the solving GPU needs the matrix)"""
-        multi.gather_rows(dist, K_t, n_vox, rank, world, 0)
-        torch.cuda.synchronize()
+        """the one exchange on the path: every rank's row block -> rank 0's resident K.  The rows travel INSIDE
+        ctx.influence: each finished batch is DMA'd into rank 0's K over NVLink (peer memory opened through CUDA IPC,
+        copy engines) while the next batch is marched, and the call returns when this rank's rows have landed; what is
+        left here is the host barrier that tells rank 0 every rank is done."""
+        dist.barrier()
 
     def one_step():
         """-> dict of device/wall times (s) for this rank"""
         t = {}
         w0 = time.perf_counter()
-        ctx.influence(v0, v1)
+        ctx.influence_ranges(v_ranges)
         t["traverse"] = ctx.kernel_ms(binding.PH_TRAVERSE)[0] * 1e-3
         t["march"] = ctx.kernel_ms(binding.PH_INFLUENCE)[0] * 1e-3
         launches = ctx.kernel_ms(binding.PH_TRAVERSE)[1] + ctx.kernel_ms(binding.PH_INFLUENCE)[1]
         t["march_launches"] = ctx.kernel_ms(binding.PH_INFLUENCE)[1] - 1      # minus the single-scattering march
         steps = ctx.last_step_count()
         w1 = time.perf_counter()
-        if world > 1:                                           # gather the row blocks onto the solving GPU (NVLink)
+        if world > 1:                                           # every rank's rows are in rank 0's K after this
             gather_rows()
         w2 = time.perf_counter()
+        # row_exchange = what the exchange adds to the critical path: the un-hidden tail of the row DMA inside
+        # ctx.influence (its wall time minus its kernels) + the barrier
+        t["exchange"] = (w2 - w1) + max(0.0, (w1 - w0) - t["traverse"] - t["march"]) if world > 1 else 0.0
+        t["influence_tail"] = (w1 - w0) - t["traverse"] - t["march"]      # host launch/sync overhead (+ un-hidden DMA tail)
+        t["barrier"] = w2 - w1
+        if os.environ.get("B200RT_BENCH_DEBUG"):
+            print(f"rank {rank}: influence wall {(w1 - w0) * 1e3:.3f} ms, kernels {(t['traverse'] + t['march']) * 1e3:.3f} ms, "
+                  f"barrier {(w2 - w1) * 1e3:.3f} ms", file=sys.stderr, flush=True)
         if rank == 0:
             ctx.solve()
             t["solve"] = ctx.kernel_ms(binding.PH_SOLVE)[0] * 1e-3
@@ -248,7 +260,7 @@ def run_ours(args):
         """the reference-facing calls with host buffers: uploads and downloads inside the timed region"""
         w0 = time.perf_counter()
         ctx.set_singlet(0, 1, b_, T_, s_, g_, tabs)             # H2D: 8 tables
-        ctx.influence(v0, v1)
+        ctx.influence_ranges(v_ranges)
         sol = ctx.solution(0, want_S=False)                     # D2H: S0 + optical depths
         w1 = time.perf_counter()
         if world > 1:
@@ -302,7 +314,7 @@ def run_ours(args):
     t_bright = reduce_max(sum(r["los_traverse"] + r["brightness"] for r in recs))
     t_solve = reduce_max(sum(r.get("solve", 0.0) for r in recs))
     t_total = reduce_max(sum(r["w_total"] for r in recs))
-    t_exch = reduce_max(sum(r["w_exchange"] for r in recs))
+    t_exch = reduce_max(sum(r["exchange"] for r in recs))
     steps_total = reduce_sum(float(recs[-1]["steps"]))
     launches = int(reduce_sum(float(sum(r["launches"] for r in recs))))
     value = steps_total * K / t_infl
@@ -324,6 +336,10 @@ def run_ours(args):
     h2d = 8 * n_vox * 8 + 9 * (l1 - l0) * 8
     d2h = 4 * n_vox * 8 + 4 * (l1 - l0) * 8
 
+    if world > 1:                     # peers let go of rank 0's K before rank 0 frees it
+        for p_ in peer_ptrs:
+            ctx.ipc_close(p_)
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -355,7 +371,7 @@ def run_ours(args):
         n_l = max(1, recs[-1]["march_launches"])
         dur = march_s / n_l
         flop = steps_rank * FLOP_EQ_PER_EMISSION_STEP / n_l
-        alg = (v1 - v0) * n_vox * 8 / n_l                        # K rows written once
+        alg = n_rows_mine * n_vox * 8 / n_l                        # K rows written once
         roof = {"kernel": "march_kernel<double,0>", "bound": "fp64", "achieved": flop / dur / 1e12, "peak": dfma,
                 "unit": "TFLOP/s", "frac": flop / dur / 1e12 / dfma, "peak_kind": "measured in this run (DFMA)",
                 "units_per_launch": {"ray_voxel_steps": steps_rank / n_l, "flop_eq_per_step": FLOP_EQ_PER_EMISSION_STEP},
@@ -381,9 +397,11 @@ def run_ours(args):
                                    f"{n_los} IUVS-like LOS brightness, n_subsamples=10",
                        "grid": GRID, "n_emissions": 1, "n_los": n_los, "ray_voxel_steps": int(steps_total),
                        "l2": "256 MB buffer written between timed iterations (L2 flush); K is 273 MB > L2",
-                       "partition": "rows by source voxel, LOS by index" if world > 1 else "single GPU"},
+                       "partition": "rows by source voxel (pushed to rank 0 over peer memory while marching), LOS by index" if world > 1 else "single GPU"},
             "phases_ms": {"influence_traverse+march": t_infl / K * 1e3, "row_exchange": t_exch / K * 1e3,
                           "solve": t_solve / K * 1e3, "brightness_traverse+march": t_bright / K * 1e3},
+            "exchange_detail_ms": {"influence_call_minus_kernels": sum(r["influence_tail"] for r in recs) / K * 1e3,
+                                   "barrier": sum(r["barrier"] for r in recs) / K * 1e3, "note": "rank 0"},
             "solve_gflops": fp64["solve_tflops"] * 1e3 if fp64["solve_tflops"] else None,
             "roofline": roof, "fp64": fp64,
             "e2e": {"value": steps_total * Ke / e_infl, "unit": "ray-voxel steps/s", "los_per_s": n_los * Ke / e_bright,

@@ -143,6 +143,9 @@ int b200rt_set_multiplet(b200rt_ctx *ctx, const b200rt_multiplet_desc *desc,
  * separately so that rows can be sharded over GPUs (rows [v_begin, v_end) only). */
 int b200rt_generate_S(b200rt_ctx *ctx);
 int b200rt_influence(b200rt_ctx *ctx, int v_begin, int v_end);
+/* the same for several ascending, disjoint source-voxel ranges in one call (singlet emissions): the interleaved shards
+ * that balance the cost of low-altitude (long rays through many voxels) and high-altitude rows across GPUs */
+int b200rt_influence_ranges(b200rt_ctx *ctx, int n_ranges, const int *v_begin, const int *v_end);
 int b200rt_solve(b200rt_ctx *ctx);                      /* RT_grid::solve_gpu, emission_voxels::solve_gpu */
 /* ray-voxel steps executed by the last b200rt_influence call (one step = one
  * RT_grid::influence_update, RT_grid.hpp:90-105, covering all emissions) */
@@ -168,6 +171,20 @@ int b200rt_last_residual(b200rt_ctx *ctx, int i_emission, double *residual);
 int b200rt_influence_dev(b200rt_ctx *ctx, int i_emission, void **K_dev, void **S0_dev,
                          void **tau_species_ss_dev, void **tau_absorber_ss_dev);
 int b200rt_sourcefn_dev(b200rt_ctx *ctx, int i_emission, void **S_dev);
+
+/* ---- multi-GPU row exchange over peer memory ------------------------------------------
+ * The reference has no multi-GPU path (single cudaSetDevice(0), RT_gpu.cu:143,257).  Influence rows shard by source
+ * voxel (RT_grid.hpp:166-167: rows are independent); the one exchange of the pipeline puts every rank's rows into the
+ * solving GPU's resident K.  One process per GPU: the solving rank exports a CUDA IPC handle of its K
+ * (b200rt_ipc_export_influence, 64 bytes, passed to the other ranks by any host channel), the others open it
+ * (b200rt_ipc_open -> a device pointer valid in their process) and name it as their row sink; from then on
+ * b200rt_influence(v_begin, v_end) marches its range in >= 4 batches and DMAs each finished batch into the sink with
+ * the copy engines over NVLink WHILE the next batch is marched (no SMs, no collective kernel), and returns when the
+ * rows have landed.  A host barrier across ranks then releases the solve.  Singlet emissions only. */
+int b200rt_ipc_export_influence(b200rt_ctx *ctx, int i_emission, void *handle64);
+int b200rt_ipc_open(b200rt_ctx *ctx, const void *handle64, void **peer_ptr);
+int b200rt_ipc_close(b200rt_ctx *ctx, void *peer_ptr);
+int b200rt_set_row_sink(b200rt_ctx *ctx, int i_emission, void *peer_K_dev);   /* NULL clears */
 
 /* ---- observations ---------------------------------------------------------------
  * host helper: observation::add_MSO_observation (observation.hpp:46-65) + atmo_point::xyz +

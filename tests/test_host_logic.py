@@ -63,3 +63,17 @@ def test_bad_arguments(binding):
     lib = binding.load()
     z = np.zeros(4)
     assert lib.b200rt_make_grid_sph(0, 1, 8, 5, 6, z, 1, 1, z, z, z, z, z, z) == 2      # B200RT_ERR_ARG
+
+
+def test_interleaved_partition_covers_every_voxel_once():
+    import importlib
+    multi = importlib.import_module("3d_planetary_rt_model_b200.multi")
+    for n, world, cpr in ((5841, 8, 8), (741, 3, 4), (10, 4, 8), (5841, 1, 8), (7, 2, 1)):
+        seen = np.zeros(n, dtype=int)
+        for r in range(world):
+            rg = multi.partition_interleaved(n, world, r, cpr)
+            assert all(a < b for a, b in rg) and all(rg[i][1] <= rg[i + 1][0] for i in range(len(rg) - 1))
+            for a, b in rg:
+                seen[a:b] += 1
+        assert (seen == 1).all()
+    assert multi.partition_interleaved(100, 1, 0) == [(0, 100)]
