@@ -96,9 +96,10 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not built: run __graft_entry__.build() (there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("B200RT_LIB", LIB_PATH)     # development aid: an experimental build of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not built: run __graft_entry__.build() (there is no CPU fallback)")
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
