@@ -122,17 +122,8 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
                   ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total,
                   int *queue, unsigned long long *substep_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n_rb = g.n_rb, n_sb = g.n_sb, n_sb1 = n_sb - 1;
-  Real *s_rb = reinterpret_cast<Real *>(smem_raw);   // [n_rb]
-  Real *s_sb = s_rb + n_rb;                          // [n_sb]
-  Real *s_pr = s_sb + n_sb;                          // [n_rb-1]
-  Real *s_lpr = s_pr + n_rb;                         // [n_rb-1]
-  Real *s_ps = s_lpr + n_rb;                         // [n_sb-1]
-  for (int i = threadIdx.x; i < n_rb; i += blockDim.x) s_rb[i] = g.rb[i];
-  for (int i = threadIdx.x; i < n_sb; i += blockDim.x) s_sb[i] = g.sb[i];
-  for (int i = threadIdx.x; i < n_rb - 1; i += blockDim.x) { s_pr[i] = g.pts_r[i]; s_lpr[i] = g.log_pts_r[i]; }
-  for (int i = threadIdx.x; i < n_sb1; i += blockDim.x) s_ps[i] = g.pts_s[i];
-  __syncthreads();
+  GeomTables<Real> T;
+  T.load(smem_raw, g);            // axes of the grid + the reciprocal tables of the double path; ends with a barrier
 
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPR - 1);
@@ -235,7 +226,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
         int idx[4];
         Real w[4];
         const Real dist = d_start + is * d_step;
-        substep_interp<Real>(s_rb, s_sb, s_pr, s_lpr, s_ps, n_rb, n_sb1, cur, px, py, pz, lx, ly, lz, dist, idx, w);
+        substep_interp<Real>(T, cur, px, py, pz, lx, ly, lz, dist, idx, w);
 #pragma unroll
         for (int e = 0; e < NEM; e++) interp_record<Real>(em[e].rec_pt, idx, w, my_in[e]);
       }
@@ -326,7 +317,7 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
   const int threads = 128;
-  const size_t smem = (size_t) (4 * g.n_rb + 2 * g.n_sb) * sizeof(Real);
+  const size_t smem = GeomTables<Real>::doubles(g.n_rb, g.n_sb) * sizeof(Real);
   const long long groups = (count + 0);
   long long blocks = (groups * LPR + threads - 1) / threads;
   const long long persistent = (long long) NUM_SMS * 4;   // __launch_bounds__(128, 4)

@@ -289,16 +289,8 @@ mult_brightness_kernel(GridView<Real> g, MultView<Real> mv, MultParams<Real> P_,
   constexpr int NQ = 2 + NLOW + NUP;     // record entries in use
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n_rb = g.n_rb, n_sb = g.n_sb, n_sb1 = n_sb - 1;
-  Real *s_rb = reinterpret_cast<Real *>(smem_raw);
-  Real *s_sb = s_rb + n_rb;
-  Real *s_pr = s_sb + n_sb;
-  Real *s_lpr = s_pr + n_rb;
-  Real *s_ps = s_lpr + n_rb;
-  for (int i = threadIdx.x; i < n_rb; i += blockDim.x) s_rb[i] = g.rb[i];
-  for (int i = threadIdx.x; i < n_sb; i += blockDim.x) s_sb[i] = g.sb[i];
-  for (int i = threadIdx.x; i < n_rb - 1; i += blockDim.x) { s_pr[i] = g.pts_r[i]; s_lpr[i] = g.log_pts_r[i]; }
-  for (int i = threadIdx.x; i < n_sb1; i += blockDim.x) s_ps[i] = g.pts_s[i];
-  __syncthreads();
+  GeomTables<Real> T;
+  T.load(smem_raw, g);
 
   const int lane = threadIdx.x & 31;
   const int sub = lane & (LPR - 1);
@@ -380,7 +372,7 @@ mult_brightness_kernel(GridView<Real> g, MultView<Real> mv, MultParams<Real> P_,
         int idx[4];
         Real w[4];
         const Real dist = d_start + is * d_step;
-        substep_interp<Real>(s_rb, s_sb, s_pr, s_lpr, s_ps, n_rb, n_sb1, cur, px, py, pz, lx, ly, lz, dist, idx, w);
+        substep_interp<Real>(T, cur, px, py, pz, lx, ly, lz, dist, idx, w);
 #pragma unroll
         for (int k = 0; k < 4; k++) {              // interp_voxel_vector: sum_k w[k] * q[idx[k]], left to right
           const Real *r = mv.rec_pt + (size_t) idx[k] * MULT_REC;
@@ -577,7 +569,7 @@ cudaError_t launch_mult_brightness(const b200rt_multiplet_desc &d, const GridVie
   if (e != cudaSuccess) return e;
   const MultParams<Real> P = mult_params<Real>(d);
   const int threads = 128;
-  const size_t smem = (size_t) (4 * g.n_rb + 2 * g.n_sb) * sizeof(Real);
+  const size_t smem = GeomTables<Real>::doubles(g.n_rb, g.n_sb) * sizeof(Real);
   long long blocks = (count * LPR + threads - 1) / threads;
   if (blocks > (long long) NUM_SMS * 4) blocks = (long long) NUM_SMS * 4;
   MULT_DISPATCH(d.kind, {

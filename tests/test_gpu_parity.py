@@ -95,6 +95,31 @@ def test_row_sharding_equals_full(synth, binding):
         assert rel_err(Kfull[e], G2.K(e)) < 1e-13         # fp64 RED ordering only
 
 
+def test_interleaved_shards_equal_full(synth, binding):
+    """b200rt_influence_ranges: the interleaved source-voxel shards of a multi-GPU build (one launch set per batch
+    through the slot -> voxel map), including empty shards and a single-range call, equal one full pass"""
+    import importlib
+    multi = importlib.import_module("3d_planetary_rt_model_b200.multi")
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=2, sza_T_contrast=0.05)
+    G = binding.GpuModel(scn, "f64")
+    _, ns_full = G.build_rows()
+    Kfull = [G.K(e).copy() for e in range(2)]
+    G2 = binding.GpuModel(scn, "f64")
+    n, total = G2.n_vox, 0
+    for rank in range(3):
+        G2.ctx.influence_ranges(multi.partition_interleaved(n, 3, rank, 5))
+        total += G2.ctx.last_step_count()
+    assert total == ns_full
+    for e in range(2):
+        assert rel_err(Kfull[e], G2.K(e)) < 1e-13
+    G2.ctx.influence_ranges([(0, n)])
+    assert G2.ctx.last_step_count() == ns_full
+    G2.ctx.influence_ranges([])                            # nothing to do: only the single-scattering rays run
+    assert G2.ctx.last_step_count() == 0
+    with pytest.raises(binding.B200RTError):
+        G2.ctx.influence_ranges([(5, 9), (7, 12)])         # overlapping ranges are refused
+
+
 def test_edge_cases(synth, binding, oraclebind):
     scn = synth.make_scenario(12, 8, 5, 6, n_em=2)
     G = binding.GpuModel(scn, "f64")
