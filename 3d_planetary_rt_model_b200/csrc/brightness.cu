@@ -234,40 +234,46 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       for (int e = 0; e < NEM; e++) my_in[e][0] = LineShape<Real>::param(my_in[e][0]);
     }
 
-    // ---- apply the four sub-steps in order
+    // ---- apply the four sub-steps in order.  The broadcasts and the wavelength sum are full-warp shuffles executed by
+    // every lane (a group past the end of its line of sight moves garbage it never uses): with the 4-lane member masks
+    // the compiler wrapped every shuffle group in MATCH / REDUX / VOTE mask checks (~5 % of the issued instructions)
     const int nvalid = have ? min(LPR, total - j0) : 0;
+    const unsigned FULL = 0xffffffffu;
 #pragma unroll
     for (int q = 0; q < LPR; q++) {
-      if (q < nvalid) {
-        const Real s = shfl_real<Real>(gmask, my_s, lead + q);
+      const bool act = q < nvalid;
+      const Real s = shfl_real<Real>(FULL, my_s, lead + q);
 #pragma unroll
-        for (int e = 0; e < NEM; e++) {
-          const Real lsp = shfl_real<Real>(gmask, my_in[e][0], lead + q);
-          const Real dens = shfl_real<Real>(gmask, my_in[e][1], lead + q);
-          const Real dts = shfl_real<Real>(gmask, my_in[e][2], lead + q);
-          const Real dta = shfl_real<Real>(gmask, my_in[e][3], lead + q);
-          const Real Sv = shfl_real<Real>(gmask, my_in[e][4], lead + q);
-          // singlet_CFR::update_tracker_start<false> + update_tracker_brightness
+      for (int e = 0; e < NEM; e++) {
+        const Real lsp = shfl_real<Real>(FULL, my_in[e][0], lead + q);
+        const Real dens = shfl_real<Real>(FULL, my_in[e][1], lead + q);
+        const Real dts = shfl_real<Real>(FULL, my_in[e][2], lead + q);
+        const Real dta = shfl_real<Real>(FULL, my_in[e][3], lead + q);
+        const Real Sv = shfl_real<Real>(FULL, my_in[e][4], lead + q);
+        // singlet_CFR::update_tracker_start<false> + update_tracker_brightness
+        const Real tau_species_voxel = dts * s;
+        Real T_int = 0;
+        if (act) {
           acc_col[e] += dens * s;
-          const Real tau_species_voxel = dts * s;
           acc_tsp[e] += tau_species_voxel;
           acc_tab[e] += dta * s;
           const Real common = dts * s;
           Real phi[NLL];
           LineShape<Real>::eval(lsp, sub, phi);
-          Real T_int = 0;
 #pragma unroll
           for (int m = 0; m < NLL; m++) {
             const Real lineshape = phi[m];
             const Real tau = (dta + dts * lineshape) * s;
             const Real tp = MathB<Real>::exp_(-tau);
-            Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::divq_(Real(1.0) - tp, tau);
-            c *= (wgt[m] * lineshape * P[e][m]) * common;
-            T_int += c;
+            const Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::divq_(Real(1.0) - tp, tau);
+            T_int = fma(c * wgt[m], lineshape * P[e][m], T_int);    // x common once, after the wavelength loop
             P[e][m] *= tp;
           }
-          T_int += __shfl_xor_sync(gmask, T_int, 1);
-          T_int += __shfl_xor_sync(gmask, T_int, 2);
+          T_int *= common;
+        }
+        T_int += __shfl_xor_sync(FULL, T_int, 1);
+        T_int += __shfl_xor_sync(FULL, T_int, 2);
+        if (act) {
           if (T_int > tau_species_voxel) T_int = tau_species_voxel;
           acc_B[e] += Sv * gfac[e] * T_int;
         }

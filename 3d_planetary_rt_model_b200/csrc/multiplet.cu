@@ -387,18 +387,22 @@ mult_brightness_kernel(GridView<Real> g, MultView<Real> mv, MultParams<Real> P_,
 
     // ---- apply the eight sub-steps in order
     const int nvalid = have ? min(LPR, total - j0) : 0;
+    // (broadcasts and wavelength sums as full-warp shuffles executed by every lane: see brightness.cu)
+    const unsigned FULL = 0xffffffffu;
     for (int q = 0; q < LPR; q++) {
-      if (q < nvalid) {
-        const Real s = __shfl_sync(gmask, my_s, lead + q);
+      {
+        const bool act = q < nvalid;
+        const Real s = __shfl_sync(FULL, my_s, lead + q);
         Real in[NQ];
 #pragma unroll
-        for (int a = 0; a < NQ; a++) in[a] = __shfl_sync(gmask, my_in[a], lead + q);
-        const Real T = in[0], nabs = in[1];
+        for (int a = 0; a < NQ; a++) in[a] = __shfl_sync(FULL, my_in[a], lead + q);
+        const Real T = act ? in[0] : Real(1), nabs = in[1];
         const Real a = P_.T_ref / T;
         const Real nf = m_sqrt<Real>(a);
         Real Tint[NL];
 #pragma unroll
         for (int l = 0; l < NL; l++) Tint[l] = 0;
+        if (act)
 #pragma unroll
         for (int j = 0; j < NLP; j++) {
           const int i = sub + LPR * j;
@@ -428,16 +432,20 @@ mult_brightness_kernel(GridView<Real> g, MultView<Real> mv, MultParams<Real> P_,
 #pragma unroll
         for (int l = 0; l < NL; l++) {
           Real t = Tint[l];
-          t += __shfl_xor_sync(gmask, t, 1);
-          t += __shfl_xor_sync(gmask, t, 2);
-          t += __shfl_xor_sync(gmask, t, 4);
+          t += __shfl_xor_sync(FULL, t, 1);
+          t += __shfl_xor_sync(FULL, t, 2);
+          t += __shfl_xor_sync(FULL, t, 4);
           if (t > s) t = s;                                             // :284-299
-          accB[l] += in[2 + NLOW + TR::upper(l)] * P_.A[l] * t / Real(1e9);   // :302-316
-          acc_tsp[l] += (in[2 + TR::lower(l)] * P_.sigma[l] * (P_.norm[l] * nf)) * s;
-          acc_tab[l] += (nabs * P_.xsec[l]) * s;
+          if (act) {
+            accB[l] += in[2 + NLOW + TR::upper(l)] * P_.A[l] * t / Real(1e9);   // :302-316
+            acc_tsp[l] += (in[2 + TR::lower(l)] * P_.sigma[l] * (P_.norm[l] * nf)) * s;
+            acc_tab[l] += (nabs * P_.xsec[l]) * s;
+          }
         }
+        if (act) {
 #pragma unroll
-        for (int l = 0; l < NLOW; l++) acc_col[l] += in[2 + l] * s;
+          for (int l = 0; l < NLOW; l++) acc_col[l] += in[2 + l] * s;
+        }
       }
     }
     j0 += LPR;
