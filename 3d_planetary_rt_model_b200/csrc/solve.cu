@@ -601,6 +601,12 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1, 4, KC_BULK, STAGES_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
+  // quarter-width tiles (128x32) for the two kernels of the critical path once the trailing matrix is small: four
+  // times as many CTAs, half the DMMA work each -- the tail of the factorisation is latency, not throughput
+  const size_t gemm_smem_q = gemm_smem_bytes(KC_DEFAULT, STAGES_DEFAULT, TN / 4);
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
+  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
+  const int quarter_below = 36;      // block columns left: (2 m1 - 1) x 4 CTAs <= 2 per SM
 
   // second stream + events for the look-ahead
   if (!c->stream2) {   // the chain is the critical path: give its stream the highest priority
@@ -631,7 +637,8 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
     launches++;
     if (m1 > 0) {
-      gemm128_kernel<2, 4><<<dim3(m1, 2), 256, gemm_smem_h, s>>>(A, np, KB, dinv, Lbuf(KB));
+      if (m1 <= quarter_below) gemm128_kernel<2, 2><<<dim3(m1, 4), 256, gemm_smem_q, s>>>(A, np, KB, dinv, Lbuf(KB));
+      else gemm128_kernel<2, 4><<<dim3(m1, 2), 256, gemm_smem_h, s>>>(A, np, KB, dinv, Lbuf(KB));
       rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, s>>>(Lbuf(KB), np, KB, b);
       launches += 2;
     }
@@ -654,7 +661,8 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       const int m1 = nK - KB - 1;                                       // block columns after KB
       if (m1 > 0) {
         mark("ui_begin", KB, st);
-        gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
+        if (m1 <= quarter_below) gemm128_kernel<0, 2><<<dim3(2 * m1 - 1, 4), 256, gemm_smem_q, st>>>(A, np, KB, dinv, Lbuf(KB));
+      else gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
         mark("ui_end", KB, st);
         launches++;
         CK(cudaEventRecord(c->lu_events[2 * KB + 1], st));  // evU[KB]

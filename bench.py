@@ -444,6 +444,7 @@ def run_ours(args):
             ex.update(extra_bench.sweep(512, 10000, 4, 1))
             ex.update(extra_bench.multiplet(0))
             ex.update(extra_bench.multiplet(1))
+            ex.update(extra_bench.float_job(n_los))
             line["extras"] = ex
         except Exception as exn:
             line["extras"] = {"error": str(exn)}

@@ -79,6 +79,28 @@ def multiplet(kind, image_px=600):
     return out
 
 
+def float_job(n_los):
+    """The bench workload with Real = float (the only precision the reference's own GPU module is built in, makefile:80,230;
+    parity bar 1e-4): 100x60 grid, 24x16 rays, H Ly alpha + n_los lines of sight; the solve stays FP64."""
+    synth = importlib.import_module(PKG + ".synth")
+    binding = importlib.import_module(PKG + ".binding")
+    scn = synth.make_scenario(100, 60, 24, 16, n_em=1, rmethod=synth.RMETHOD_ALTITUDE, rmax=synth.rMars + 50000e5)
+    G = binding.GpuModel(scn, "f32")
+    locs, dirs = synth.random_los(n_los)
+    G.ctx.los_upload(G.ctx.los_from_MSO(locs, dirs))
+    for it in range(3):
+        G.ctx.influence(0, scn.n_vox)
+        t_tr, t_in = G.ctx.kernel_ms(binding.PH_TRAVERSE)[0], G.ctx.kernel_ms(binding.PH_INFLUENCE)[0]
+        steps = G.ctx.last_step_count()
+        G.ctx.solve()
+        t_so = G.ctx.kernel_ms(binding.PH_SOLVE)[0]
+        G.ctx.brightness_resident(10)
+        t_lt, t_br = G.ctx.kernel_ms(binding.PH_TRAVERSE)[0], G.ctx.kernel_ms(binding.PH_BRIGHTNESS)[0]
+    return {"f32_job": {"influence_traverse_ms": t_tr, "influence_march_ms": t_in, "steps_per_s": steps / ((t_tr + t_in) * 1e-3),
+                        "solve_ms": t_so, "los_traverse_ms": t_lt, "brightness_ms": t_br,
+                        "los_per_s": n_los / ((t_lt + t_br) * 1e-3), "job_ms": t_tr + t_in + t_so + t_lt + t_br}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iph-los", type=int, default=1000000)
