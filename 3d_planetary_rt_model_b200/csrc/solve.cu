@@ -632,15 +632,14 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     cudaEventRecord(ev, s);
     marks.push_back({what, KB, ev});
   };
-  auto chain = [&](int KB, cudaStream_t s) {       // invert the diagonal block, form L21, forward-substitute
+  auto chain = [&](int KB, cudaStream_t s) {       // invert the diagonal block, form L21
     const int m1 = nK - KB - 1;
     gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
     launches++;
     if (m1 > 0) {
       if (m1 <= quarter_below) gemm128_kernel<2, 2><<<dim3(m1, 4), 256, gemm_smem_q, s>>>(A, np, KB, dinv, Lbuf(KB));
       else gemm128_kernel<2, 4><<<dim3(m1, 2), 256, gemm_smem_h, s>>>(A, np, KB, dinv, Lbuf(KB));
-      rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, s>>>(Lbuf(KB), np, KB, b);
-      launches += 2;
+      launches += 1;
     }
   };
   // The ~280 launches of the factorisation and back substitution (two streams, ~140 event dependencies) are captured
@@ -662,11 +661,15 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       if (m1 > 0) {
         mark("ui_begin", KB, st);
         if (m1 <= quarter_below) gemm128_kernel<0, 2><<<dim3(2 * m1 - 1, 4), 256, gemm_smem_q, st>>>(A, np, KB, dinv, Lbuf(KB));
-      else gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
+        else gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
         mark("ui_end", KB, st);
         launches++;
         CK(cudaEventRecord(c->lu_events[2 * KB + 1], st));  // evU[KB]
         CK(cudaStreamWaitEvent(sB, c->lu_events[2 * KB + 1], 0));
+        // forward substitution of the right-hand side: off the critical path (the next chain does not need it), on
+        // the update stream, in block-column order
+        rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, st>>>(Lbuf(KB), np, KB, b);
+        launches++;
         mark("chain_begin", KB + 1, sB);
         chain(KB + 1, sB);
         mark("chain_end", KB + 1, sB);
