@@ -299,10 +299,12 @@ class Context:
             raise B200RTError(f"b200rt_los_from_MSO: status {rc}")
         return out
 
-    def brightness(self, los, n_subsamples=10):
-        """host buffers in, host buffers out: the reference-facing call (brightness_gpu)."""
+    def brightness(self, los, n_subsamples=10, out=None):
+        """host buffers in, host buffers out: the reference-facing call (brightness_gpu).  `out`: four caller-owned
+        float64 arrays of shape (rows, n) to receive the results (e.g. page-locked buffers that are re-used)."""
         n = len(los[0])
-        out = [np.zeros((r, n)) for r in self._out_rows()]
+        if out is None:
+            out = [np.zeros((r, n)) for r in self._out_rows()]
         self._ck(self.lib.b200rt_brightness(self.h, n, *los, n_subsamples, *[_ptr(o) for o in out]))
         self.n_los = n
         return dict(brightness=out[0], tau_species_final=out[1], tau_absorber_final=out[2], species_col_dens=out[3])

@@ -479,6 +479,66 @@ backsolve128_kernel(const double *__restrict__ A, int np, int KB, const double *
   }
 }
 
+// ---- the whole back substitution in ONE launch: CTA I owns y_I; for K = nK-1 .. 0 CTA K forms x_K = A_KK^-1 y_K, publishes
+// it and raises flag[K]; every CTA I < K waits for the flag and applies y_I -= A_IK x_K.  Critical path per block column: one
+// flag round trip + two 128x128 mat-vecs, against a kernel launch + the same two mat-vecs before (46 launches, ~0.5 ms).
+__global__ void __launch_bounds__(512)
+backsolve_fused_kernel(const double *__restrict__ A, int np, int nK, const double *__restrict__ dinv, const double *__restrict__ b,
+                       double *__restrict__ x, int *flags) {
+  __shared__ double yk[TB], xk[TB];
+  // CTAs are handed out in blockIdx order: the producers (large K) come first, so a waiting CTA's producers are
+  // always resident or done
+  const int I = nK - 1 - (int) blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < TB) yk[tid] = b[(size_t) I * TB + tid];
+  __syncthreads();
+  // 16 warps x 8 rows each: out[row] = sum_c M[row][c] v[c]
+  auto matvec = [&](const double *M, size_t ld, const double *v, double (&out)[8]) {
+    double vv[TB / 32], m[8][TB / 32];
+#pragma unroll
+    for (int q = 0; q < TB / 32; q++) vv[q] = v[lane + 32 * q];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int q = 0; q < TB / 32; q++) m[i][q] = __ldcg(M + (size_t) (warp * 8 + i) * ld + lane + 32 * q);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      double sacc = 0;
+#pragma unroll
+      for (int q = 0; q < TB / 32; q++) sacc += m[i][q] * vv[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      out[i] = sacc;
+    }
+  };
+  for (int K = nK - 1; K > I; K--) {
+    if (tid == 0) {
+      while (*reinterpret_cast<volatile int *>(flags + K) == 0) { }
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid < TB) xk[tid] = __ldcg(x + (size_t) K * TB + tid);
+    __syncthreads();
+    double r[8];
+    matvec(A + ((size_t) I * TB) * np + (size_t) K * TB, np, xk, r);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) yk[warp * 8 + i] -= r[i];
+    }
+    __syncthreads();
+  }
+  double r[8];
+  matvec(dinv + (size_t) I * TB * TB, TB, yk, r);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[(size_t) I * TB + warp * 8 + i] = r[i];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    *reinterpret_cast<volatile int *>(flags + I) = 1;
+  }
+}
+
 // ---- residual of the ORIGINAL system: |S0 - (S - w K S)|, one warp per row
 __global__ void residual_kernel(const double *__restrict__ K, int n, double w, const double *__restrict__ S0,
                                 const double *__restrict__ S, double *__restrict__ rabs) {
@@ -544,6 +604,8 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   double *b = A + (size_t) np * np, *x = b + np, *margin = x + np, *rabs = margin + np;
   double *dinv = c->lu_dinv.as<double>();
   double *Lbuf0 = dinv + (size_t) nK * TB * TB;
+  B200RT_CUDA(c, c->lu_flag.ensure((size_t) nK * sizeof(int)));
+  int *flags = c->lu_flag.as<int>();
   auto Lbuf = [&](int KB) { return Lbuf0 + (size_t) (KB & 1) * np * TB; };
   int launches = 0;
 
@@ -683,9 +745,15 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       }
     }
     mark("factor_end", 0, st);
-    for (int KB = nK - 1; KB >= 0; KB--) {
-      backsolve128_kernel<<<KB + 1, 512, 0, st>>>(A, np, KB, dinv, b, x);
+    if (nK <= NUM_SMS) {     // every CTA resident at once: the fused back substitution
+      CK(cudaMemsetAsync(flags, 0, nK * sizeof(int), st));
+      backsolve_fused_kernel<<<nK, 512, 0, st>>>(A, np, nK, dinv, b, x, flags);
       launches++;
+    } else {
+      for (int KB = nK - 1; KB >= 0; KB--) {
+        backsolve128_kernel<<<KB + 1, 512, 0, st>>>(A, np, KB, dinv, b, x);
+        launches++;
+      }
     }
     mark("backsolve_end", 0, st);
   return cudaGetLastError();
