@@ -139,12 +139,11 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
     }
     const Real Tr0 = valid ? em.T_ratio[v0] : Real(1);
     const Real renorm = one_over_sqrt_pi<Real>() * rsqrt_<Real>(Tr0);   // line_shape_normalization
-    Real nl0[LAMBDA_PER_LANE], P[LAMBDA_PER_LANE];                      // norm(T0) * phi0_i ;  transmission
+    // P[m] carries norm(T0) * phi0_i * transmission_i: the line shape at the origin is constant along the ray, so it is
+    // folded into the running product once instead of multiplying every step's contribution
+    Real P[LAMBDA_PER_LANE];
 #pragma unroll
-    for (int m = 0; m < LAMBDA_PER_LANE; m++) {
-      nl0[m] = renorm * rexp<Real>(-l2[m] * Tr0);
-      P[m] = Real(1);
-    }
+    for (int m = 0; m < LAMBDA_PER_LANE; m++) P[m] = renorm * rexp<Real>(-l2[m] * Tr0);
     const Real domega = (MODE == 0 && valid) ? g.ray_domega[ir] : Real(1);
     Real tau_sp = 0, tau_abs = 0;
 
@@ -201,7 +200,7 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
           const Real tp = exp_neg<Real, PP>(-tau);
           if (MODE == 0) {
             const Real f = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) * tau : (Real(1.0) - tp);
-            G += (rec[m].y * P[m]) * f * nl0[m];
+            G = fma(rec[m].y * P[m], f, G);
           }
           P[m] *= tp;
         }
@@ -222,7 +221,7 @@ march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_r
       // holstein_T_final = sum_i w_i * norm(T0) * phi0_i * P_i   (singlet_CFR.hpp:183-186)
       Real T = 0;
 #pragma unroll
-      for (int m = 0; m < LAMBDA_PER_LANE; m++) T += w[m] * nl0[m] * P[m];
+      for (int m = 0; m < LAMBDA_PER_LANE; m++) T += w[m] * P[m];
       T += __shfl_xor_sync(0xffffffffu, T, 1);
       T += __shfl_xor_sync(0xffffffffu, T, 2);
       if (valid && sub == 0) {
