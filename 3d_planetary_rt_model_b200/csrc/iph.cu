@@ -74,46 +74,61 @@ struct Tables {
 struct Hint { int alt, ang; };
 
 // lower bound (first j with x <= ax[j]) starting from the previous bracket: the hint is right or off by one in all but
-// a handful of look-ups per line of sight, so one predicated correction + one check replace the search; the rare miss
-// (the first look-up, the jump from the end of one TOP segment to the next outer point) takes the binary search.
-// On return a_lo = ax[lo-1] (or ax[0]) and a_hi = ax[lo] (or ax[n-1]) are the values the interpolation needs.
-__device__ __forceinline__ int lower_bound_hint(const float *ax, int n, float x, int hint) {
+// a handful of look-ups per line of sight.  Right: the two table values read to find that out ARE the bracket.  Off by
+// one: one more value decides whether the neighbouring cell is the bracket.  Anything else (the first look-up, the jump
+// from the end of one TOP segment to the next outer point) takes the binary search.  below = ax[lo-1], at = ax[lo].
+struct Bracket { int lo; float below, at; };
+__device__ __forceinline__ Bracket lower_bound_hint(const float *ax, int n, float x, int hint) {
   int lo = hint;
-  const bool up = ax[lo] < x;
-  const bool down = (lo > 0) && !(ax[lo - 1] < x);
-  lo += (up ? 1 : 0) - (down ? 1 : 0);
-  const bool ok = (lo == 0 || ax[lo - 1] < x) && (lo >= n || !(ax[lo] < x));
-  if (!ok) {
-    int l = 0, hh = n;
-    while (l < hh) {
-      const int mid = (l + hh) >> 1;
-      if (ax[mid] < x) l = mid + 1; else hh = mid;
+  float at = ax[lo];
+  float below = ax[max(lo - 1, 0)];
+  const bool up = at < x;
+  const bool down = (lo > 0) && !(below < x);
+  if (up || down) {
+    const int nlo = up ? lo + 1 : lo - 1;
+    const float extra = ax[up ? min(lo + 1, n - 1) : max(lo - 2, 0)];
+    const bool ok = up ? (nlo >= n || !(extra < x)) : (nlo == 0 || extra < x);
+    if (ok) {
+      if (up) { below = at; at = extra; } else { at = below; below = extra; }
+      lo = nlo;
+    } else {
+      int l = 0, hh = n;
+      while (l < hh) {
+        const int mid = (l + hh) >> 1;
+        if (ax[mid] < x) l = mid + 1; else hh = mid;
+      }
+      lo = l;
+      at = ax[min(lo, n - 1)];
+      below = ax[max(lo - 1, 0)];
     }
-    lo = l;
   }
-  return lo;
+  return {lo, below, at};
 }
 // first j with T <= ang[j]  (the Fortran's arithmetic-IF scan, :517-528) and the weight of the upper neighbour;
 // the case analysis of the scan (below the axis, on a node, beyond the axis) as selects
 __device__ __forceinline__ void bracket_ang(const Tables &t, float T, int &ll, int &llp, float &dt, Hint &h) {
-  const int lo = lower_bound_hint(t.ang, t.lmax, T, h.ang);
+  const Bracket b = lower_bound_hint(t.ang, t.lmax, T, h.ang);
+  const int lo = b.lo;
   h.ang = min(lo, t.lmax - 1);
-  const bool on_node = (lo < t.lmax) && (T == t.ang[h.ang]);
+  const bool on_node = (lo < t.lmax) && (T == b.at);
   ll = min(max(lo - 1, 0), t.lmax - 2);
   llp = ll + 1;
-  const float a0 = t.ang[ll];
-  dt = (T - a0) / (t.ang[llp] - a0);
+  float a0 = b.below, a1 = b.at;
+  if (lo == 0 || lo >= t.lmax) { a0 = t.ang[ll]; a1 = t.ang[llp]; }     // off the axis: the end cell extrapolates
+  dt = (T - a0) / (a1 - a0);
   if (on_node) { ll = lo; llp = min(lo + 1, t.lmax - 1); dt = 0.f; }
 }
 __device__ __forceinline__ void bracket_alt(const Tables &t, float Z, int &kk, int &kkp, float &du, Hint &h) {
-  const int lo = lower_bound_hint(t.alt, t.kmax, Z, h.alt);
+  const Bracket b = lower_bound_hint(t.alt, t.kmax, Z, h.alt);
+  const int lo = b.lo;
   h.alt = min(lo, t.kmax - 1);
   const bool beyond = lo >= t.kmax;
-  const bool on_node = !beyond && (Z == t.alt[h.alt]);
+  const bool on_node = !beyond && (Z == b.at);
   kk = min(max(lo - 1, 0), t.kmax - 2);
   kkp = kk + 1;
-  const float a0 = t.alt[kk];
-  du = (Z - a0) / (t.alt[kkp] - a0);
+  float a0 = b.below, a1 = b.at;
+  if (lo == 0 || beyond) { a0 = t.alt[kk]; a1 = t.alt[kkp]; }
+  du = (Z - a0) / (a1 - a0);
   if (on_node) { kk = lo; kkp = min(lo + 1, t.kmax - 1); du = 0.f; }
   if (beyond) { kk = kkp = t.kmax - 1; du = 0.f; }
 }
