@@ -29,6 +29,7 @@
 // All products use mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4: tcgen05 has no FP64 kind, so
 // this is the FP64 tensor-core path on sm_100a).  Back substitution walks the block columns from
 // the right:  x_K = A_KK^-1 y_K ;  y_I -= A_IK x_K  (I < K).
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -126,6 +127,7 @@ constexpr int TB = 128;   // block size of the factorisation
 constexpr int GJ_THREADS = 512;
 __global__ void __launch_bounds__(GJ_THREADS)
 gj128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ dinv) {
+  KB += blockIdx.x;     // (the factorisation launches one CTA; the profiling probe inverts many diagonal blocks at once)
   __shared__ __align__(16) double prow[2][4][TB];   // rows J of the step
   __shared__ __align__(16) double pcol[2][TB][4];   // columns J of the step
   __shared__ __align__(16) double pinv[2][4][4];    // P^-1 of the step
@@ -286,6 +288,189 @@ gj128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ 
 #pragma unroll
     for (int nt = 0; nt < 4; nt++)
       *reinterpret_cast<double2 *>(out + (size_t) (wm + 8 * mt + g) * TB + wn + 8 * nt + 2 * tq) =
+          make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+}
+
+// ---- (1b) the same block Gauss-Jordan inverse on a CLUSTER of four CTAs (four SMs): CTA c keeps rows 32c .. 32c+31 of
+// the block (8 warps x 16 columns, 8 DMMA tiles per warp).  On one SM a step costs ~3300 cycles: 1230 of DMMA issue and
+// ~1500 of shared-memory bandwidth moving the fragments (measured, tools/dev/README.md); four SMs cut both by four.
+// Per step the CTA that owns the pivot rows writes the raw rows J of the next step, and the warp that owns the next
+// pivot block its inverse, into the shared memory of ALL four CTAs (distributed shared memory), every CTA publishes its
+// own part of the columns J locally, and one cluster barrier closes the step.
+constexpr int GJC_THREADS = 256;
+template <int GJC_CTAS>
+__global__ void __launch_bounds__(GJC_THREADS)
+gj128_cluster_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ dinv) {
+  constexpr int GJC_ROWS = TB / GJC_CTAS, MT = GJC_ROWS / 8;   // rows and m-tiles per CTA (4 CTAs: 32, 4; 8 CTAs: 16, 2)
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int) cluster.block_rank();
+  __shared__ __align__(16) double prow[2][4][TB];          // raw rows J of the step (same content in every CTA)
+  __shared__ __align__(16) double pcol[2][GJC_ROWS][4];    // raw columns J, this CTA's rows
+  __shared__ __align__(16) double pinv[2][4][4];           // P^-1 of the step (same content in every CTA)
+  __shared__ __align__(16) double praw[4][4];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int wn = w * 16, row0 = crank * GJC_ROWS;
+  const double *Akk = A + ((size_t) KB * TB) * np + (size_t) KB * TB;
+  double acc[MT][2][2];   // element (row0 + 8 mt + g, wn + 8 nt + 2 tq + c)
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+      const double2 v = *reinterpret_cast<const double2 *>(Akk + (size_t) (row0 + 8 * mt + g) * np + wn + 8 * nt + 2 * tq);
+      acc[mt][nt][0] = v.x;
+      acc[mt][nt][1] = v.y;
+    }
+  double *prow_r[GJC_CTAS], *pinv_r[GJC_CTAS];
+#pragma unroll
+  for (int r = 0; r < GJC_CTAS; r++) {
+    prow_r[r] = cluster.map_shared_rank(&prow[0][0][0], r);
+    pinv_r[r] = cluster.map_shared_rank(&pinv[0][0][0], r);
+  }
+  // step (band, tJ, half): pivots 32 band + 8 tJ + 4 half .. +3; they sit in CTA `band`, m-tile tJ, lanes g >> 2 == half,
+  // and in warp wJ = (32 band + 8 tJ) / 16, n-tile nJ = tJ & 1 of every CTA, lanes tq >> 1 == half
+  auto invert_next_pivot = [&](int band, int tJ, int half, int nb) {
+    const int wJ = (GJC_ROWS * band + 8 * tJ) / 16;
+    if (crank == band && w == wJ) {               // one warp of one CTA
+      if ((g >> 2) == half && (tq >> 1) == half) {
+#pragma unroll
+        for (int t = 0; t < MT; t++)
+          if (t == tJ) *reinterpret_cast<double2 *>(&praw[g & 3][(2 * tq) & 3]) = make_double2(acc[t][t & 1][0], acc[t][t & 1][1]);
+      }
+      __syncwarp();
+      double m[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double2 a = *reinterpret_cast<const double2 *>(&praw[q][0]);
+        const double2 b = *reinterpret_cast<const double2 *>(&praw[q][2]);
+        m[q][0] = a.x; m[q][1] = a.y; m[q][2] = b.x; m[q][3] = b.y;
+      }
+      __syncwarp();
+      inv4(m);
+      if (lane < 4) {
+        const double2 lo = make_double2(sel4(m[0][0], m[1][0], m[2][0], m[3][0], lane), sel4(m[0][1], m[1][1], m[2][1], m[3][1], lane));
+        const double2 hi = make_double2(sel4(m[0][2], m[1][2], m[2][2], m[3][2], lane), sel4(m[0][3], m[1][3], m[2][3], m[3][3], lane));
+#pragma unroll
+        for (int r = 0; r < GJC_CTAS; r++) {
+          *reinterpret_cast<double2 *>(pinv_r[r] + (nb * 4 + lane) * 4 + 0) = lo;
+          *reinterpret_cast<double2 *>(pinv_r[r] + (nb * 4 + lane) * 4 + 2) = hi;
+        }
+      }
+    }
+  };
+  auto publish = [&](int band, int tJ, int half, int nb) {
+    if (crank == band && (g >> 2) == half) {      // the rows J: into every CTA
+#pragma unroll
+      for (int t = 0; t < MT; t++)
+        if (t == tJ) {
+#pragma unroll
+          for (int nt = 0; nt < 2; nt++) {
+            const double2 v = make_double2(acc[t][nt][0], acc[t][nt][1]);
+#pragma unroll
+            for (int r = 0; r < GJC_CTAS; r++)
+              *reinterpret_cast<double2 *>(prow_r[r] + ((size_t) nb * 4 + (g & 3)) * TB + wn + 8 * nt + 2 * tq) = v;
+          }
+        }
+    }
+    const int wJ = (GJC_ROWS * band + 8 * tJ) / 16;
+    if (w == wJ && (tq >> 1) == half) {           // this CTA's part of the columns J: local
+#pragma unroll
+      for (int t = 0; t < 2; t++)
+        if (t == (tJ & 1)) {
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++)
+            *reinterpret_cast<double2 *>(&pcol[nb][8 * mt + g][(2 * tq) & 3]) = make_double2(acc[mt][t][0], acc[mt][t][1]);
+        }
+    }
+  };
+  invert_next_pivot(0, 0, 0, 0);
+  publish(0, 0, 0, 0);
+  cluster.sync();
+  constexpr int SPB = 2 * MT;              // steps per band (per CTA of pivot rows)
+  for (int kk = 0; kk < GJC_CTAS; kk++) {  // CTA holding the pivot rows
+#pragma unroll
+    for (int ks = 0; ks < SPB; ks++) {     // step within its rows: m-tile ks >> 1, half ks & 1
+      const int tJ = ks >> 1, half = ks & 1, buf = ks & 1, nJ = tJ & 1, wJ = (GJC_ROWS * kk + 8 * tJ) / 16;
+      const int tJn = ((ks + 1) % SPB) >> 1, halfn = (ks + 1) & 1, kkn = kk + (ks == SPB - 1 ? 1 : 0);   // the step after
+      const bool own_rows = (crank == kk) && ((g >> 2) == half);
+      const bool own_cols = (w == wJ) && ((tq >> 1) == half);
+      // B fragments of the update: (P^-1 A[J,:])[tq][wn + 8 nt + g];  A fragments: -A[:,J][row][tq]
+      double pk[4], spb[2], fa[MT];
+      {
+        const double2 a = *reinterpret_cast<const double2 *>(&pinv[buf][tq][0]);
+        const double2 b = *reinterpret_cast<const double2 *>(&pinv[buf][tq][2]);
+        pk[0] = a.x; pk[1] = a.y; pk[2] = b.x; pk[3] = b.y;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; nt++) {
+        const int col = wn + 8 * nt + g;
+        spb[nt] = pk[0] * prow[buf][0][col];
+        spb[nt] = fma(pk[1], prow[buf][1][col], spb[nt]);
+        spb[nt] = fma(pk[2], prow[buf][2][col], spb[nt]);
+        spb[nt] = fma(pk[3], prow[buf][3][col], spb[nt]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) fa[mt] = -pcol[buf][8 * mt + g][tq];
+      // the tile holding the next pivot block first: its owner inverts it while the other DMMAs drain
+      dmma8x8x4(acc[tJn][tJn & 1][0], acc[tJn][tJn & 1][1], fa[tJn], spb[tJn & 1]);
+      if (kkn < GJC_CTAS) invert_next_pivot(kkn, tJn, halfn, buf ^ 1);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
+          if (!(mt == tJn && nt == (tJn & 1))) dmma8x8x4(acc[mt][nt][0], acc[mt][nt][1], fa[mt], spb[nt]);
+      // the pivot rows / columns are then overwritten with their new values
+      if (own_rows) {      // A[J,:] <- P^-1 A[J,:]
+        double pr[4];
+        {
+          const double2 a = *reinterpret_cast<const double2 *>(&pinv[buf][g & 3][0]);
+          const double2 b = *reinterpret_cast<const double2 *>(&pinv[buf][g & 3][2]);
+          pr[0] = a.x; pr[1] = a.y; pr[2] = b.x; pr[3] = b.y;
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) {
+          double c0 = 0, c1 = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const double2 r = *reinterpret_cast<const double2 *>(&prow[buf][q][wn + 8 * nt + 2 * tq]);
+            c0 = fma(pr[q], r.x, c0);
+            c1 = fma(pr[q], r.y, c1);
+          }
+          acc[tJ][nt][0] = c0;
+          acc[tJ][nt][1] = c1;
+        }
+      }
+      if (own_cols) {      // A[:,J] <- -A[:,J] P^-1, and the pivot block itself <- P^-1
+        const int cq = (2 * tq) & 3;   // 0 or 2: this lane's two columns of J
+        double pc0[4], pc1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const double2 a = *reinterpret_cast<const double2 *>(&pinv[buf][q][cq]);
+          pc0[q] = a.x;
+          pc1[q] = a.y;
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+          const double2 f01 = *reinterpret_cast<const double2 *>(&pcol[buf][8 * mt + g][0]);
+          const double2 f23 = *reinterpret_cast<const double2 *>(&pcol[buf][8 * mt + g][2]);
+          acc[mt][nJ][0] = -fma(f23.y, pc0[3], fma(f23.x, pc0[2], fma(f01.y, pc0[1], f01.x * pc0[0])));
+          acc[mt][nJ][1] = -fma(f23.y, pc1[3], fma(f23.x, pc1[2], fma(f01.y, pc1[1], f01.x * pc1[0])));
+        }
+        if (own_rows) {
+          acc[tJ][nJ][0] = sel4(pc0[0], pc0[1], pc0[2], pc0[3], g & 3);
+          acc[tJ][nJ][1] = sel4(pc1[0], pc1[1], pc1[2], pc1[3], g & 3);
+        }
+      }
+      if (kkn < GJC_CTAS) publish(kkn, tJn, halfn, buf ^ 1);
+      cluster.sync();
+    }
+  }
+  double *out = dinv + (size_t) KB * TB * TB;
+#pragma unroll
+  for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+      *reinterpret_cast<double2 *>(out + (size_t) (row0 + 8 * mt + g) * TB + wn + 8 * nt + 2 * tq) =
           make_double2(acc[mt][nt][0], acc[mt][nt][1]);
 }
 
@@ -696,7 +881,17 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   };
   auto chain = [&](int KB, cudaStream_t s) {       // invert the diagonal block, form L21
     const int m1 = nK - KB - 1;
-    gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
+    {   // diagonal-block inverse on a cluster of four SMs (gj128_cluster_kernel); gj128_kernel is the one-SM form
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(4); cfg.blockDim = dim3(GJC_THREADS); cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      const double *Ac = A;
+      if (cudaLaunchKernelEx(&cfg, gj128_cluster_kernel<4>, Ac, np, KB, dinv) != cudaSuccess)
+        gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
+    }
     launches++;
     if (m1 > 0) {
       if (m1 <= quarter_below) gemm128_kernel<2, 2><<<dim3(m1, 4), 256, gemm_smem_q, s>>>(A, np, KB, dinv, Lbuf(KB));
