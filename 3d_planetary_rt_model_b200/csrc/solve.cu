@@ -675,16 +675,27 @@ backsolve_fused_kernel(const double *__restrict__ A, int np, int nK, const doubl
   // always resident or done
   const int I = nK - 1 - (int) blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < TB) yk[tid] = b[(size_t) I * TB + tid];
+  extern __shared__ __align__(16) double sdinv[];       // A_II^-1, 128 kB: needed at the very end, fetched at the very start
+  {
+    const double2 *src = reinterpret_cast<const double2 *>(dinv + (size_t) I * TB * TB);
+    double2 *dst = reinterpret_cast<double2 *>(sdinv);
+    for (int i = tid; i < TB * TB / 2; i += blockDim.x) dst[i] = __ldcg(src + i);
+  }
   __syncthreads();
-  // 16 warps x 8 rows each: out[row] = sum_c M[row][c] v[c]
-  auto matvec = [&](const double *M, size_t ld, const double *v, double (&out)[8]) {
-    double vv[TB / 32], m[8][TB / 32];
-#pragma unroll
-    for (int q = 0; q < TB / 32; q++) vv[q] = v[lane + 32 * q];
+  // 16 warps x 8 rows each.  The matrix tile of the NEXT product is fetched into registers BEFORE the wait for the
+  // vector it multiplies (the factorisation is complete: every tile is final), so the critical path per block column is
+  // flag -> 1 kB vector -> FMAs + shuffle reduction, not flag -> 128 kB tile.
+  double m[8][TB / 32];
+  auto fetch = [&](const double *M, size_t ld) {
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
       for (int q = 0; q < TB / 32; q++) m[i][q] = __ldcg(M + (size_t) (warp * 8 + i) * ld + lane + 32 * q);
+  };
+  auto apply = [&](const double *v, double (&out)[8]) {
+    double vv[TB / 32];
+#pragma unroll
+    for (int q = 0; q < TB / 32; q++) vv[q] = v[lane + 32 * q];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       double sacc = 0;
@@ -696,6 +707,7 @@ backsolve_fused_kernel(const double *__restrict__ A, int np, int nK, const doubl
     }
   };
   for (int K = nK - 1; K > I; K--) {
+    fetch(A + ((size_t) I * TB) * np + (size_t) K * TB, np);
     if (tid == 0) {
       while (*reinterpret_cast<volatile int *>(flags + K) == 0) { }
       __threadfence();
@@ -704,15 +716,20 @@ backsolve_fused_kernel(const double *__restrict__ A, int np, int nK, const doubl
     if (tid < TB) xk[tid] = __ldcg(x + (size_t) K * TB + tid);
     __syncthreads();
     double r[8];
-    matvec(A + ((size_t) I * TB) * np + (size_t) K * TB, np, xk, r);
+    apply(xk, r);
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < 8; i++) yk[warp * 8 + i] -= r[i];
     }
     __syncthreads();
   }
+  // x_I = A_II^-1 y_I from the copy of the block inverse staged in shared memory at the start
   double r[8];
-  matvec(dinv + (size_t) I * TB * TB, TB, yk, r);
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int q = 0; q < TB / 32; q++) m[i][q] = sdinv[(size_t) (warp * 8 + i) * TB + lane + 32 * q];
+  apply(yk, r);
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 8; i++) x[(size_t) I * TB + warp * 8 + i] = r[i];
@@ -853,6 +870,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   const size_t gemm_smem_q = gemm_smem_bytes(KC_DEFAULT, STAGES_DEFAULT, TN / 4);
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
+  B200RT_CUDA(c, cudaFuncSetAttribute(backsolve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (TB * TB * sizeof(double))));
   const int quarter_below = 36;      // block columns left: (2 m1 - 1) x 4 CTAs <= 2 per SM
 
   // second stream + events for the look-ahead
@@ -942,7 +960,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     mark("factor_end", 0, st);
     if (nK <= NUM_SMS) {     // every CTA resident at once: the fused back substitution
       CK(cudaMemsetAsync(flags, 0, nK * sizeof(int), st));
-      backsolve_fused_kernel<<<nK, 512, 0, st>>>(A, np, nK, dinv, b, x, flags);
+      backsolve_fused_kernel<<<nK, 512, TB * TB * sizeof(double), st>>>(A, np, nK, dinv, b, x, flags);
       launches++;
     } else {
       for (int KB = nK - 1; KB >= 0; KB--) {
