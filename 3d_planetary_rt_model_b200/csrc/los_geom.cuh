@@ -7,6 +7,11 @@
 
 namespace b200rt {
 
+namespace fm {
+__device__ __forceinline__ double rsqrt_pos(double x);
+__device__ __forceinline__ double acos_fast(double x);
+__device__ __forceinline__ double log_pos(double x);
+}
 template <class Real> struct MathB;
 template <> struct MathB<double> {
   __device__ static double exp_(double x) { return fm::exp_nonpos(x); }   // arguments are <= 0 and finite
@@ -23,18 +28,25 @@ template <> struct MathB<double> {
   __device__ static double coneeps() { return 1e-6; }   // CONEEPS  Real.hpp:25
 };
 template <> struct MathB<float> {
-  __device__ static float exp_(float x) { return expf(x); }
+  // inside the wavelength loops: ex2.approx / rcp.approx based (2 ulp + |x| 6e-8 on exp, 2 ulp on the quotient),
+  // against the 1e-4 bar of the float build; everything that decides an index or a weight keeps IEEE operations
+  __device__ static float exp_(float x) { return __expf(x); }
   __device__ static float div_(float a, float b) { return a / b; }
-  __device__ static float divq_(float a, float b) { return a / b; }
+  __device__ static float divq_(float a, float b) { return __fdividef(a, b); }
   __device__ static float divc_(float a, float b, float) { return a / b; }
   __device__ static float rcp_(float b) { return 1.0f / b; }
   // std::log(float) of the host libm is (nearly) correctly rounded; CUDA logf is not (1 ulp), and one ulp of
   // logf(r) moves the radial interpolation weight by ~3e-5.  Rounding the double log gives the host's result.
-  __device__ static float log_(float x) { return (float) log((double) x); }
+  __device__ static float log_(float x) { return (float) fm::log_pos((double) x); }
   // atmo_point::xyz calls the unqualified (double) hypot / acos even when Real = float
   // (atmo_vec.cpp:53-54) and rounds on assignment: do the same
-  __device__ static float hypot2_(float a, float b, float c) { return (float) hypot(hypot((double) a, (double) b), (double) c); }
-  __device__ static float acos_(float x) { return (float) acos((double) x); }
+  // (the double intermediates are formed with the trimmed routines of the double path, good to <= 1e-13: after the
+  // rounding to float they are the libm values in all but ~1e-6 of the cases, against a 1e-4 tolerance)
+  __device__ static float hypot2_(float a, float b, float c) {
+    const double r2 = fma((double) a, (double) a, fma((double) b, (double) b, (double) c * (double) c));
+    return (float) (r2 * fm::rsqrt_pos(r2));
+  }
+  __device__ static float acos_(float x) { return (float) fm::acos_fast(fmin(fmax((double) x, -1.0), 1.0)); }
   template <class TT> __device__ static float sza_weight(float t, const TT &T, int slo) { return (t - T.ps[slo]) / (T.ps[slo + 1] - T.ps[slo]); }
   __device__ static float eps() { return 1e-3f; }       // Real.hpp:14
   __device__ static float coneeps() { return 1e-2f; }   // Real.hpp:16
@@ -112,6 +124,14 @@ __device__ __forceinline__ double log1p_series(double u) {
   p = fma(p, z2, 1.0 / 3.0);
   p = fma(p, z2, 1.0);
   return 2.0 * z * p;
+}
+// log(x) for normal positive x: exponent split + the series on the mantissa in [0.75, 1.5), error < 1e-12
+__device__ __forceinline__ double log_pos(double x) {
+  int hi = __double2hiint(x);
+  int e = ((hi >> 20) & 0x7ff) - 1023;
+  double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
+  if (m > 1.5) { m *= 0.5; e += 1; }
+  return fma((double) e, 0.69314718055994530942, log1p_series(m - 1.0));
 }
 } // namespace fm
 
