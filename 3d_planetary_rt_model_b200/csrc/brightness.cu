@@ -245,11 +245,12 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
     // ---- apply the four sub-steps in order.  The broadcasts and the wavelength sum are full-warp shuffles executed by
     // every lane (a group past the end of its line of sight moves garbage it never uses): with the 4-lane member masks
     // the compiler wrapped every shuffle group in MATCH / REDUX / VOTE mask checks (~5 % of the issued instructions)
-    const int nvalid = have ? min(LPR, total - j0) : 0;
     const unsigned FULL = 0xffffffffu;
 #pragma unroll
     for (int q = 0; q < LPR; q++) {
-      const bool act = q < nvalid;
+      // a sub-step past the end of the line of sight has my_s == 0 and all-zero records on its lane (set above), so every
+      // increment below is exactly 0: the body needs no branch, and the scheduler can overlap the tail of one sub-step
+      // (shuffle reduction, clamp) with the wavelength loop of the next.  The shuffles stay unconditional (full mask).
       const Real s = shfl_real<Real>(FULL, my_s, lead + q);
 #pragma unroll
       for (int e = 0; e < NEM; e++) {
@@ -260,31 +261,26 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
         const Real Sv = shfl_real<Real>(FULL, my_in[e][4], lead + q);
         // singlet_CFR::update_tracker_start<false> + update_tracker_brightness
         const Real tau_species_voxel = dts * s;
+        acc_col[e] += dens * s;
+        acc_tsp[e] += tau_species_voxel;
+        acc_tab[e] += dta * s;
+        Real phi[NLL];
+        LineShape<Real>::eval(lsp, sub, phi);
         Real T_int = 0;
-        if (act) {
-          acc_col[e] += dens * s;
-          acc_tsp[e] += tau_species_voxel;
-          acc_tab[e] += dta * s;
-          const Real common = dts * s;
-          Real phi[NLL];
-          LineShape<Real>::eval(lsp, sub, phi);
 #pragma unroll
-          for (int m = 0; m < NLL; m++) {
-            const Real lineshape = phi[m];
-            const Real tau = (dta + dts * lineshape) * s;
-            const Real tp = MathB<Real>::exp_(-tau);
-            const Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::divq_(Real(1.0) - tp, tau);
-            T_int = fma(c * wgt[m], lineshape * P[e][m], T_int);    // x common once, after the wavelength loop
-            P[e][m] *= tp;
-          }
-          T_int *= common;
+        for (int m = 0; m < NLL; m++) {
+          const Real lineshape = phi[m];
+          const Real tau = (dta + dts * lineshape) * s;
+          const Real tp = MathB<Real>::exp_(-tau);
+          const Real c = ((double) tau < 1e-3) ? (Real(1.0) - Real(0.5) * tau) : MathB<Real>::divq_(Real(1.0) - tp, tau);
+          T_int = fma(c * wgt[m], lineshape * P[e][m], T_int);    // x dts * s once, after the wavelength loop
+          P[e][m] *= tp;
         }
+        T_int *= tau_species_voxel;
         T_int += __shfl_xor_sync(FULL, T_int, 1);
         T_int += __shfl_xor_sync(FULL, T_int, 2);
-        if (act) {
-          if (T_int > tau_species_voxel) T_int = tau_species_voxel;
-          acc_B[e] += Sv * gfac[e] * T_int;
-        }
+        if (T_int > tau_species_voxel) T_int = tau_species_voxel;
+        acc_B[e] += Sv * gfac[e] * T_int;
       }
     }
     j0 += LPR;
