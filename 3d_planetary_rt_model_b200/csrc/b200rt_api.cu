@@ -13,7 +13,11 @@ using namespace b200rt;
 
 namespace {
 
-constexpr size_t SCRATCH_BUDGET_BYTES = size_t(1) << 31;   // boundary-list scratch per batch (2 GiB of 180 GB)
+// Boundary-list scratch per batch: 8 GiB of the 180 GB, so that the bench workload (2.24e6 voxel rays, 1e6 lines of
+// sight on the 100x60 grid: 7.0 and 3.1 GB of lists) runs as ONE batch per phase.  Every batch boundary drains the
+// persistent brightness kernel (a single line of sight takes ~0.5 ms): measured 1.45 ms per boundary (r01n launch
+// list: 686k LOS in 29.63 ms, 314k in 14.35 ms).  B200RT_SCRATCH_BYTES overrides it (tests force several batches).
+constexpr size_t SCRATCH_BUDGET_BYTES = size_t(1) << 33;
 
 struct PhaseTimer {
   b200rt_ctx *c;
@@ -90,7 +94,9 @@ int ensure_lists(b200rt_ctx *c, long long n_rays, ListView<Real> *lv) {
 
 long long batch_capacity(b200rt_ctx *c, size_t real_bytes) {
   const size_t per_ray = (size_t) c->hg.cap * (real_bytes + sizeof(int)) + 2 * sizeof(int);
-  long long n = (long long) (SCRATCH_BUDGET_BYTES / per_ray);
+  size_t budget = SCRATCH_BUDGET_BYTES;
+  if (const char *env = getenv("B200RT_SCRATCH_BYTES")) budget = (size_t) std::max(1LL, atoll(env));
+  long long n = (long long) (budget / per_ray);
   return std::max<long long>(n, 1);
 }
 
@@ -263,10 +269,29 @@ int solve_impl(b200rt_ctx *c, bool reset_timer) {
 }
 
 // ------------------------------------------------------------------ brightness
+// With `io` (double builds only) the lines of sight come from, and the results go to, HOST arrays.  When the set needs
+// several batches (more lists than the scratch budget holds) they are pipelined -- batch b+1's nine input slices travel
+// on copy_stream and batch b-1's result slices on out_stream while batch b is traversed and marched on the compute
+// stream -- so that only the first upload and the last download are exposed (b200rt_brightness; with pageable host
+// memory the copies degrade to staged ones, still correct).  Batches are NOT made smaller to get more overlap: a
+// forced 4-way split of the 1e6-LOS bench set cost more in kernel tails (+3 ms) than the hidden copies saved (2 ms).
+struct HostLos {
+  int n;
+  const double *const *src;   // [9]
+  double *const *dst;         // [4], entries may be null
+};
+
 template <class Real>
-int brightness_impl(b200rt_ctx *c, int n_subsamples) {
+int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr) {
   if (n_subsamples == 1 || n_subsamples < 0)
     return fail(c, B200RT_ERR_ARG, "n_subsamples must be 0 or > 1 (RT_grid.hpp:237)");
+  if (io) {
+    B200RT_CUDA(c, c->los_in.ensure((size_t) 9 * io->n * sizeof(Real)));
+    c->n_los = io->n;
+    c->los_done = false;
+    if (!c->copy_stream) B200RT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->out_stream) B200RT_CUDA(c, cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
+  }
   if (c->n_los <= 0) return fail(c, B200RT_ERR_STATE, "no lines of sight uploaded");
   if (c->hg.pp)
     return fail(c, B200RT_ERR_STATE, "interp_weights not implemented in grid_plane_parallel (grid_plane_parallel.hpp:304-311)");
@@ -282,6 +307,29 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
   if (int rc = ensure_lists<Real>(c, per_batch, &lv)) return rc;
   B200RT_CUDA(c, c->los_out.ensure((size_t) c->n_em * 4 * n * sizeof(Real)));
   const Real *li = c->los_in.as<Real>();
+  std::vector<cudaEvent_t> io_events;
+  struct EventGuard {
+    std::vector<cudaEvent_t> &v;
+    ~EventGuard() { for (auto e : v) cudaEventDestroy(e); }
+  } io_guard{io_events};
+  auto io_event = [&](cudaStream_t on, cudaEvent_t *out) -> cudaError_t {   // event recorded on `on`; destroyed at return
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (rc != cudaSuccess) return rc;
+    io_events.push_back(e);
+    if (out) *out = e;
+    return cudaEventRecord(e, on);
+  };
+  cudaEvent_t uploaded = nullptr;                                           // completion of the latest upload_batch
+  auto upload_batch = [&](long long first) -> cudaError_t {
+    const long long count = std::min(per_batch, n - first);
+    for (int a = 0; a < 9; a++) {
+      cudaError_t rc = cudaMemcpyAsync(c->los_in.as<double>() + (size_t) a * n + first, io->src[a] + first,
+                                       (size_t) count * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream);
+      if (rc != cudaSuccess) return rc;
+    }
+    return io_event(c->copy_stream, &uploaded);
+  };
   EmissionView<Real> ev[MAX_EMISSIONS];
   for (int e = 0; e < c->n_em; e++) {
     ev[e] = em_view<Real>(c, e);
@@ -297,6 +345,10 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
     RayList<Real> rl;
     rl.r = li + 3 * n + first; rl.z = li + 2 * n + first; rl.t = li + 4 * n + first;
     rl.cost = li + 8 * n + first; rl.lz = li + 7 * n + first; rl.i_voxel = nullptr;
+    if (io) {
+      if (first == 0) B200RT_CUDA(c, upload_batch(0));
+      B200RT_CUDA(c, cudaStreamWaitEvent(c->stream, uploaded, 0));   // this batch's slices have arrived
+    }
     {
       PhaseTimer t(c, PH_TRAVERSE);
       B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, count, lv, overflow, c->stream));
@@ -309,10 +361,26 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples) {
                                              c->step_counter.as<unsigned long long>(), c->stream));
       t.stop(1);
     }
+    if (io) {
+      cudaEvent_t done;
+      B200RT_CUDA(c, io_event(c->stream, &done));
+      // order matters for pageable host memory, whose copies block the host: the kernels of this batch are queued
+      // first, the next batch's upload runs beside them, and only then does the download wait for them
+      if (first + count < n) B200RT_CUDA(c, upload_batch(first + count));
+      B200RT_CUDA(c, cudaStreamWaitEvent(c->out_stream, done, 0));
+      for (int e = 0; e < c->n_em; e++)
+        for (int q = 0; q < 4; q++)
+          if (io->dst[q])
+            B200RT_CUDA(c, cudaMemcpyAsync(io->dst[q] + (size_t) e * n + first,
+                                           c->los_out.as<double>() + ((size_t) e * 4 + q) * n + first,
+                                           (size_t) count * sizeof(double), cudaMemcpyDeviceToHost, c->out_stream));
+    }
   }
   unsigned long long substeps = 0;
   B200RT_CUDA(c, cudaMemcpyAsync(&substeps, c->step_counter.p, sizeof(substeps), cudaMemcpyDeviceToHost, c->stream));
-  if (int rc = check_overflow(c)) return rc;
+  const int rc_overflow = check_overflow(c);
+  if (io) B200RT_CUDA(c, cudaStreamSynchronize(c->out_stream));   // nothing is in flight into the caller's arrays at return
+  if (rc_overflow) return rc_overflow;
   PhaseTimer::collect(c);
   c->last_substeps = (long long) substeps;
   c->los_done = true;
@@ -732,6 +800,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   for (cudaEvent_t ev : c->lu_events) cudaEventDestroy(ev);
   if (c->lu_graph) cudaGraphExecDestroy(c->lu_graph);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->out_stream) cudaStreamDestroy(c->out_stream);
   if (c->ev_rows) cudaEventDestroy(c->ev_rows);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
@@ -1108,6 +1177,15 @@ int b200rt_los_download(b200rt_ctx *c, double *B, double *tsp, double *tab, doub
 int b200rt_brightness(b200rt_ctx *c, int n, const double *x, const double *y, const double *z, const double *r,
                       const double *t, const double *lx, const double *ly, const double *lz, const double *cost,
                       int n_subsamples, double *B, double *tsp, double *tab, double *col) {
+  if (c && is64(c) && !c->mult.defined && n > 0 && c->have_grid && c->n_em >= 1) {
+    // double singlet model: upload, kernels and download pipelined batch by batch
+    const double *src[9] = {x, y, z, r, t, lx, ly, lz, cost};
+    for (auto p : src) if (!p) return fail(c, B200RT_ERR_ARG, "null line-of-sight array");
+    double *dst[4] = {B, tsp, tab, col};
+    cudaSetDevice(c->device);
+    HostLos io{n, src, dst};
+    return brightness_impl<double>(c, n_subsamples, &io);
+  }
   int rc = b200rt_los_upload(c, n, x, y, z, r, t, lx, ly, lz, cost);
   if (rc) return rc;
   rc = b200rt_brightness_resident(c, n_subsamples);

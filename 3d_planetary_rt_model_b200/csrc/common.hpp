@@ -204,6 +204,7 @@ struct b200rt_ctx {
   b200rt::DevBuf vox_map;                    // source voxels of an interleaved shard, ascending
   void *row_sink[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t out_stream = nullptr;     // device -> host results of the pipelined host-buffer brightness
   cudaEvent_t ev_rows = nullptr;
   int row_push_batches = 4;                  // a rank's row range is marched in at least this many batches when a sink is set
 

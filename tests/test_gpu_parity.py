@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): voxel traversal and intersection indices bit-exa
 influence matrix, source function and brightness within 1e-6 relative (double Real) and
 1e-4 (float Real).  Run on the B200 box: python -m pytest tests -m gpu
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -118,6 +120,33 @@ def test_interleaved_shards_equal_full(synth, binding):
     assert G2.ctx.last_step_count() == 0
     with pytest.raises(binding.B200RTError):
         G2.ctx.influence_ranges([(5, 9), (7, 12)])         # overlapping ranges are refused
+
+
+def test_pipelined_host_brightness_equals_resident(synth, binding):
+    """b200rt_brightness with host arrays runs as a pipeline of batches (upload / kernels / download on three streams,
+    b200rt_api.cu brightness_impl); it must return exactly what upload -> brightness_resident -> download returns,
+    for a line-of-sight count that spans several batches with a ragged last one, and with a null output skipped"""
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=2)
+    G = binding.GpuModel(scn, "f64")
+    for e in range(2):
+        G.set_sourcefn(e, np.linspace(1.0, 0.05, scn.n_vox) * (1 + e))
+    locs, dirs = synth.random_los(70001, seed=5)
+    los = G.ctx.los_from_MSO(locs, dirs)
+    os.environ["B200RT_SCRATCH_BYTES"] = str(8 << 20)               # a few thousand lines of sight per batch
+    try:
+        a = G.ctx.brightness(los, 6)
+    finally:
+        del os.environ["B200RT_SCRATCH_BYTES"]
+    assert G.ctx.kernel_ms(binding.PH_BRIGHTNESS)[1] >= 4           # several batches were launched
+    G.ctx.los_upload(los)
+    G.ctx.brightness_resident(6)
+    b = G.ctx.los_download()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    # the lines of sight stay resident after the host-buffer call
+    G.ctx.brightness_resident(6)
+    c = G.ctx.los_download()
+    assert np.array_equal(a["brightness"], c["brightness"])
 
 
 def test_edge_cases(synth, binding, oraclebind):
