@@ -306,6 +306,7 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
   ListView<Real> lv;
   if (int rc = ensure_lists<Real>(c, per_batch, &lv)) return rc;
   B200RT_CUDA(c, c->los_out.ensure((size_t) c->n_em * 4 * n * sizeof(Real)));
+  B200RT_CUDA(c, c->los_order.ensure(((size_t) per_batch + 2 * (size_t) (c->hg.cap + 1)) * sizeof(int)));
   const Real *li = c->los_in.as<Real>();
   std::vector<cudaEvent_t> io_events;
   struct EventGuard {
@@ -356,10 +357,16 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
     }
     {
       PhaseTimer t(c, PH_BRIGHTNESS);
+      const int *order = nullptr;
+      if (lv.cap <= LOS_ORDER_MAX_CAP && count >= 4096) {    // small sets finish in one wave: nothing to balance
+        int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
+        B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
+        order = ord;
+      }
       B200RT_CUDA(c, launch_brightness<Real>(g, ev, c->n_em, li, n, first, count, lv, n_subsamples,
                                              c->los_out.as<Real>(), n, c->work_counter.as<int>(),
-                                             c->step_counter.as<unsigned long long>(), c->stream));
-      t.stop(1);
+                                             c->step_counter.as<unsigned long long>(), order, c->stream));
+      t.stop(order ? 4 : 1);     // histogram, prefix, scatter + the march
     }
     if (io) {
       cudaEvent_t done;
@@ -782,7 +789,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->grid_tables, &c->sun_rays, &c->list_dist, &c->list_ent, &c->list_len, &c->list_flag,
-                    &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->lu, &c->lu_dinv, &c->lu_flag,
+                    &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->los_order, &c->lu, &c->lu_dinv, &c->lu_flag,
                     &c->iph.dev, &c->iph.io};
   for (DevBuf *b : bufs) b->release();
   for (int e = 0; e < MAX_EMISSIONS; e++) {

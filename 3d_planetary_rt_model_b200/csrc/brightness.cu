@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128, (NEM == 2 && sizeof(Real) == 8) ? 3 : 4)
 brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> em1,
                   const Real *__restrict__ los_in, long long los_stride, long long first, long long count,
                   ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total,
-                  int *queue, unsigned long long *substep_counter) {
+                  int *queue, unsigned long long *substep_counter, const int *__restrict__ order) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GeomTables<Real> T;
   T.load(smem_raw, g);            // axes of the grid + the reciprocal tables of the double path; ends with a barrier
@@ -174,6 +174,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       if (sub == 0) t = atomicAdd(queue, 1);
       t = __shfl_sync(gmask, t, lead);
       if (t >= count) { exhausted = true; break; }
+      if (order) t = order[t];      // longest lines of sight first: the queue drains with short ones (launch_los_order)
       los = first + t;
       const int len = lists.len[t];
       if (len <= 0) {     // misses the grid: tracker reset values
@@ -306,6 +307,62 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
   }
 }
 
+
+// ---- longest-first order of a batch of lines of sight.  The brightness kernel is persistent (groups pull lines of
+// sight from a queue) and one long line of sight takes ~0.5 ms, so in input order the last ~1.5 ms of a launch run on a
+// draining machine; with the long ones first the queue ends on short ones.  Counting sort on the list length:
+// (1) histogram, (2) descending exclusive prefix, (3) scatter with block-aggregated reservations.
+constexpr int ORDER_THREADS = 256, ORDER_ITEMS = 16;
+
+__global__ void __launch_bounds__(ORDER_THREADS)
+los_hist_kernel(const int *__restrict__ len, long long count, int cap, int *__restrict__ hist) {
+  extern __shared__ int sh_hist[];
+  for (int b = threadIdx.x; b <= cap; b += ORDER_THREADS) sh_hist[b] = 0;
+  __syncthreads();
+  const long long base = (long long) blockIdx.x * ORDER_THREADS * ORDER_ITEMS;
+  for (int k = 0; k < ORDER_ITEMS; k++) {
+    const long long i = base + (long long) k * ORDER_THREADS + threadIdx.x;
+    if (i < count) atomicAdd(&sh_hist[min(max(len[i], 0), cap)], 1);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= cap; b += ORDER_THREADS)
+    if (sh_hist[b]) atomicAdd(&hist[b], sh_hist[b]);
+}
+
+__global__ void los_prefix_kernel(const int *__restrict__ hist, int cap, int *__restrict__ offset) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int run = 0;
+    for (int b = cap; b >= 0; b--) { offset[b] = run; run += hist[b]; }
+  }
+}
+
+__global__ void __launch_bounds__(ORDER_THREADS)
+los_scatter_kernel(const int *__restrict__ len, long long count, int cap, int *__restrict__ offset,
+                   int *__restrict__ order) {
+  extern __shared__ int sh[];
+  int *sh_hist = sh, *sh_base = sh + (cap + 1);
+  for (int b = threadIdx.x; b <= cap; b += ORDER_THREADS) sh_hist[b] = 0;
+  __syncthreads();
+  const long long base = (long long) blockIdx.x * ORDER_THREADS * ORDER_ITEMS;
+  int bin[ORDER_ITEMS], rank[ORDER_ITEMS];
+#pragma unroll
+  for (int k = 0; k < ORDER_ITEMS; k++) {
+    const long long i = base + (long long) k * ORDER_THREADS + threadIdx.x;
+    bin[k] = -1;
+    if (i < count) {
+      bin[k] = min(max(len[i], 0), cap);
+      rank[k] = atomicAdd(&sh_hist[bin[k]], 1);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b <= cap; b += ORDER_THREADS)
+    if (sh_hist[b]) sh_base[b] = atomicAdd(&offset[b], sh_hist[b]);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < ORDER_ITEMS; k++)
+    if (bin[k] >= 0) order[sh_base[bin[k]] + rank[k]] = (int) (base + (long long) k * ORDER_THREADS + threadIdx.x);
+}
+
 } // namespace
 
 template <class Real>
@@ -322,7 +379,7 @@ template <class Real>
 cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em, const Real *los_in,
                               long long los_stride, long long first, long long count, ListView<Real> lists,
                               int n_subsamples, Real *out, long long n_los_total, int *queue,
-                              unsigned long long *substep_counter, cudaStream_t s) {
+                              unsigned long long *substep_counter, const int *order, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
@@ -336,21 +393,37 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
     e = cudaFuncSetAttribute(brightness_kernel<Real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     brightness_kernel<Real, 1><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[0], los_in, los_stride, first, count,
-                                                                        lists, n_subsamples, out, n_los_total, queue, substep_counter);
+                                                                        lists, n_subsamples, out, n_los_total, queue, substep_counter, order);
   } else {
     e = cudaFuncSetAttribute(brightness_kernel<Real, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     brightness_kernel<Real, 2><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[1], los_in, los_stride, first, count,
-                                                                        lists, n_subsamples, out, n_los_total, queue, substep_counter);
+                                                                        lists, n_subsamples, out, n_los_total, queue, substep_counter, order);
   }
   return cudaGetLastError();
 }
 template cudaError_t launch_brightness<double>(const GridView<double> &, const EmissionView<double> *, int,
                                                const double *, long long, long long, long long, ListView<double>, int,
-                                               double *, long long, int *, unsigned long long *, cudaStream_t);
+                                               double *, long long, int *, unsigned long long *, const int *, cudaStream_t);
 template cudaError_t launch_brightness<float>(const GridView<float> &, const EmissionView<float> *, int, const float *,
                                               long long, long long, long long, ListView<float>, int, float *,
-                                              long long, int *, unsigned long long *, cudaStream_t);
+                                              long long, int *, unsigned long long *, const int *, cudaStream_t);
+cudaError_t launch_los_order(const int *len, long long count, int cap, int *bins, int *order, cudaStream_t s) {
+  if (count <= 0) return cudaSuccess;
+  if (cap > LOS_ORDER_MAX_CAP || count > 0x7fffffffLL) return cudaErrorInvalidValue;
+  int *hist = bins, *offset = bins + (cap + 1);
+  cudaError_t e = cudaMemsetAsync(hist, 0, (size_t) (cap + 1) * sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  const long long per_block = (long long) ORDER_THREADS * ORDER_ITEMS;
+  const unsigned blocks = (unsigned) ((count + per_block - 1) / per_block);
+  los_hist_kernel<<<blocks, ORDER_THREADS, (size_t) (cap + 1) * sizeof(int), s>>>(len, count, cap, hist);
+  los_prefix_kernel<<<1, 32, 0, s>>>(hist, cap, offset);
+  e = cudaFuncSetAttribute(los_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (2 * (cap + 1) * sizeof(int)));
+  if (e != cudaSuccess) return e;
+  los_scatter_kernel<<<blocks, ORDER_THREADS, (size_t) 2 * (cap + 1) * sizeof(int), s>>>(len, count, cap, offset, order);
+  return cudaGetLastError();
+}
+
 template cudaError_t launch_pack_records<double>(const EmissionView<double> &, int, double *, double *, cudaStream_t);
 template cudaError_t launch_pack_records<float>(const EmissionView<float> &, int, float *, float *, cudaStream_t);
 

@@ -189,6 +189,7 @@ struct b200rt_ctx {
   int n_los = 0;
   b200rt::DevBuf los_in;            // 9 * n_los Real: x y z r t lx ly lz cost
   b200rt::DevBuf los_out;           // n_em * 4 * n_los Real
+  b200rt::DevBuf los_order;         // per batch: processing order of the lines of sight (longest first) + its bins
   bool los_done = false;
 
   // dense solve workspace
@@ -270,7 +271,12 @@ template <class Real>
 cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em,
                               const Real *los_in, long long los_stride, long long first,
                               long long count, ListView<Real> lists, int n_subsamples, Real *out,
-                              long long n_los_total, int *queue, unsigned long long *substep_counter, cudaStream_t s);
+                              long long n_los_total, int *queue, unsigned long long *substep_counter,
+                              const int *order, cudaStream_t s);
+// longest-first processing order of the `count` lists (counting sort of their lengths): bins = 2 * (cap + 1) ints of
+// scratch, order = count ints.  Returns cudaErrorInvalidValue when cap is too large for the shared-memory histogram.
+cudaError_t launch_los_order(const int *len, long long count, int cap, int *bins, int *order, cudaStream_t s);
+constexpr int LOS_ORDER_MAX_CAP = 8000;
 template <class Real>
 cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *rec_pt, Real *rec_avg, cudaStream_t s);
 

@@ -137,7 +137,7 @@ def test_pipelined_host_brightness_equals_resident(synth, binding):
         a = G.ctx.brightness(los, 6)
     finally:
         del os.environ["B200RT_SCRATCH_BYTES"]
-    assert G.ctx.kernel_ms(binding.PH_BRIGHTNESS)[1] >= 4           # several batches were launched
+    assert G.ctx.kernel_ms(binding.PH_BRIGHTNESS)[1] >= 13          # several batches (order kernels + march each)
     G.ctx.los_upload(los)
     G.ctx.brightness_resident(6)
     b = G.ctx.los_download()
