@@ -92,6 +92,14 @@ int ensure_lists(b200rt_ctx *c, long long n_rays, ListView<Real> *lv) {
   return B200RT_OK;
 }
 
+// The longest-first order only pays when the queue is several times deeper than the machine (148 SMs x 4 CTAs x 32
+// 4-lane groups = 18944 lines of sight in flight): below that every group gets at most a few lines of sight and the
+// order only concentrates the long ones in the first CTAs.  B200RT_LOS_ORDER_MIN overrides (tests, diagnosis).
+long long los_order_min() {
+  if (const char *env = getenv("B200RT_LOS_ORDER_MIN")) return atoll(env);
+  return 4LL * NUM_SMS * 4 * 32;
+}
+
 long long batch_capacity(b200rt_ctx *c, size_t real_bytes) {
   const size_t per_ray = (size_t) c->hg.cap * (real_bytes + sizeof(int)) + 2 * sizeof(int);
   size_t budget = SCRATCH_BUDGET_BYTES;
@@ -321,15 +329,23 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
     if (out) *out = e;
     return cudaEventRecord(e, on);
   };
-  cudaEvent_t uploaded = nullptr;                                           // completion of the latest upload_batch
+  // the traversal reads r, z, t, cos(theta), line_z (arrays 3, 2, 4, 8, 7); x, y, line_x, line_y are only read by the
+  // march, so they travel while the batch is being traversed
+  cudaEvent_t uploaded_trav = nullptr, uploaded_all = nullptr;              // of the latest upload_batch
   auto upload_batch = [&](long long first) -> cudaError_t {
     const long long count = std::min(per_batch, n - first);
-    for (int a = 0; a < 9; a++) {
+    static const int order_of_arrays[9] = {3, 2, 4, 8, 7, 0, 1, 5, 6};
+    for (int k = 0; k < 9; k++) {
+      const int a = order_of_arrays[k];
       cudaError_t rc = cudaMemcpyAsync(c->los_in.as<double>() + (size_t) a * n + first, io->src[a] + first,
                                        (size_t) count * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream);
       if (rc != cudaSuccess) return rc;
+      if (k == 4) {
+        rc = io_event(c->copy_stream, &uploaded_trav);
+        if (rc != cudaSuccess) return rc;
+      }
     }
-    return io_event(c->copy_stream, &uploaded);
+    return io_event(c->copy_stream, &uploaded_all);
   };
   EmissionView<Real> ev[MAX_EMISSIONS];
   for (int e = 0; e < c->n_em; e++) {
@@ -348,17 +364,18 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
     rl.cost = li + 8 * n + first; rl.lz = li + 7 * n + first; rl.i_voxel = nullptr;
     if (io) {
       if (first == 0) B200RT_CUDA(c, upload_batch(0));
-      B200RT_CUDA(c, cudaStreamWaitEvent(c->stream, uploaded, 0));   // this batch's slices have arrived
+      B200RT_CUDA(c, cudaStreamWaitEvent(c->stream, uploaded_trav, 0));   // this batch's traversal slices have arrived
     }
     {
       PhaseTimer t(c, PH_TRAVERSE);
       B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, count, lv, overflow, c->stream));
       t.stop(1);
     }
+    if (io) B200RT_CUDA(c, cudaStreamWaitEvent(c->stream, uploaded_all, 0));
     {
       PhaseTimer t(c, PH_BRIGHTNESS);
       const int *order = nullptr;
-      if (lv.cap <= LOS_ORDER_MAX_CAP && count >= 4096) {    // small sets finish in one wave: nothing to balance
+      if (lv.cap <= LOS_ORDER_MAX_CAP && count >= los_order_min()) {
         int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
         B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
         order = ord;
@@ -697,6 +714,7 @@ int mult_brightness_impl(b200rt_ctx *c, int n_subsamples) {
   if (int rc = ensure_lists<Real>(c, per_batch, &lv)) return rc;
   const size_t n_out = 3 * d.n_lines + d.n_lower;
   B200RT_CUDA(c, c->los_out.ensure(n_out * n * sizeof(Real)));
+  B200RT_CUDA(c, c->los_order.ensure(((size_t) per_batch + 2 * (size_t) (c->hg.cap + 1)) * sizeof(int)));
   const Real *li = c->los_in.as<Real>();
   MultView<Real> mv = mult_view<Real>(c);
   if (M.rec_dirty) {
@@ -716,9 +734,15 @@ int mult_brightness_impl(b200rt_ctx *c, int n_subsamples) {
     }
     {
       PhaseTimer t(c, PH_BRIGHTNESS);
+      const int *order = nullptr;
+      if (lv.cap <= LOS_ORDER_MAX_CAP && count >= los_order_min()) {
+        int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
+        B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
+        order = ord;
+      }
       B200RT_CUDA(c, launch_mult_brightness<Real>(d, g, mv, li, n, first, count, lv, n_subsamples, c->los_out.as<Real>(), n,
-                                                  c->work_counter.as<int>(), c->stream));
-      t.stop(1);
+                                                  c->work_counter.as<int>(), order, c->stream));
+      t.stop(order ? 4 : 1);
     }
   }
   if (int rc = check_overflow(c)) return rc;

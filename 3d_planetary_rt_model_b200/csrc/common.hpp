@@ -300,7 +300,7 @@ template <class Real>
 cudaError_t launch_mult_brightness(const b200rt_multiplet_desc &d, const GridView<Real> &g, MultView<Real> mv,
                                    const Real *los_in, long long los_stride, long long first, long long count,
                                    ListView<Real> lists, int n_subsamples, Real *out, long long n_los_total, int *queue,
-                                   cudaStream_t s);
+                                   const int *order, cudaStream_t s);
 // ---- grid_host.cpp: tracker constants of the reference (O_1026_tracker.hpp, H_multiplet_tracker*.hpp) in Real
 template <class Real>
 int multiplet_desc_init(int kind, b200rt_multiplet_desc *d);

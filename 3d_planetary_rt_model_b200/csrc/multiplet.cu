@@ -284,7 +284,7 @@ template <class Real, class TR>
 __global__ void __launch_bounds__(128)
 mult_brightness_kernel(GridView<Real> g, MultView<Real> mv, MultParams<Real> P_, const Real *__restrict__ los_in,
                        long long los_stride, long long first, long long count, ListView<Real> lists, int n_subsamples,
-                       Real *__restrict__ out, long long n_los_total, int *queue) {
+                       Real *__restrict__ out, long long n_los_total, int *queue, const int *__restrict__ order) {
   constexpr int NL = TR::NL, NM = TR::NM, NLOW = TR::NLOW, NUP = TR::NUP, NLP = Dim<TR>::NLP;
   constexpr int NQ = 2 + NLOW + NUP;     // record entries in use
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -318,6 +318,7 @@ mult_brightness_kernel(GridView<Real> g, MultView<Real> mv, MultParams<Real> P_,
       if (sub == 0) t = atomicAdd(queue, 1);
       t = __shfl_sync(gmask, t, lead);
       if (t >= count) { exhausted = true; break; }
+      if (order) t = order[t];      // longest lines of sight first (launch_los_order, brightness.cu)
       los = first + t;
       const int len = lists.len[t];
       if (len <= 0) {     // misses the grid: tracker reset values
@@ -571,7 +572,7 @@ template <class Real>
 cudaError_t launch_mult_brightness(const b200rt_multiplet_desc &d, const GridView<Real> &g, MultView<Real> mv,
                                    const Real *los_in, long long los_stride, long long first, long long count,
                                    ListView<Real> lists, int n_subsamples, Real *out, long long n_los_total, int *queue,
-                                   cudaStream_t s) {
+                                   const int *order, cudaStream_t s) {
   if (count <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
@@ -584,7 +585,7 @@ cudaError_t launch_mult_brightness(const b200rt_multiplet_desc &d, const GridVie
     e = cudaFuncSetAttribute(mult_brightness_kernel<Real, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     mult_brightness_kernel<Real, TR><<<(unsigned) blocks, threads, smem, s>>>(g, mv, P, los_in, los_stride, first, count, lists,
-                                                                               n_subsamples, out, n_los_total, queue);
+                                                                               n_subsamples, out, n_los_total, queue, order);
   });
   return cudaGetLastError();
 }
@@ -600,7 +601,7 @@ cudaError_t launch_mult_brightness(const b200rt_multiplet_desc &d, const GridVie
                                                            double *, int *, cudaStream_t);                                  \
   template cudaError_t launch_mult_brightness<Real>(const b200rt_multiplet_desc &, const GridView<Real> &, MultView<Real>,  \
                                                     const Real *, long long, long long, long long, ListView<Real>, int,     \
-                                                    Real *, long long, int *, cudaStream_t);
+                                                    Real *, long long, int *, const int *, cudaStream_t);
 INST(double)
 INST(float)
 

@@ -132,14 +132,16 @@ def test_pipelined_host_brightness_equals_resident(synth, binding):
         G.set_sourcefn(e, np.linspace(1.0, 0.05, scn.n_vox) * (1 + e))
     locs, dirs = synth.random_los(70001, seed=5)
     los = G.ctx.los_from_MSO(locs, dirs)
-    os.environ["B200RT_SCRATCH_BYTES"] = str(8 << 20)               # a few thousand lines of sight per batch
+    os.environ["B200RT_SCRATCH_BYTES"] = str(8 << 20)               # ~2e4 lines of sight per batch
+    os.environ["B200RT_LOS_ORDER_MIN"] = "1000"                     # ... each processed longest-first
     try:
         a = G.ctx.brightness(los, 6)
     finally:
-        del os.environ["B200RT_SCRATCH_BYTES"]
+        del os.environ["B200RT_SCRATCH_BYTES"], os.environ["B200RT_LOS_ORDER_MIN"]
     assert G.ctx.kernel_ms(binding.PH_BRIGHTNESS)[1] >= 13          # several batches (order kernels + march each)
     G.ctx.los_upload(los)
-    G.ctx.brightness_resident(6)
+    G.ctx.brightness_resident(6)                                    # one batch, input order (70001 < the order threshold)
+    assert G.ctx.kernel_ms(binding.PH_BRIGHTNESS)[1] == 1
     b = G.ctx.los_download()
     for k in a:
         assert np.array_equal(a[k], b[k]), k
