@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libb200rt.so")
 
 F64, F32 = 0, 1
 ROW_MAJOR, COL_MAJOR = 0, 1
-PH_TRAVERSE, PH_INFLUENCE, PH_SOLVE, PH_BRIGHTNESS, PH_IPH = 0, 1, 2, 3, 4
+PH_TRAVERSE, PH_INFLUENCE, PH_SOLVE, PH_BRIGHTNESS, PH_IPH, PH_ORDER = 0, 1, 2, 3, 4, 5
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -29,6 +29,8 @@ SIGNATURES = {
     "b200rt_destroy": (C.c_int, [_vp]),
     "b200rt_last_error": (C.c_char_p, [_vp]),
     "b200rt_device_count": (C.c_int, []),
+    "b200rt_create_multi": (C.c_int, [C.c_int, _vp, C.c_int, C.POINTER(_vp)]),
+    "b200rt_group_size": (C.c_int, [_vp]),
     "b200rt_set_grid_sph": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int] + [_dp] * 7),
     "b200rt_make_grid_sph": (C.c_int, [C.c_int] * 5 + [_dp, C.c_int, C.c_int] + [_dp] * 6),
     "b200rt_set_grid_pp": (C.c_int, [_vp, C.c_int, C.c_int] + [_dp] * 4),
@@ -117,15 +119,23 @@ def _ptr(a):
 
 
 class Context:
-    """One b200rt_ctx (one GPU).  Method names follow the reference's RT_grid where one exists."""
+    """One b200rt_ctx: one GPU (device=...) or several GPUs of this process behind one handle (devices=[...] or
+    devices="all": b200rt_create_multi).  Method names follow the reference's RT_grid where one exists."""
 
-    def __init__(self, device: int = 0, precision: int = F64):
+    def __init__(self, device: int = 0, precision: int = F64, devices=None):
         self.lib = load()
         self.h = _vp()
-        rc = self.lib.b200rt_create(device, precision, C.byref(self.h))
+        if devices is None:
+            rc = self.lib.b200rt_create(device, precision, C.byref(self.h))
+        elif isinstance(devices, str):     # "all"
+            rc = self.lib.b200rt_create_multi(0, None, precision, C.byref(self.h))
+        else:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.b200rt_create_multi(len(devices), C.cast(ids, _vp), precision, C.byref(self.h))
         if rc != 0:
-            raise B200RTError(f"b200rt_create(device={device}) failed with status {rc}: no usable CUDA device "
-                              "(this library has no CPU path)")
+            raise B200RTError(f"b200rt_create(device={device}, devices={devices}) failed with status {rc}: no usable "
+                              "CUDA device (this library has no CPU path)")
+        self.n_devices = self.lib.b200rt_group_size(self.h)
         self.precision = precision
         self.n_vox = 0
         self.n_em = 0
@@ -415,10 +425,10 @@ class GpuModel:
     """Scenario-level convenience: one synthetic Scenario (synth.py) on one GPU, with the
     method vocabulary the parity tests use (grid / traverse / build_rows / solve / brightness)."""
 
-    def __init__(self, scn, precision="f64", device=0):
+    def __init__(self, scn, precision="f64", device=0, devices=None):
         self.scn = scn
         self.prec = F64 if precision == "f64" else F32
-        self.ctx = Context(device, self.prec)
+        self.ctx = Context(device, self.prec, devices=devices)
         if getattr(scn, "pp", False):
             self.g = self.ctx.make_grid_pp(scn.n_rb, scn.n_theta, scn.rb)
             self.ctx.set_grid_pp(self.g)
@@ -496,10 +506,10 @@ def define_multiplet_tables(scn, precision=F64):
 class GpuMultiplet:
     """One MultipletScenario (synth.py) on one GPU, with the vocabulary of oracle/multbind.py."""
 
-    def __init__(self, scn, precision="f64", device=0):
+    def __init__(self, scn, precision="f64", device=0, devices=None):
         self.scn = scn
         self.prec = F64 if precision == "f64" else F32
-        self.ctx = Context(device, self.prec)
+        self.ctx = Context(device, self.prec, devices=devices)
         self.g = self.ctx.make_grid(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.rb, scn.szamethod, scn.raymethod)
         self.ctx.set_grid(self.g)
         self.desc = self.ctx.multiplet_desc(scn.kind, scn.solar)

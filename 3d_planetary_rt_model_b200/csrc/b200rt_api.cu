@@ -11,6 +11,9 @@
 
 using namespace b200rt;
 
+// a context made by b200rt_create_multi owns no device state itself: every call fans out to its members (device_group.cu)
+#define GROUP_DISPATCH(c, call) do { if ((c)->group) return call; } while (0)
+
 namespace {
 
 // Boundary-list scratch per batch: 8 GiB of the 180 GB, so that the bench workload (2.24e6 voxel rays, 1e6 lines of
@@ -23,14 +26,20 @@ struct PhaseTimer {
   b200rt_ctx *c;
   int phase;
   cudaEvent_t a, b;
+  bool stopped = false;
   PhaseTimer(b200rt_ctx *ctx, int ph) : c(ctx), phase(ph) {
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     cudaEventRecord(a, c->stream);
   }
+  PhaseTimer(const PhaseTimer &) = delete;
+  ~PhaseTimer() {   // an error path returned before stop(): the events are not handed to pending()
+    if (!stopped) { cudaEventDestroy(a); cudaEventDestroy(b); }
+  }
   void stop(int launches) {
     cudaEventRecord(b, c->stream);
     pending().push_back({phase, launches, a, b});
+    stopped = true;
   }
   struct Rec { int phase, launches; cudaEvent_t a, b; };
   static std::vector<Rec> &pending() { static thread_local std::vector<Rec> v; return v; }
@@ -169,7 +178,11 @@ int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges
   const long long cap_rays = batch_capacity(c, sizeof(Real));
   int vox_per_batch = (int) std::max<long long>(1, std::min<long long>(cap_rays / g.n_rays, std::max(n_rows, 1)));
   bool pushing = false;
-  for (int e = 0; e < c->n_em; e++) pushing = pushing || c->row_sink[e] != nullptr;
+  for (int e = 0; e < c->n_em; e++) {
+    if (c->row_sink[e] && c->row_sink_n_vox[e] != n_vox)
+      return fail(c, B200RT_ERR_STATE, "row sink was named for a different grid (b200rt_set_row_sink after the grid is set)");
+    pushing = pushing || c->row_sink[e] != nullptr;
+  }
   if (pushing && n_rows > 0) {     // several batches, so that the DMA of one overlaps the march of the next
     if (const char *env = getenv("B200RT_ROW_PUSH_BATCHES")) c->row_push_batches = std::max(1, atoi(env));
     vox_per_batch = std::max(1, std::min(vox_per_batch, (n_rows + c->row_push_batches - 1) / c->row_push_batches));
@@ -245,8 +258,9 @@ int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges
   }
   unsigned long long steps = 0;
   B200RT_CUDA(c, cudaMemcpyAsync(&steps, c->step_counter.p, sizeof(steps), cudaMemcpyDeviceToHost, c->stream));
-  if (int rc = check_overflow(c)) return rc;   // synchronises
+  const int rc_overflow = check_overflow(c);   // synchronises
   if (pushing) B200RT_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the rows have landed on the solving GPU
+  if (rc_overflow) return rc_overflow;
   PhaseTimer::collect(c);
   c->last_steps = (long long) steps;
   for (int e = 0; e < c->n_em; e++) { c->em[e].have_K = true; c->em[e].have_S = false; }
@@ -287,6 +301,8 @@ struct HostLos {
   int n;
   const double *const *src;   // [9]
   double *const *dst;         // [4], entries may be null
+  long long out_stride;       // the caller's result arrays are [n_emissions][out_stride]; this call fills
+  long long out_offset;       // [out_offset, out_offset + n) of each row (a device group hands every member a slice)
 };
 
 template <class Real>
@@ -372,18 +388,20 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
       t.stop(1);
     }
     if (io) B200RT_CUDA(c, cudaStreamWaitEvent(c->stream, uploaded_all, 0));
+    const int *order = nullptr;
+    if (lv.cap <= LOS_ORDER_MAX_CAP && count >= los_order_min()) {
+      PhaseTimer t(c, PH_ORDER);   // histogram, prefix, scatter: timed and counted apart from the march they feed
+      int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
+      B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
+      order = ord;
+      t.stop(3);
+    }
     {
       PhaseTimer t(c, PH_BRIGHTNESS);
-      const int *order = nullptr;
-      if (lv.cap <= LOS_ORDER_MAX_CAP && count >= los_order_min()) {
-        int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
-        B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
-        order = ord;
-      }
       B200RT_CUDA(c, launch_brightness<Real>(g, ev, c->n_em, li, n, first, count, lv, n_subsamples,
                                              c->los_out.as<Real>(), n, c->work_counter.as<int>(),
                                              c->step_counter.as<unsigned long long>(), order, c->stream));
-      t.stop(order ? 4 : 1);     // histogram, prefix, scatter + the march
+      t.stop(1);
     }
     if (io) {
       cudaEvent_t done;
@@ -395,7 +413,7 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
       for (int e = 0; e < c->n_em; e++)
         for (int q = 0; q < 4; q++)
           if (io->dst[q])
-            B200RT_CUDA(c, cudaMemcpyAsync(io->dst[q] + (size_t) e * n + first,
+            B200RT_CUDA(c, cudaMemcpyAsync(io->dst[q] + (size_t) e * io->out_stride + io->out_offset + first,
                                            c->los_out.as<double>() + ((size_t) e * 4 + q) * n + first,
                                            (size_t) count * sizeof(double), cudaMemcpyDeviceToHost, c->out_stream));
     }
@@ -429,7 +447,7 @@ int los_upload_impl(b200rt_ctx *c, int n, const double *const src[9]) {
 }
 
 template <class Real>
-int los_download_impl(b200rt_ctx *c, double *const dst[4]) {
+int los_download_impl(b200rt_ctx *c, double *const dst[4], long long stride, long long offset) {
   const long long n = c->n_los;
   const Real *o = c->los_out.as<Real>();
   DevBuf stage;
@@ -437,7 +455,7 @@ int los_download_impl(b200rt_ctx *c, double *const dst[4]) {
     for (int q = 0; q < 4; q++) {
       if (!dst[q]) continue;
       const Real *src = o + ((size_t) e * 4 + q) * n;
-      double *out = dst[q] + (size_t) e * n;
+      double *out = dst[q] + (size_t) e * stride + offset;
       if (sizeof(Real) == sizeof(double)) {
         B200RT_CUDA(c, cudaMemcpyAsync(out, src, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       } else {
@@ -732,17 +750,19 @@ int mult_brightness_impl(b200rt_ctx *c, int n_subsamples) {
       B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, count, lv, overflow, c->stream));
       t.stop(1);
     }
+    const int *order = nullptr;
+    if (lv.cap <= LOS_ORDER_MAX_CAP && count >= los_order_min()) {
+      PhaseTimer t(c, PH_ORDER);
+      int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
+      B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
+      order = ord;
+      t.stop(3);
+    }
     {
       PhaseTimer t(c, PH_BRIGHTNESS);
-      const int *order = nullptr;
-      if (lv.cap <= LOS_ORDER_MAX_CAP && count >= los_order_min()) {
-        int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
-        B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
-        order = ord;
-      }
       B200RT_CUDA(c, launch_mult_brightness<Real>(d, g, mv, li, n, first, count, lv, n_subsamples, c->los_out.as<Real>(), n,
                                                   c->work_counter.as<int>(), order, c->stream));
-      t.stop(order ? 4 : 1);
+      t.stop(1);
     }
   }
   if (int rc = check_overflow(c)) return rc;
@@ -754,31 +774,65 @@ int mult_brightness_impl(b200rt_ctx *c, int n_subsamples) {
 // multiplet outputs [3 n_lines + n_lower][n_los] -> brightness, tau_species_final, tau_absorber_final [n_lines][n],
 // species_col_dens [n_lower][n]
 template <class Real>
-int mult_los_download_impl(b200rt_ctx *c, double *const dst[4]) {
+int mult_los_download_impl(b200rt_ctx *c, double *const dst[4], long long stride, long long offset) {
   const long long n = c->n_los;
   const b200rt_multiplet_desc &d = c->mult.d;
   const Real *o = c->los_out.as<Real>();
   const int rows[4] = {d.n_lines, d.n_lines, d.n_lines, d.n_lower};
-  size_t off = 0;
+  size_t row0 = 0;
+  std::vector<float> tmp;
   for (int q = 0; q < 4; q++) {
-    const size_t cnt = (size_t) rows[q] * n;
-    if (dst[q]) {
-      if (sizeof(Real) == sizeof(double)) {
-        B200RT_CUDA(c, cudaMemcpyAsync(dst[q], o + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      } else {
-        std::vector<float> tmp(cnt);
-        B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), o + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (size_t i = 0; i < cnt; i++) dst[q][i] = tmp[i];
+    if (dst[q])
+      for (int r = 0; r < rows[q]; r++) {
+        const Real *src = o + (row0 + r) * (size_t) n;
+        double *out = dst[q] + (size_t) r * stride + offset;
+        if (sizeof(Real) == sizeof(double)) {
+          B200RT_CUDA(c, cudaMemcpyAsync(out, src, (size_t) n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        } else {
+          tmp.resize(n);
+          B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), src, (size_t) n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+          B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+          for (long long i = 0; i < n; i++) out[i] = tmp[i];
+        }
       }
-    }
-    off += cnt;
+    row0 += rows[q];
   }
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
   return B200RT_OK;
 }
 
 } // namespace
+
+// ---- the two calls a device group hands its members with a slice of the caller's arrays (device_group.cu)
+namespace b200rt {
+
+int los_download_slice(b200rt_ctx *c, double *const dst[4], long long stride, long long offset) {
+  if (!c) return B200RT_ERR_ARG;
+  if (!c->los_done) return fail(c, B200RT_ERR_STATE, "no brightness result to download");
+  cudaSetDevice(c->device);
+  if (c->mult.defined)
+    return is64(c) ? mult_los_download_impl<double>(c, dst, stride, offset) : mult_los_download_impl<float>(c, dst, stride, offset);
+  return is64(c) ? los_download_impl<double>(c, dst, stride, offset) : los_download_impl<float>(c, dst, stride, offset);
+}
+
+int brightness_slice(b200rt_ctx *c, int n, const double *const src[9], int n_subsamples, double *const dst[4],
+                     long long stride, long long offset) {
+  if (!c) return B200RT_ERR_ARG;
+  if (is64(c) && !c->mult.defined && n > 0 && c->have_grid && c->n_em >= 1) {
+    // double singlet model: upload, kernels and download pipelined batch by batch
+    for (int a = 0; a < 9; a++) if (!src[a]) return fail(c, B200RT_ERR_ARG, "null line-of-sight array");
+    cudaSetDevice(c->device);
+    HostLos io{n, src, dst, stride, offset};
+    return brightness_impl<double>(c, n_subsamples, &io);
+  }
+  int rc = b200rt_los_upload(c, n, src[0], src[1], src[2], src[3], src[4], src[5], src[6], src[7], src[8]);
+  if (rc) return rc;
+  rc = b200rt_brightness_resident(c, n_subsamples);
+  if (rc) return rc;
+  return los_download_slice(c, dst, stride, offset);
+}
+
+} // namespace b200rt
 
 // ====================================================================== C ABI
 extern "C" {
@@ -810,11 +864,12 @@ int b200rt_create(int device, int precision, b200rt_ctx **out) {
 
 int b200rt_destroy(b200rt_ctx *c) {
   if (!c) return B200RT_OK;
+  if (c->group) return group_destroy(c);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->grid_tables, &c->sun_rays, &c->list_dist, &c->list_ent, &c->list_len, &c->list_flag,
                     &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->los_order, &c->lu, &c->lu_dinv, &c->lu_flag,
-                    &c->iph.dev, &c->iph.io};
+                    &c->iph.dev, &c->iph.io, &c->vox_map};
   for (DevBuf *b : bufs) b->release();
   for (int e = 0; e < MAX_EMISSIONS; e++) {
     Emission &E = c->em[e];
@@ -843,6 +898,7 @@ const char *b200rt_last_error(const b200rt_ctx *c) { return c ? c->err.c_str() :
 
 int b200rt_synchronize(b200rt_ctx *c) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_synchronize(c));
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
   return B200RT_OK;
 }
@@ -860,6 +916,7 @@ int b200rt_set_grid_sph(b200rt_ctx *c, int n_rb, int n_sb, int n_rays, const dou
                         const double *pts_r, const double *pts_s, const double *ray_t, const double *ray_p,
                         const double *ray_domega) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_set_grid_sph(c, n_rb, n_sb, n_rays, rb, sb, pts_r, pts_s, ray_t, ray_p, ray_domega));
   if (n_rb < 2 || n_sb < 3 || n_rays < 1 || !rb || !sb || !pts_r || !pts_s || !ray_t || !ray_p || !ray_domega)
     return fail(c, B200RT_ERR_ARG, "b200rt_set_grid_sph: bad argument");
   cudaSetDevice(c->device);
@@ -874,6 +931,7 @@ int b200rt_set_grid_sph(b200rt_ctx *c, int n_rb, int n_sb, int n_rays, const dou
   if (rc) return rc;
   c->have_grid = true;
   c->n_em = 0;
+  for (int e = 0; e < 2; e++) { c->row_sink[e] = nullptr; c->row_sink_n_vox[e] = 0; }   // named for the old geometry
   for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
   c->mult.defined = c->mult.have_K = c->mult.have_S = false;
   return B200RT_OK;
@@ -890,6 +948,7 @@ int b200rt_make_grid_pp(int precision, int n_rb, int n_theta, const double *rb, 
 int b200rt_set_grid_pp(b200rt_ctx *c, int n_rb, int n_rays, const double *rb, const double *pts_r,
                        const double *ray_t, const double *ray_domega) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_set_grid_pp(c, n_rb, n_rays, rb, pts_r, ray_t, ray_domega));
   if (n_rb < 2 || n_rays < 1 || !rb || !pts_r || !ray_t || !ray_domega)
     return fail(c, B200RT_ERR_ARG, "b200rt_set_grid_pp: bad argument");
   cudaSetDevice(c->device);
@@ -906,6 +965,7 @@ int b200rt_set_grid_pp(b200rt_ctx *c, int n_rb, int n_rays, const double *rb, co
   if (rc) return rc;
   c->have_grid = true;
   c->n_em = 0;
+  for (int e = 0; e < 2; e++) { c->row_sink[e] = nullptr; c->row_sink_n_vox[e] = 0; }   // named for the old geometry
   for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
   c->mult.defined = c->mult.have_K = c->mult.have_S = false;
   return B200RT_OK;
@@ -916,6 +976,7 @@ int b200rt_set_singlet(b200rt_ctx *c, int e, int n_em, double branching, double 
                        const double *dtau_absorber, const double *T_ratio_pt, const double *density_pt,
                        const double *dtau_species_pt, const double *dtau_absorber_pt) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_set_singlet(c, e, n_em, branching, T_ref, sigma_ref, g, T_ratio, density, dtau_species, dtau_absorber, T_ratio_pt, density_pt, dtau_species_pt, dtau_absorber_pt));
   if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "set the grid before the emissions");
   if (n_em < 1 || n_em > MAX_EMISSIONS || e < 0 || e >= n_em) return fail(c, B200RT_ERR_ARG, "bad emission index");
   const double *arr[8] = {T_ratio, density, dtau_species, dtau_absorber, T_ratio_pt, density_pt, dtau_species_pt, dtau_absorber_pt};
@@ -940,6 +1001,7 @@ int b200rt_set_multiplet(b200rt_ctx *c, const b200rt_multiplet_desc *d, const do
                          const double *species_density_pt, const double *species_T, const double *species_T_pt,
                          const double *absorber_density, const double *absorber_density_pt) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_set_multiplet(c, d, species_density, species_density_pt, species_T, species_T_pt, absorber_density, absorber_density_pt));
   if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "set the grid before the emissions");
   const double *arr[6] = {species_density, species_density_pt, species_T, species_T_pt, absorber_density, absorber_density_pt};
   for (auto p : arr) if (!p) return fail(c, B200RT_ERR_ARG, "null emission table");
@@ -947,6 +1009,7 @@ int b200rt_set_multiplet(b200rt_ctx *c, const b200rt_multiplet_desc *d, const do
     return fail(c, B200RT_ERR_ARG, "multiplet descriptor does not match the line / level tables of its kind");
   cudaSetDevice(c->device);
   c->n_em = 0;
+  for (int e = 0; e < 2; e++) { c->row_sink[e] = nullptr; c->row_sink_n_vox[e] = 0; }
   for (int e = 0; e < MAX_EMISSIONS; e++) { c->em[e].defined = c->em[e].have_K = c->em[e].have_S = false; }
   Multiplet &M = c->mult;
   M.d = *d;
@@ -959,12 +1022,14 @@ int b200rt_set_multiplet(b200rt_ctx *c, const b200rt_multiplet_desc *d, const do
 
 int b200rt_set_g_factor(b200rt_ctx *c, int e, double g) {
   if (!c || e < 0 || e >= MAX_EMISSIONS) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_set_g_factor(c, e, g));
   c->em[e].g_factor = g;
   return B200RT_OK;
 }
 
 int b200rt_influence(b200rt_ctx *c, int v_begin, int v_end) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_influence(c, 1, &v_begin, &v_end));
   if (!c->have_grid || (c->n_em < 1 && !c->mult.defined)) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
   if (v_begin < 0 || v_end > c->hg.n_vox || v_begin > v_end) return fail(c, B200RT_ERR_ARG, "bad voxel range");
   cudaSetDevice(c->device);
@@ -975,6 +1040,7 @@ int b200rt_influence(b200rt_ctx *c, int v_begin, int v_end) {
 
 int b200rt_influence_ranges(b200rt_ctx *c, int n_ranges, const int *v_begin, const int *v_end) {
   if (!c || n_ranges < 0 || (n_ranges > 0 && (!v_begin || !v_end))) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_influence(c, n_ranges, v_begin, v_end));
   if (!c->have_grid || c->n_em < 1) return fail(c, B200RT_ERR_STATE, "grid / singlet emissions not set");
   if (c->mult.defined) return fail(c, B200RT_ERR_STATE, "b200rt_influence_ranges: singlet emissions only");
   std::vector<std::pair<int, int>> r;
@@ -991,6 +1057,7 @@ int b200rt_influence_ranges(b200rt_ctx *c, int n_ranges, const int *v_begin, con
 
 int b200rt_solve(b200rt_ctx *c) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_solve(c));
   cudaSetDevice(c->device);
   if (c->mult.defined) return mult_solve_impl(c, true);
   return solve_impl(c, true);
@@ -998,6 +1065,7 @@ int b200rt_solve(b200rt_ctx *c) {
 
 int b200rt_generate_S(b200rt_ctx *c) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_generate_S(c));
   int rc = b200rt_influence(c, 0, c->hg.n_vox);
   if (rc) return rc;
   if (c->mult.defined) return mult_solve_impl(c, false);
@@ -1006,18 +1074,21 @@ int b200rt_generate_S(b200rt_ctx *c) {
 
 int b200rt_last_step_count(b200rt_ctx *c, long long *n) {
   if (!c || !n) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_counts(c, 0, n));
   *n = c->last_steps;
   return B200RT_OK;
 }
 
 int b200rt_last_substep_count(b200rt_ctx *c, long long *n) {
   if (!c || !n) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_counts(c, 1, n));
   *n = c->last_substeps;
   return B200RT_OK;
 }
 
 int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp, double *tab) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_get_solution(group_primary(c), e, S, S0, tsp, tab)));
   if (c->mult.defined) {
     if (e != 0) return B200RT_ERR_ARG;
     cudaSetDevice(c->device);
@@ -1052,6 +1123,7 @@ int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp
 
 int b200rt_get_influence(b200rt_ctx *c, int e, int layout, double *K) {
   if (!c || !K) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_get_influence(group_primary(c), e, layout, K)));
   const bool mm = c->mult.defined;
   if (mm ? e != 0 : (e < 0 || e >= c->n_em)) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
@@ -1072,6 +1144,7 @@ int b200rt_get_influence(b200rt_ctx *c, int e, int layout, double *K) {
 
 int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
   if (!c || !S) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_set_sourcefn(c, e, S));
   if (c->mult.defined) {
     if (e != 0) return B200RT_ERR_ARG;
     cudaSetDevice(c->device);
@@ -1101,6 +1174,7 @@ int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
 
 int b200rt_last_residual(b200rt_ctx *c, int e, double *r) {
   if (!c || !r) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_last_residual(group_primary(c), e, r)));
   if (c->mult.defined) { *r = c->mult.residual; return e == 0 ? B200RT_OK : B200RT_ERR_ARG; }
   if (e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
   *r = c->em[e].residual;
@@ -1109,6 +1183,7 @@ int b200rt_last_residual(b200rt_ctx *c, int e, double *r) {
 
 int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, void **tab) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_influence_dev(group_primary(c), e, K, S0, tsp, tab)));
   if (c->mult.defined) {
     if (e != 0) return B200RT_ERR_ARG;
     Multiplet &M = c->mult;
@@ -1133,6 +1208,7 @@ int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, 
 // ---- peer-memory row exchange (one process per GPU): the solving rank exports its K, the others open it and
 // name it as the sink of their row batches
 int b200rt_ipc_export_influence(b200rt_ctx *c, int e, void *handle64) {
+  if (c && c->group) return group_forward(c, b200rt_ipc_export_influence(group_primary(c), e, handle64));
   if (!c || !handle64 || e < 0 || e >= c->n_em || c->mult.defined) return B200RT_ERR_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   cudaSetDevice(c->device);
@@ -1144,6 +1220,7 @@ int b200rt_ipc_export_influence(b200rt_ctx *c, int e, void *handle64) {
 }
 int b200rt_ipc_open(b200rt_ctx *c, const void *handle64, void **peer_ptr) {
   if (!c || !handle64 || !peer_ptr) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_ipc_open(group_primary(c), handle64, peer_ptr)));
   cudaSetDevice(c->device);
   cudaIpcMemHandle_t h;
   std::memcpy(&h, handle64, sizeof h);
@@ -1152,6 +1229,7 @@ int b200rt_ipc_open(b200rt_ctx *c, const void *handle64, void **peer_ptr) {
 }
 int b200rt_ipc_close(b200rt_ctx *c, void *peer_ptr) {
   if (!c || !peer_ptr) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_ipc_close(group_primary(c), peer_ptr)));
   cudaSetDevice(c->device);
   for (auto &sk : c->row_sink) if (sk == peer_ptr) sk = nullptr;
   B200RT_CUDA(c, cudaIpcCloseMemHandle(peer_ptr));
@@ -1159,11 +1237,18 @@ int b200rt_ipc_close(b200rt_ctx *c, void *peer_ptr) {
 }
 int b200rt_set_row_sink(b200rt_ctx *c, int e, void *peer_K_dev) {
   if (!c || e < 0 || e >= 2) return B200RT_ERR_ARG;
+  if (c->group) return fail(c, B200RT_ERR_STATE, "b200rt_set_row_sink: a device group wires its own row sinks");
+  if (peer_K_dev) {
+    if (c->mult.defined) return fail(c, B200RT_ERR_STATE, "b200rt_set_row_sink: singlet emissions only");
+    if (!c->have_grid || e >= c->n_em) return fail(c, B200RT_ERR_STATE, "b200rt_set_row_sink: set the grid and the emissions first");
+  }
   c->row_sink[e] = peer_K_dev;
+  c->row_sink_n_vox[e] = peer_K_dev ? c->hg.n_vox : 0;
   return B200RT_OK;
 }
 
 int b200rt_sourcefn_dev(b200rt_ctx *c, int e, void **S) {
+  if (c && c->group) return group_forward(c, b200rt_sourcefn_dev(group_primary(c), e, S));
   if (c && S && c->mult.defined && e == 0) { *S = c->mult.S.p; return B200RT_OK; }
   if (!c || e < 0 || e >= c->n_em || !S) return B200RT_ERR_ARG;
   *S = c->em[e].S.p;
@@ -1181,6 +1266,7 @@ int b200rt_los_from_MSO(int precision, int n, const double *loc, const double *d
 int b200rt_los_upload(b200rt_ctx *c, int n, const double *x, const double *y, const double *z, const double *r,
                       const double *t, const double *lx, const double *ly, const double *lz, const double *cost) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_los_upload(c, n, x, y, z, r, t, lx, ly, lz, cost));
   if (n <= 0) return fail(c, B200RT_ERR_ARG, "there must be at least one observation to simulate");
   const double *src[9] = {x, y, z, r, t, lx, ly, lz, cost};
   for (auto p : src) if (!p) return fail(c, B200RT_ERR_ARG, "null line-of-sight array");
@@ -1190,6 +1276,7 @@ int b200rt_los_upload(b200rt_ctx *c, int n, const double *x, const double *y, co
 
 int b200rt_brightness_resident(b200rt_ctx *c, int n_subsamples) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_brightness_resident(c, n_subsamples));
   if (!c->have_grid || (c->n_em < 1 && !c->mult.defined)) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
   cudaSetDevice(c->device);
   if (c->mult.defined) return is64(c) ? mult_brightness_impl<double>(c, n_subsamples) : mult_brightness_impl<float>(c, n_subsamples);
@@ -1198,35 +1285,25 @@ int b200rt_brightness_resident(b200rt_ctx *c, int n_subsamples) {
 
 int b200rt_los_download(b200rt_ctx *c, double *B, double *tsp, double *tab, double *col) {
   if (!c) return B200RT_ERR_ARG;
-  if (!c->los_done) return fail(c, B200RT_ERR_STATE, "no brightness result to download");
-  cudaSetDevice(c->device);
+  GROUP_DISPATCH(c, group_los_download(c, B, tsp, tab, col));
   double *dst[4] = {B, tsp, tab, col};
-  if (c->mult.defined) return is64(c) ? mult_los_download_impl<double>(c, dst) : mult_los_download_impl<float>(c, dst);
-  return is64(c) ? los_download_impl<double>(c, dst) : los_download_impl<float>(c, dst);
+  return los_download_slice(c, dst, c->n_los, 0);
 }
 
 int b200rt_brightness(b200rt_ctx *c, int n, const double *x, const double *y, const double *z, const double *r,
                       const double *t, const double *lx, const double *ly, const double *lz, const double *cost,
                       int n_subsamples, double *B, double *tsp, double *tab, double *col) {
-  if (c && is64(c) && !c->mult.defined && n > 0 && c->have_grid && c->n_em >= 1) {
-    // double singlet model: upload, kernels and download pipelined batch by batch
-    const double *src[9] = {x, y, z, r, t, lx, ly, lz, cost};
-    for (auto p : src) if (!p) return fail(c, B200RT_ERR_ARG, "null line-of-sight array");
-    double *dst[4] = {B, tsp, tab, col};
-    cudaSetDevice(c->device);
-    HostLos io{n, src, dst};
-    return brightness_impl<double>(c, n_subsamples, &io);
-  }
-  int rc = b200rt_los_upload(c, n, x, y, z, r, t, lx, ly, lz, cost);
-  if (rc) return rc;
-  rc = b200rt_brightness_resident(c, n_subsamples);
-  if (rc) return rc;
-  return b200rt_los_download(c, B, tsp, tab, col);
+  if (!c) return B200RT_ERR_ARG;
+  const double *src[9] = {x, y, z, r, t, lx, ly, lz, cost};
+  double *dst[4] = {B, tsp, tab, col};
+  GROUP_DISPATCH(c, group_brightness(c, n, src, n_subsamples, dst));
+  return brightness_slice(c, n, src, n_subsamples, dst, n, 0);
 }
 
 int b200rt_traverse_voxel_rays(b200rt_ctx *c, int v_begin, int v_end, long long capacity, int *len, int *eb,
                                int *entering, double *distance, long long *n_entries) {
   if (!c || !len || !eb || !entering || !distance) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_traverse_voxel_rays(group_primary(c), v_begin, v_end, capacity, len, eb, entering, distance, n_entries)));
   if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "grid not set");
   if (v_begin < 0 || v_end > c->hg.n_vox || v_begin > v_end) return fail(c, B200RT_ERR_ARG, "bad voxel range");
   cudaSetDevice(c->device);
@@ -1237,6 +1314,7 @@ int b200rt_traverse_voxel_rays(b200rt_ctx *c, int v_begin, int v_end, long long 
 int b200rt_traverse_los(b200rt_ctx *c, long long capacity, int *len, int *eb, int *entering, double *distance,
                         long long *n_entries) {
   if (!c || !len || !eb || !entering || !distance) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_traverse_los(c, capacity, len, eb, entering, distance, n_entries));
   if (!c->have_grid) return fail(c, B200RT_ERR_STATE, "grid not set");
   cudaSetDevice(c->device);
   return is64(c) ? traverse_los_impl<double>(c, capacity, len, eb, entering, distance, n_entries)
@@ -1245,6 +1323,7 @@ int b200rt_traverse_los(b200rt_ctx *c, long long capacity, int *len, int *eb, in
 
 int b200rt_last_kernel_ms(b200rt_ctx *c, int phase, float *ms, int *n_launches) {
   if (!c || phase < 0 || phase >= PH_COUNT) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_kernel_ms(c, phase, ms, n_launches));
   if (ms) *ms = c->phase_ms[phase];
   if (n_launches) *n_launches = c->phase_launches[phase];
   return B200RT_OK;
@@ -1252,6 +1331,7 @@ int b200rt_last_kernel_ms(b200rt_ctx *c, int phase, float *ms, int *n_launches) 
 
 int b200rt_iph_load_table(b200rt_ctx *c, const char *fname) {
   if (!c || !fname) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_iph_load_table(c, fname));
   cudaSetDevice(c->device);
   return iph_load_table(c, fname);
 }
@@ -1259,6 +1339,7 @@ int b200rt_iph_load_table(b200rt_ctx *c, const char *fname) {
 int b200rt_iph_set_table(b200rt_ctx *c, int kmax, int lmax, int ninf, float temp, const float *alt_au, const float *ang,
                          const float *dans, const float *sot, const float *so, const float *sn, const float *dinf_cm3) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_iph_set_table(c, kmax, lmax, ninf, temp, alt_au, ang, dans, sot, so, sn, dinf_cm3));
   cudaSetDevice(c->device);
   return iph_set_table(c, kmax, lmax, ninf, temp, alt_au, ang, dans, sot, so, sn, dinf_cm3);
 }
@@ -1266,6 +1347,7 @@ int b200rt_iph_set_table(b200rt_ctx *c, int kmax, int lmax, int ninf, float temp
 int b200rt_iph_background(b200rt_ctx *c, float fs, float xpos, float ypos, float zpos, int n_los, const float *u,
                           const float *v, const float *w, float *fln, int *n_steps) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_iph_background(c, fs, xpos, ypos, zpos, n_los, u, v, w, fln, n_steps));
   cudaSetDevice(c->device);
   return iph_background(c, fs, xpos, ypos, zpos, n_los, u, v, w, fln, n_steps);
 }
@@ -1273,6 +1355,7 @@ int b200rt_iph_background(b200rt_ctx *c, float fs, float xpos, float ypos, float
 int b200rt_iph_model(b200rt_ctx *c, double g_lya, const double *marspos, int n_los, const double *ra, const double *dec,
                      double *iph_kR) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_iph_model(c, g_lya, marspos, n_los, ra, dec, iph_kR));
   cudaSetDevice(c->device);
   return iph_model(c, g_lya, marspos, n_los, ra, dec, iph_kR);
 }
@@ -1285,6 +1368,7 @@ int b200rt_iph_extinction(int n, const double *iph, const double *tau_abs, doubl
 
 int b200rt_measure_fp64_peaks(b200rt_ctx *c, double *dfma, double *dmma) {
   if (!c) return B200RT_ERR_ARG;
+  GROUP_DISPATCH(c, group_forward(c, b200rt_measure_fp64_peaks(group_primary(c), dfma, dmma)));
   cudaSetDevice(c->device);
   return measure_fp64_peaks(c, dfma, dmma);
 }

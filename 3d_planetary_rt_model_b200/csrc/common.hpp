@@ -146,7 +146,7 @@ struct Multiplet {
   DevBuf S_real, rec_pt, rec_avg;
 };
 
-enum Phase { PH_TRAVERSE = 0, PH_INFLUENCE = 1, PH_SOLVE = 2, PH_BRIGHTNESS = 3, PH_IPH = 4, PH_COUNT = 5 };
+enum Phase { PH_TRAVERSE = 0, PH_INFLUENCE = 1, PH_SOLVE = 2, PH_BRIGHTNESS = 3, PH_IPH = 4, PH_ORDER = 5, PH_COUNT = 6 };
 
 // Quemerais IPH model: tables and the constants of BACKGROUND (ipbackgroundCFR_fun.f:176-235), iph.cu
 struct IphTable {
@@ -160,7 +160,11 @@ struct IphTable {
 
 } // namespace b200rt
 
+namespace b200rt { struct Group; }
+
 struct b200rt_ctx {
+  b200rt::Group *group = nullptr;   // set only on the handle b200rt_create_multi returns: it owns no device state, every
+                                    // call fans out to the member contexts (one per device), device_group.cu
   int device = 0;
   int precision = B200RT_F64;
   cudaStream_t stream = nullptr;
@@ -204,6 +208,7 @@ struct b200rt_ctx {
   // NVLink by the copy engines while the next batch is marched
   b200rt::DevBuf vox_map;                    // source voxels of an interleaved shard, ascending
   void *row_sink[2] = {nullptr, nullptr};
+  int row_sink_n_vox[2] = {0, 0};            // the geometry a sink was named for: a re-grid clears it, a mismatch is an error
   cudaStream_t copy_stream = nullptr;
   cudaStream_t out_stream = nullptr;     // device -> host results of the pipelined host-buffer brightness
   cudaEvent_t ev_rows = nullptr;
@@ -211,8 +216,8 @@ struct b200rt_ctx {
 
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  float phase_ms[b200rt::PH_COUNT] = {0, 0, 0, 0, 0};
-  int phase_launches[b200rt::PH_COUNT] = {0, 0, 0, 0, 0};
+  float phase_ms[b200rt::PH_COUNT] = {0, 0, 0, 0, 0, 0};
+  int phase_launches[b200rt::PH_COUNT] = {0, 0, 0, 0, 0, 0};
 
   b200rt::IphTable iph;
 };
@@ -313,6 +318,47 @@ int iph_background(b200rt_ctx *c, float fs, float xpos, float ypos, float zpos, 
                    const float *v1, const float *w1, float *fln, int *n_steps);
 int iph_model(b200rt_ctx *c, double g_lya, const double *marspos, int n_los, const double *ra, const double *dec,
               double *iph_kR);
+
+// ---- b200rt_api.cu: the two calls a device group hands its members with a slice of the caller's arrays
+int los_download_slice(b200rt_ctx *c, double *const dst[4], long long stride, long long offset);
+int brightness_slice(b200rt_ctx *c, int n, const double *const src[9], int n_subsamples, double *const dst[4],
+                     long long stride, long long offset);
+
+// ---- device_group.cu: one handle, several devices of one process (b200rt_create_multi)
+b200rt_ctx *group_primary(b200rt_ctx *g);
+int group_forward(b200rt_ctx *g, int rc);      // rc of a call on the primary member; copies its error text on failure
+int group_destroy(b200rt_ctx *g);
+int group_synchronize(b200rt_ctx *g);
+int group_set_grid_sph(b200rt_ctx *g, int n_rb, int n_sb, int n_rays, const double *rb, const double *sb, const double *pts_r,
+                       const double *pts_s, const double *ray_t, const double *ray_p, const double *ray_domega);
+int group_set_grid_pp(b200rt_ctx *g, int n_rb, int n_rays, const double *rb, const double *pts_r, const double *ray_t,
+                      const double *ray_domega);
+int group_set_singlet(b200rt_ctx *g, int e, int n_em, double branching, double T_ref, double sigma_ref, double gf,
+                      const double *a0, const double *a1, const double *a2, const double *a3, const double *a4,
+                      const double *a5, const double *a6, const double *a7);
+int group_set_multiplet(b200rt_ctx *g, const b200rt_multiplet_desc *d, const double *a0, const double *a1, const double *a2,
+                        const double *a3, const double *a4, const double *a5);
+int group_set_g_factor(b200rt_ctx *g, int e, double gf);
+int group_influence(b200rt_ctx *g, int n_ranges, const int *v_begin, const int *v_end);
+int group_solve(b200rt_ctx *g);
+int group_generate_S(b200rt_ctx *g);
+int group_counts(b200rt_ctx *g, int which, long long *n);
+int group_set_sourcefn(b200rt_ctx *g, int e, const double *S);
+int group_los_upload(b200rt_ctx *g, int n, const double *x, const double *y, const double *z, const double *r, const double *t,
+                     const double *lx, const double *ly, const double *lz, const double *cost);
+int group_brightness_resident(b200rt_ctx *g, int n_subsamples);
+int group_los_download(b200rt_ctx *g, double *B, double *tsp, double *tab, double *col);
+int group_brightness(b200rt_ctx *g, int n, const double *const src[9], int n_subsamples, double *const dst[4]);
+int group_traverse_los(b200rt_ctx *g, long long capacity, int *len, int *eb, int *entering, double *distance,
+                       long long *n_entries);
+int group_kernel_ms(b200rt_ctx *g, int phase, float *ms, int *n_launches);
+int group_iph_load_table(b200rt_ctx *g, const char *fname);
+int group_iph_set_table(b200rt_ctx *g, int kmax, int lmax, int ninf, float temp, const float *alt_au, const float *ang,
+                        const float *dans, const float *sot, const float *so, const float *sn, const float *dinf_cm3);
+int group_iph_background(b200rt_ctx *g, float fs, float xpos, float ypos, float zpos, int n_los, const float *u,
+                         const float *v, const float *w, float *fln, int *n_steps);
+int group_iph_model(b200rt_ctx *g, double g_lya, const double *marspos, int n_los, const double *ra, const double *dec,
+                    double *iph_kR);
 
 // ---- peaks.cu
 int measure_fp64_peaks(b200rt_ctx *c, double *dfma_tflops, double *dmma_tflops);

@@ -817,9 +817,17 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   std::vector<double> hm(np);
   B200RT_CUDA(c, cudaMemcpyAsync(hm.data(), margin, np * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200RT_CUDA(c, cudaStreamSynchronize(st));
+  // NaN-safe: std::min / std::max drop a NaN operand, so a non-finite margin is tested for explicitly (a NaN row must
+  // fail the dominance test AND the certificate, never slip through them)
   double min_margin = 1e300;
-  for (int i = 0; i < n; i++) min_margin = std::min(min_margin, hm[i]);
+  bool finite_in = true;
+  for (int i = 0; i < n; i++) {
+    if (!std::isfinite(hm[i])) { finite_in = false; min_margin = -INFINITY; break; }
+    min_margin = std::min(min_margin, hm[i]);
+  }
   if (res) res->min_margin = min_margin;
+  if (!finite_in)
+    return fail(c, B200RT_ERR_NOT_DOMINANT, "I - w*K has non-finite entries (NaN / Inf in the influence matrix or the branching ratio)");
   if (!(min_margin > 0.0)) {
     // Not row dominant as it stands (the multiplet emissions: K[(v0,iu),(v,ju)] carries the ORIGIN voxel's lower-state
     // density, multiplet_CFR_emission.hpp:264-271, so its rows are probabilities only after a diagonal rescaling).
@@ -840,14 +848,20 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       if (it == 0) {
         B200RT_CUDA(c, cudaMemcpyAsync(hm.data(), margin, n * sizeof(double), cudaMemcpyDeviceToHost, st));
         B200RT_CUDA(c, cudaStreamSynchronize(st));
-        for (int i = 0; i < n; i++) kmin = std::min(kmin, hm[i]);
-        if (kmin < 0.0 || branching < 0.0) break;
+        for (int i = 0; i < n; i++) {
+          if (!std::isfinite(hm[i])) { kmin = -INFINITY; break; }
+          kmin = std::min(kmin, hm[i]);
+        }
+        if (!(kmin >= 0.0) || !(branching >= 0.0)) break;
       }
       if ((it & 7) == 7 || it == 0) {
         B200RT_CUDA(c, cudaMemcpyAsync(hy.data(), ya, n * sizeof(double), cudaMemcpyDeviceToHost, st));
         B200RT_CUDA(c, cudaStreamSynchronize(st));
         ymax = 0;
-        for (int i = 0; i < n; i++) ymax = std::max(ymax, hy[i]);
+        for (int i = 0; i < n; i++) {
+          if (!std::isfinite(hy[i])) { ymax = INFINITY; break; }
+          ymax = std::max(ymax, hy[i]);
+        }
         if (ymax < 1.0) certified = true;
         if (!(ymax < 1e200)) break;    // diverging
       }
@@ -897,6 +911,20 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     cudaEventRecord(ev, s);
     marks.push_back({what, KB, ev});
   };
+  // whether a 4-CTA cluster of the Gauss-Jordan kernel can be resident is decided ONCE, outside any stream capture (a
+  // failed launch inside a capture would invalidate it); the one-SM kernel is the form for devices / partitions without
+  static const bool use_cluster = [] {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4); cfg.blockDim = dim3(GJC_THREADS);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n_clusters = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, gj128_cluster_kernel<4>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return n_clusters > 0;
+  }();
   auto chain = [&](int KB, cudaStream_t s) {       // invert the diagonal block, form L21
     const int m1 = nK - KB - 1;
     {   // diagonal-block inverse on a cluster of four SMs (gj128_cluster_kernel); gj128_kernel is the one-SM form
@@ -907,8 +935,8 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       const double *Ac = A;
-      if (cudaLaunchKernelEx(&cfg, gj128_cluster_kernel<4>, Ac, np, KB, dinv) != cudaSuccess)
-        gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
+      if (use_cluster) cudaLaunchKernelEx(&cfg, gj128_cluster_kernel<4>, Ac, np, KB, dinv);
+      else gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
     }
     launches++;
     if (m1 > 0) {
@@ -1017,8 +1045,18 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     for (auto &m : marks) cudaEventDestroy(m.ev);
   }
   double rmax = 0, smax = 0;
-  for (int i = 0; i < n; i++) { rmax = std::max(rmax, hr[i]); smax = std::max(smax, std::fabs(hs0[i])); }
-  if (res) { res->residual = rmax / (smax > 0 ? smax : 1.0); res->launches = launches; }
+  bool finite_out = true;
+  for (int i = 0; i < n; i++) {
+    if (!std::isfinite(hr[i])) finite_out = false;
+    rmax = std::max(rmax, hr[i]);
+    smax = std::max(smax, std::fabs(hs0[i]));
+  }
+  const double rel = finite_out ? rmax / (smax > 0 ? smax : 1.0) : INFINITY;
+  if (res) { res->residual = rel; res->launches = launches; }
+  // a solution whose residual is not small is never reported as success (elimination without exchanges is backward
+  // stable for the matrices the checks above admit: anything else means the input slipped past them)
+  if (!(rel <= 1e-8))
+    return fail(c, B200RT_ERR_NOT_DOMINANT, "solve: relative residual " + std::to_string(rel) + " of (I - w*K) S = S0 is not small");
   return B200RT_OK;
 }
 

@@ -1,5 +1,6 @@
 // observation_fit.cpp -- see observation_fit.hpp
 #include "observation_fit.hpp"
+#include <cstdlib>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -53,9 +54,30 @@ void observation_fit::check(int rc, b200rt_ctx *c) const {
     throw std::runtime_error(string("b200rt status ") + std::to_string(rc) + ": " + (c ? b200rt_last_error(c) : "no context"));
 }
 
+// device >= 0: that GPU.  device < 0 (the default): every visible GPU of this process behind one handle
+// (b200rt_create_multi): generate_source_function splits the influence rows over them and brightness() the lines of
+// sight, exactly the calls the reference's user makes (observation_fit.cpp:122-169,491-516).  B200RT_DEVICES="0,2,3"
+// restricts the set; work too small to pay for the fan-out stays on the first device (include/b200rt.h).
 b200rt_ctx *observation_fit::make_ctx() const {
   b200rt_ctx *c = nullptr;
-  if (b200rt_create(device, B200RT_F64, &c) != B200RT_OK)
+  int rc;
+  if (device >= 0) {
+    rc = b200rt_create(device, B200RT_F64, &c);
+  } else {
+    std::vector<int> ids;
+    if (const char *env = getenv("B200RT_DEVICES")) {
+      const char *p = env;
+      while (*p) {
+        char *end = nullptr;
+        const long v = strtol(p, &end, 10);
+        if (end == p) break;
+        ids.push_back((int) v);
+        p = (*end == ',') ? end + 1 : end;
+      }
+    }
+    rc = b200rt_create_multi((int) ids.size(), ids.empty() ? nullptr : ids.data(), B200RT_F64, &c);
+  }
+  if (rc != B200RT_OK)
     throw std::runtime_error("observation_fit: no usable CUDA device (this library has no CPU path)");
   return c;
 }

@@ -41,7 +41,7 @@ public:
   static const int n_hydrogen_emissions = 2;
   static const int n_voxels = (n_radial_boundaries - 1) * (n_sza_boundaries - 1);
 
-  explicit observation_fit(const std::string iph_sfn_fnamee, int device = 0);
+  explicit observation_fit(const std::string iph_sfn_fnamee, int device = -1);   // -1: every visible GPU (one handle)
   ~observation_fit();
   observation_fit(const observation_fit &) = delete;
   observation_fit &operator=(const observation_fit &) = delete;

@@ -83,7 +83,7 @@ class Pyobservation_fit:
     n_emissions, n_rb, n_sb = 2, 40, 20
     n_vox = (n_rb - 1) * (n_sb - 1)
 
-    def __init__(self, iph_table_fname="", device=0):
+    def __init__(self, iph_table_fname="", device=-1):
         self.lib = load()
         self.h = self.lib.obsfit_create(os.fsencode(iph_table_fname), device)
         if not self.h:

@@ -116,7 +116,7 @@ def run_reference(args):
     scn, locs, dirs = make_workload(synth, args.ref_los)
     R = refbind.RefModel(scn, "f64")
     stride = args.ref_stride
-    threads = R.omp_threads()
+    threads = R.use_all_cores()      # torchrun exports OMP_NUM_THREADS=1: pin the OpenMP arm to every core of the box
     # source function for the brightness sample: single scattering only (no CPU solve of 5841^2)
     times_b, times_l, steps = [], [], 0
     for it in range(args.warmup + args.steps):
@@ -163,7 +163,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200RT_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG is left as the caller set it (the driver counts ranks in NCCL's INFO log); the log goes to stderr so
+        # that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -250,9 +252,11 @@ def run_ours(args):
         ctx.brightness_resident(10)
         t["los_traverse"] = ctx.kernel_ms(binding.PH_TRAVERSE)[0] * 1e-3
         t["brightness"] = ctx.kernel_ms(binding.PH_BRIGHTNESS)[0] * 1e-3
-        t["brightness_launches"] = ctx.kernel_ms(binding.PH_BRIGHTNESS)[1]
+        t["brightness_launches"] = ctx.kernel_ms(binding.PH_BRIGHTNESS)[1]     # the march launches alone
+        t["order"] = ctx.kernel_ms(binding.PH_ORDER)[0] * 1e-3                 # longest-first ordering (3 launches per batch)
         t["substeps"] = ctx.last_substep_count()
-        launches += ctx.kernel_ms(binding.PH_TRAVERSE)[1] + ctx.kernel_ms(binding.PH_BRIGHTNESS)[1]
+        launches += (ctx.kernel_ms(binding.PH_TRAVERSE)[1] + ctx.kernel_ms(binding.PH_BRIGHTNESS)[1] +
+                     ctx.kernel_ms(binding.PH_ORDER)[1])
         ctx.synchronize()
         w4 = time.perf_counter()
         t.update(w_influence=w1 - w0, w_exchange=w2 - w1, w_solve=w3 - w2, w_brightness=w4 - w3, w_total=w4 - w0,
@@ -314,7 +318,7 @@ def run_ours(args):
 
     K = len(recs)
     t_infl = reduce_max(sum(r["traverse"] + r["march"] for r in recs))            # device time, max over ranks
-    t_bright = reduce_max(sum(r["los_traverse"] + r["brightness"] for r in recs))
+    t_bright = reduce_max(sum(r["los_traverse"] + r["order"] + r["brightness"] for r in recs))
     t_solve = reduce_max(sum(r.get("solve", 0.0) for r in recs))
     t_total = reduce_max(sum(r["w_total"] for r in recs))
     t_exch = reduce_max(sum(r["exchange"] for r in recs))
@@ -418,6 +422,7 @@ def run_ours(args):
             from oracle import refbind
             if refbind.available("f64"):
                 R = refbind.RefModel(scn, "f64")
+                R.use_all_cores()
                 tb, ns = R.build_rows(0, n_vox, args.ref_stride)
                 R.set_sourcefn(0, ctx.solution(0)["S"])
                 tl, _ = R.brightness(locs[:args.ref_los], dirs[:args.ref_los], 10)

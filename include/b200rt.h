@@ -46,6 +46,24 @@ int b200rt_create(int device, int precision, b200rt_ctx **ctx);
 int b200rt_destroy(b200rt_ctx *ctx);
 const char *b200rt_last_error(const b200rt_ctx *ctx);
 int b200rt_device_count(void);
+/* Several GPUs of ONE process behind one handle.  The reference's callers make one call per phase
+ * (RT_grid::generate_S_gpu / brightness_gpu, RT_gpu.cu:255-309,138-192; above them
+ * observation_fit::generate_source_function + brightness, observation_fit.cpp:122-169,491-516), so the handle fans
+ * each call out itself and every other entry point of this header takes it unchanged:
+ *   geometry, emission tables, source function: replicated on every device;
+ *   b200rt_generate_S / b200rt_influence*:      source-voxel rows split into interleaved shards; the devices write
+ *                                               their finished row batches into the first device's resident K over
+ *                                               peer memory (copy engines, NVLink) while marching the next batch;
+ *   b200rt_solve:                               on the first device, S handed to the others;
+ *   b200rt_brightness*, b200rt_iph_*:           lines of sight split by index, results at their offsets in the
+ *                                               caller's arrays; counters add up, b200rt_last_kernel_ms is the
+ *                                               slowest device's time.
+ * Work too small to pay for the fan-out stays on the first device (B200RT_GROUP_MIN_RAYS voxel rays, default 262144;
+ * B200RT_GROUP_MIN_LOS lines of sight, default 65536).  n_dev <= 0: every visible device; dev_ids NULL: 0..n_dev-1;
+ * one device: a plain context, exactly b200rt_create; an id may repeat (several members on one device, as the sweep's
+ * contexts per GPU).  b200rt_group_size: devices behind a handle (1 for a plain one). */
+int b200rt_create_multi(int n_dev, const int *dev_ids, int precision, b200rt_ctx **ctx);
+int b200rt_group_size(const b200rt_ctx *ctx);
 
 /* ---- geometry -------------------------------------------------------------------
  * replaces RT_grid::RT_to_device() for grid_type = spherical_azimuthally_symmetric_grid
@@ -252,7 +270,8 @@ int b200rt_traverse_los(b200rt_ctx *ctx, long long capacity,
 
 /* ---- timing ---------------------------------------------------------------------
  * device time (CUDA events on the ctx stream) of the kernels of the last call:
- * phase 0 = traversal, 1 = influence march, 2 = solve, 3 = brightness march, 4 = IPH */
+ * phase 0 = traversal, 1 = influence march, 2 = solve, 3 = brightness march (the march launches alone),
+ * 4 = IPH, 5 = the longest-first ordering kernels of the lines of sight (3 launches per batch) */
 int b200rt_last_kernel_ms(b200rt_ctx *ctx, int phase, float *ms, int *n_launches);
 int b200rt_synchronize(b200rt_ctx *ctx);
 /* measured FP64 peaks of this device (TFLOP/s): plain DFMA and DMMA.8x8x4 (mma.sync m8n8k4.f64).

@@ -492,5 +492,7 @@ double ref_brightness(void *h, int n, const double *loc, const double *dir, int 
   return static_cast<ref_model*>(h)->brightness(n, loc, dir, n_subsamples, out);
 }
 int ref_omp_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1: the caller pins the thread count of the CPU arm explicitly
+void ref_set_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 }

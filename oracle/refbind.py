@@ -57,6 +57,8 @@ def _load(precision: str):
     lib.ref_brightness.restype = C.c_double
     lib.ref_brightness.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp]
     lib.ref_omp_threads.restype = C.c_int
+    if hasattr(lib, "ref_set_omp_threads"):
+        lib.ref_set_omp_threads.argtypes = [C.c_int]
     lib.ref_real_bytes.restype = C.c_int
     _libs[precision] = lib
     return lib
@@ -168,4 +170,14 @@ class RefModel:
         return t, out
 
     def omp_threads(self) -> int:
+        return self.lib.ref_omp_threads()
+
+    def use_all_cores(self) -> int:
+        """pin the OpenMP thread count to the cores this process may run on (torchrun exports OMP_NUM_THREADS=1,
+        which would otherwise time the reference on one core) -> the thread count in effect"""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        self.lib.ref_set_omp_threads(n)
         return self.lib.ref_omp_threads()
