@@ -55,6 +55,16 @@ struct GridView {
   const Real *ray_sint;    // [n_rays]
   const double *ray_cp;    // [n_rays] cos(ray.p) (double call in ptray)
   const Real *ray_domega;  // [n_rays]
+  // voxel-origin rays: the sphere crossings of a ray depend on (radial shell of its voxel, cos of its polar angle) only,
+  // so their ordered, trimmed list is built once per (shell, polar-angle class) and shared by every voxel of the shell
+  // and every azimuth (traverse.cu, sphere_table_kernel).  nullptr: every ray builds its own.
+  int n_cls;               // distinct values of ray_cost
+  const int *ray_cls;      // [n_rays] class of each ray
+  const int *cls_ray;      // [n_cls]  one ray of each class
+  const int *sph_hdr;      // [(n_rb-1) * n_cls][2]: kept entries (-1: this pair takes the general path), unused
+  const Real *sph_de;      // [(n_rb-1) * n_cls]     distance of `end` (+inf: none)
+  const Real *sph_d;       // [(n_rb-1) * n_cls][2 n_rb]
+  const int *sph_i;        // [(n_rb-1) * n_cls][2 n_rb]
 };
 
 // boundary lists produced by the traversal kernel for a batch of rays: fixed stride
@@ -174,6 +184,7 @@ struct b200rt_ctx {
   b200rt::HostGrid hg;
   b200rt::DevBuf grid_tables;       // one slab holding every GridView array
   void *grid_view = nullptr;        // heap GridView<Real> (host struct of device pointers)
+  b200rt::DevBuf sph_table;         // ordered sphere-crossing lists per (radial shell, polar-angle class), traverse.cu
   b200rt::DevBuf sun_rays;          // RayList arrays for the n_vox sun-ward rays + shadow flags
   std::vector<int> shadow;          // host copy of the shadow test per voxel
 
@@ -251,6 +262,9 @@ void los_from_MSO(int n, const double *loc, const double *dir, double *x, double
                   double *r, double *t, double *lx, double *ly, double *lz, double *cost);
 
 // ---- traverse.cu  (compiled with -fmad=false: decides voxel indices)
+// fills the sphere-list table g points to (g.sph_* already carved, g.n_cls / ray_cls / cls_ray set); once per grid
+template <class Real>
+cudaError_t launch_sphere_table(const GridView<Real> &g, cudaStream_t s);
 template <class Real>
 cudaError_t launch_traverse_voxel_rays(const GridView<Real> &g, int v_begin, int v_end,
                                        ListView<Real> out, int *overflow_flag, cudaStream_t s);

@@ -98,6 +98,20 @@ int upload_grid(b200rt_ctx *c) {
     rdom[k] = (Real) h.ray_domega[k];
   }
 
+  // polar-angle classes of the rays: rays with bitwise equal cos(theta) cross every sphere at the same distances
+  std::vector<int> rcls(n_rays), cls_ray;
+  for (int k = 0; k < n_rays; k++) {
+    int c_id = -1;
+    for (size_t q = 0; q < cls_ray.size() && c_id < 0; q++)
+      if (std::memcmp(&rcost[cls_ray[q]], &rcost[k], sizeof(Real)) == 0) c_id = (int) q;
+    if (c_id < 0) { c_id = (int) cls_ray.size(); cls_ray.push_back(k); }
+    rcls[k] = c_id;
+  }
+  const int n_cls = (int) cls_ray.size();
+  // the table pays when classes are shared (n_phi rays per class); n_rb <= 128 is what the fast kernels cover
+  const bool use_table = !h.pp && n_rb <= 128 && 2 * n_cls <= n_rays;
+  const size_t n_pairs = (size_t) (n_rb - 1) * n_cls;
+
   // one slab
   size_t off = 0;
   const size_t o_rb = carve<Real>(off, n_rb), o_R2 = carve<Real>(off, n_rb), o_sb = carve<Real>(off, n_sb),
@@ -105,7 +119,8 @@ int upload_grid(b200rt_ctx *c) {
                o_lpr = carve<Real>(off, n_rb), o_ps = carve<Real>(off, n_sb), o_vz = carve<Real>(off, n_vox),
                o_ct = carve<double>(off, n_sb), o_st = carve<double>(off, n_sb),
                o_rc = carve<Real>(off, n_rays), o_rs = carve<Real>(off, n_rays),
-               o_rcp = carve<double>(off, n_rays), o_rd = carve<Real>(off, n_rays);
+               o_rcp = carve<double>(off, n_rays), o_rd = carve<Real>(off, n_rays),
+               o_cls = carve<int>(off, n_rays), o_clr = carve<int>(off, n_cls);
   std::vector<char> slab(off + 16, 0);
   auto put = [&](size_t at, const void *src, size_t bytes) { std::memcpy(slab.data() + at, src, bytes); };
   put(o_rb, rb.data(), n_rb * sizeof(Real));       put(o_R2, R2.data(), n_rb * sizeof(Real));
@@ -116,6 +131,7 @@ int upload_grid(b200rt_ctx *c) {
   put(o_ct, ct.data(), (n_sb - 1) * sizeof(double)); put(o_st, st.data(), (n_sb - 1) * sizeof(double));
   put(o_rc, rcost.data(), n_rays * sizeof(Real));  put(o_rs, rsint.data(), n_rays * sizeof(Real));
   put(o_rcp, rcp.data(), n_rays * sizeof(double)); put(o_rd, rdom.data(), n_rays * sizeof(Real));
+  put(o_cls, rcls.data(), n_rays * sizeof(int));   put(o_clr, cls_ray.data(), n_cls * sizeof(int));
 
   B200RT_CUDA(c, c->grid_tables.ensure(slab.size()));
   B200RT_CUDA(c, cudaMemcpyAsync(c->grid_tables.p, slab.data(), slab.size(), cudaMemcpyHostToDevice, c->stream));
@@ -134,6 +150,20 @@ int upload_grid(b200rt_ctx *c) {
   g->col_st = (const double *) (base + o_st);    g->ray_cost = (const Real *) (base + o_rc);
   g->ray_sint = (const Real *) (base + o_rs);    g->ray_cp = (const double *) (base + o_rcp);
   g->ray_domega = (const Real *) (base + o_rd);
+  g->n_cls = n_cls;
+  g->ray_cls = (const int *) (base + o_cls);     g->cls_ray = (const int *) (base + o_clr);
+  g->sph_hdr = nullptr; g->sph_de = nullptr; g->sph_d = nullptr; g->sph_i = nullptr;
+  if (use_table) {
+    size_t toff = 0;
+    const size_t t_de = carve<Real>(toff, n_pairs), t_d = carve<Real>(toff, n_pairs * 2 * n_rb),
+                 t_hdr = carve<int>(toff, n_pairs * 2), t_i = carve<int>(toff, n_pairs * 2 * n_rb);
+    B200RT_CUDA(c, c->sph_table.ensure(toff + 16));
+    char *tb = static_cast<char *>(c->sph_table.p);
+    g->sph_de = (const Real *) (tb + t_de);  g->sph_d = (const Real *) (tb + t_d);
+    g->sph_hdr = (const int *) (tb + t_hdr); g->sph_i = (const int *) (tb + t_i);
+    B200RT_CUDA(c, launch_sphere_table<Real>(*g, c->stream));
+    B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   c->grid_view = g;
 
   // sun-ward ray descriptors + shadow flags: [r | z | t | cost | lz](Real) [i_voxel | shadow](int)
