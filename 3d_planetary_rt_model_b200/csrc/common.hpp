@@ -49,6 +49,7 @@ struct GridView {
   const Real *log_pts_r;   // [n_rb-1]
   const Real *pts_s;       // [n_sb-1]
   const Real *vox_z;       // [n_vox]  r*cos(t) of the voxel point   atmo_point::rtp
+  const Real *vox_zn;      // [n_vox]  vox_z / pts_r: the IEEE quotient the cone intersections start from (cone::intersections)
   const double *col_ct;    // [n_sb-1] cos(pt.t) as the double libm call ptray makes
   const double *col_st;    // [n_sb-1] sin(pt.t)
   const Real *ray_cost;    // [n_rays] std::cos(ray.t)         atmo_ray::tp

@@ -44,7 +44,7 @@ int upload_grid(b200rt_ctx *c) {
   const int n_rb = h.n_rb, n_sb = h.n_sb, n_vox = h.n_vox, n_rays = h.n_rays;
 
   std::vector<Real> rb(n_rb), R2(n_rb), sb(n_sb), ccos(std::max(n_sb - 2, 1)), ccos2(std::max(n_sb - 2, 1)),
-      pr(n_rb - 1), lpr(n_rb - 1), ps(n_sb - 1), vz(n_vox), rcost(n_rays), rsint(n_rays), rdom(n_rays);
+      pr(n_rb - 1), lpr(n_rb - 1), ps(n_sb - 1), vz(n_vox), vzn(n_vox), rcost(n_rays), rsint(n_rays), rdom(n_rays);
   std::vector<double> ct(n_sb - 1), st(n_sb - 1), rcp(n_rays);
   // sun-ward rays
   std::vector<Real> sr(n_vox), sz(n_vox), stt(n_vox), scost(n_vox), slz(n_vox);
@@ -81,6 +81,7 @@ int upload_grid(b200rt_ctx *c) {
       const Real y = r * ::sin((double) t) * ::sin((double) p);
       const Real z = r * ::cos((double) t);
       vz[v] = z;
+      vzn[v] = z / r;
       c->shadow[v] = (z < 0 && x * x + y * y < rmin * rmin) ? 1 : 0;
       // ptxyz(pt, 0, 0, 1): line = (0,0,1)/hypot(hypot(0,0),1)
       const Real mag = ::hypot(::hypot(0.0, 0.0), 1.0);
@@ -120,7 +121,7 @@ int upload_grid(b200rt_ctx *c) {
                o_ct = carve<double>(off, n_sb), o_st = carve<double>(off, n_sb),
                o_rc = carve<Real>(off, n_rays), o_rs = carve<Real>(off, n_rays),
                o_rcp = carve<double>(off, n_rays), o_rd = carve<Real>(off, n_rays),
-               o_cls = carve<int>(off, n_rays), o_clr = carve<int>(off, n_cls);
+               o_cls = carve<int>(off, n_rays), o_clr = carve<int>(off, n_cls), o_vzn = carve<Real>(off, n_vox);
   std::vector<char> slab(off + 16, 0);
   auto put = [&](size_t at, const void *src, size_t bytes) { std::memcpy(slab.data() + at, src, bytes); };
   put(o_rb, rb.data(), n_rb * sizeof(Real));       put(o_R2, R2.data(), n_rb * sizeof(Real));
@@ -131,6 +132,7 @@ int upload_grid(b200rt_ctx *c) {
   put(o_ct, ct.data(), (n_sb - 1) * sizeof(double)); put(o_st, st.data(), (n_sb - 1) * sizeof(double));
   put(o_rc, rcost.data(), n_rays * sizeof(Real));  put(o_rs, rsint.data(), n_rays * sizeof(Real));
   put(o_rcp, rcp.data(), n_rays * sizeof(double)); put(o_rd, rdom.data(), n_rays * sizeof(Real));
+  put(o_vzn, vzn.data(), n_vox * sizeof(Real));
   put(o_cls, rcls.data(), n_rays * sizeof(int));   put(o_clr, cls_ray.data(), n_cls * sizeof(int));
 
   B200RT_CUDA(c, c->grid_tables.ensure(slab.size()));
@@ -151,6 +153,7 @@ int upload_grid(b200rt_ctx *c) {
   g->ray_sint = (const Real *) (base + o_rs);    g->ray_cp = (const double *) (base + o_rcp);
   g->ray_domega = (const Real *) (base + o_rd);
   g->n_cls = n_cls;
+  g->vox_zn = (const Real *) (base + o_vzn);
   g->ray_cls = (const int *) (base + o_cls);     g->cls_ray = (const int *) (base + o_clr);
   g->sph_hdr = nullptr; g->sph_de = nullptr; g->sph_d = nullptr; g->sph_i = nullptr;
   if (use_table) {

@@ -169,11 +169,18 @@ __device__ __forceinline__ int cone_hits(Real r, Real zn, Real lz, Real cost, Re
 // first boundary with c < b[i], minus one (n-1 if none); warp-cooperative.
 template <class Real>
 __device__ __forceinline__ int find_index(Real c, const Real *__restrict__ b, int n, int lane) {
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    const bool p = (i < n) && (c < b[i]);
-    const unsigned m = __ballot_sync(0xffffffffu, p);
-    if (m) return base + __ffs(m) - 2;
+  for (int base = 0; base < n; base += 128) {
+    // four groups of 32 boundaries with their loads in flight together
+    unsigned m[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int i = base + 32 * q + lane;
+      const bool p = (i < n) && (c < b[i]);
+      m[q] = __ballot_sync(0xffffffffu, p);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (m[q]) return base + 32 * q + __ffs(m[q]) - 2;
   }
   return n - 1;
 }
@@ -423,9 +430,11 @@ __device__ __forceinline__ void ray_scalars(const GridView<Real> &g, const RayLi
   const int n_rb = g.n_rb, n_sb = g.n_sb;
   int i_voxel;
   if (VOXEL_RAYS) {
-    int iv = v_begin + (int) (ray / g.n_rays);
+    // a batch of voxel-origin rays is far below 2^32 rays (launch_impl checks): 32-bit division
+    const unsigned slot_v = (unsigned) ray / (unsigned) g.n_rays;
+    int iv = v_begin + (int) slot_v;
     if (g.vox_map) iv = g.vox_map[iv];
-    const int ir = (int) (ray % g.n_rays);
+    const int ir = (int) ((unsigned) ray - slot_v * (unsigned) g.n_rays);
     const int irad = iv / (n_sb - 1), isza = iv % (n_sb - 1);
     r = g.pts_r[irad];
     t = g.pts_s[isza];
@@ -484,6 +493,14 @@ traverse_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> 
 //     and since the position of an entry in the OTHER list is then known, so is the index it inherits from it
 //     (propagate_indices): every entry writes its final list position, distance and voxel id directly -- no ranking of
 //     the whole list (count^2 / 32 compares), no forward-fill scan, no sorted copy in shared memory.
+// element-sized asynchronous copy global -> shared (LDGSTS): issued before the cone loop, waited for after it
+template <class T>
+__device__ __forceinline__ void cp_async_elem(T *smem, const T *gmem) {
+  const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
 template <class Real>
 __device__ __forceinline__ int count_below(const Real *a, int n, Real d) {      // #{a[i] < d}, a ascending
   int lo = 0;
@@ -534,11 +551,19 @@ __device__ __forceinline__ bool build_sphere_list(const GridView<Real> &g, Real 
     n2 += __popc(ms);
     total += __popc(mf) + __popc(ms);
   }
-  bool ok = (total == 2 * n2 + (n_rb - i0));
+  // the place formulas below are a bijection onto [0, total) exactly when the inner spheres that are hit are the n2
+  // outermost ones, each hit twice, and every outer sphere is hit once: checked lane by lane
+  bool shape_ok = true;
+#pragma unroll
+  for (int it = 0; it < SPH_ITERS; it++) {
+    const int ir = it * 32 + lane;
+    if (ir < n_rb) {
+      const bool above = (above_bits >> it) & 1u, h1 = hf[it] < INF, h2 = hs[it] < INF;
+      shape_ok = shape_ok && (above ? (h2 == (ir >= i0 - n2) && h1 == h2) : (h1 && !h2));
+    }
+  }
+  bool ok = __all_sync(0xffffffffu, shape_ok) && (total == 2 * n2 + (n_rb - i0));
   if (ok) {
-#pragma unroll 1
-    for (int j = lane; j < total; j += 32) S_i[j] = -1;
-    __syncwarp();
 #pragma unroll
     for (int it = 0; it < SPH_ITERS; it++) {
       const int ir = it * 32 + lane;
@@ -558,7 +583,6 @@ __device__ __forceinline__ bool build_sphere_list(const GridView<Real> &g, Real 
 #pragma unroll 1
     for (int j = lane; j < total; j += 32) {
       const int info = S_i[j];
-      if (info < 0) { bad = true; continue; }
       if (j > 0 && !key_less(S_d[j - 1], info_slot(S_i[j - 1]), S_d[j], info_slot(info))) bad = true;
       const int val = info_val(info);
       if ((val < 0 || val > n_rb - 2) && j < first_out) first_out = j;
@@ -593,13 +617,16 @@ sphere_table_kernel(GridView<Real> g, int *hdr, Real *tde, Real *td, int *ti) {
     for (int j = lane; j < nS; j += 32) { td[(size_t) pair * nS_max + j] = S_d[j]; ti[(size_t) pair * nS_max + j] = S_i[j]; }
 }
 
+#ifndef FAST_MIN_BLOCKS
+#define FAST_MIN_BLOCKS 6
+#endif
 template <class Real>
 __host__ __device__ __forceinline__ size_t fast_scratch_bytes(int n_rb, int n_sb) {
   return ((size_t) (2 * n_rb + 4 * n_sb) * (sizeof(Real) + sizeof(int)) + 15) & ~size_t(15);
 }
 
-template <class Real, bool VOXEL_RAYS, int SPH_ITERS>
-__global__ void __launch_bounds__(128)
+template <class Real, bool VOXEL_RAYS, int SPH_ITERS, bool USE_TABLE>
+__global__ void __launch_bounds__(128, FAST_MIN_BLOCKS)
 traverse_fast_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<Real> rl, ListView<Real> out,
                      int *overflow_flag, unsigned per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -624,6 +651,8 @@ traverse_fast_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<R
     int r0, s0;
     ray_scalars<Real, VOXEL_RAYS>(g, rl, v_begin, ray, lane, r, z, t, cost, lz, r0, s0);
     const bool origin_in = (r0 >= 0 && r0 <= n_rb - 2 && s0 >= 0 && s0 <= n_sb - 2);
+    Real zn_tab = 0;
+    if (VOXEL_RAYS && g.vox_zn) zn_tab = g.vox_zn[r0 * (n_sb - 1) + s0];   // z / r of the voxel point, divided on the host
     if (!origin_in) {   // warp-uniform
       general_ray<Real>(g, base, ray, r, z, t, cost, lz, r0, s0, false, out, overflow_flag);
       continue;
@@ -633,9 +662,10 @@ traverse_fast_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<R
     bool ok;
     int nS = 0;
     Real de = INF;
-    if (VOXEL_RAYS && g.sph_hdr) {
-      const int iv_ = g.vox_map ? g.vox_map[v_begin + (int) (ray / g.n_rays)] : v_begin + (int) (ray / g.n_rays);
-      const size_t pair = (size_t) (iv_ / (n_sb - 1)) * g.n_cls + g.ray_cls[(int) (ray % g.n_rays)];
+    if (USE_TABLE) {
+      const unsigned slot_v = (unsigned) ray / (unsigned) g.n_rays;
+      const int iv_ = g.vox_map ? g.vox_map[v_begin + (int) slot_v] : v_begin + (int) slot_v;
+      const size_t pair = (size_t) (iv_ / (n_sb - 1)) * g.n_cls + g.ray_cls[(int) ((unsigned) ray - slot_v * (unsigned) g.n_rays)];
       nS = g.sph_hdr[2 * pair];
       ok = nS >= 0;
       if (ok) {
@@ -643,7 +673,7 @@ traverse_fast_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<R
         const Real *td = g.sph_d + pair * nS_max;
         const int *ti = g.sph_i + pair * nS_max;
 #pragma unroll 1
-        for (int j = lane; j < nS; j += 32) { S_d[j] = td[j]; S_i[j] = ti[j]; }
+        for (int j = lane; j < nS; j += 32) { cp_async_elem(S_d + j, td + j); cp_async_elem(S_i + j, ti + j); }
       }
     } else {
       ok = build_sphere_list<Real, SPH_ITERS>(g, r, cost, lane, S_d, S_i, nS, de);
@@ -656,7 +686,7 @@ traverse_fast_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<R
 
     // ---- cones before `end` (a cone crossing AT the distance of `end` comes after it: its slot is higher)
     int nC = 0;
-    const Real zn = z / r;
+    const Real zn = (VOXEL_RAYS && g.vox_zn) ? zn_tab : z / r;
 #pragma unroll 1
     for (int base_k = 0; base_k < n_sb - 2; base_k += 32) {
       const int k = base_k + lane;
@@ -692,19 +722,46 @@ traverse_fast_kernel(GridView<Real> g, int v_begin, long long n_total, RayList<R
       __syncwarp();
       continue;
     }
+    if (USE_TABLE) asm volatile("cp.async.wait_all;" ::: "memory");     // the shared sphere list has landed
     __syncwarp();
-    // cones among themselves: exact (distance, slot) rank
+    // cones among themselves: rank by distance alone (distances read 16 bytes at a time); two crossings at exactly the
+    // same distance collide on one rank and leave a hole, which sends the (rare) ray through the exact (distance, slot) rank
+    {
+      constexpr int VEC = 16 / (int) sizeof(Real);
+      typedef typename VecOf<Real>::type RealV;
+      const int nC_pad = (nC + VEC - 1) / VEC * VEC;
 #pragma unroll 1
-    for (int e = lane; e < nC; e += 32) {
-      const Real d = C_d[e];
-      const int info = C_i[e], slot = info_slot(info);
-      int rank = 0;
-#pragma unroll 2
-      for (int j = 0; j < nC; j++) rank += key_less(C_d[j], info_slot(C_i[j]), d, slot) ? 1 : 0;
-      Cs_d[rank] = d;
-      Cs_i[rank] = info;
+      for (int e = nC + lane; e < nC_pad; e += 32) C_d[e] = INF;      // padding never counts (INF < d is false)
+#pragma unroll 1
+      for (int e = lane; e < nC; e += 32) Cs_i[e] = -1;
+      __syncwarp();
+      const RealV *cv = reinterpret_cast<const RealV *>(C_d);
+#pragma unroll 1
+      for (int e = lane; e < nC; e += 32) {
+        const Real d = C_d[e];
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < nC_pad / VEC; j++) rank += VecOf<Real>::count_less(cv[j], d);
+        Cs_d[rank] = d;
+        Cs_i[rank] = C_i[e];
+      }
+      __syncwarp();
+      bool hole = false;
+#pragma unroll 1
+      for (int e = lane; e < nC; e += 32) hole |= (Cs_i[e] < 0);
+      if (__any_sync(0xffffffffu, hole)) {
+#pragma unroll 1
+        for (int e = lane; e < nC; e += 32) {
+          const Real d = C_d[e];
+          const int info = C_i[e], slot = info_slot(info);
+          int rank = 0;
+          for (int j = 0; j < nC; j++) rank += key_less(C_d[j], info_slot(C_i[j]), d, slot) ? 1 : 0;
+          Cs_d[rank] = d;
+          Cs_i[rank] = info;
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
 
     // ---- merge: every entry writes its final position, distance and voxel id
     Real *od = out.dist + (size_t) ray * cap;
@@ -753,9 +810,16 @@ cudaError_t launch_fast(const GridView<Real> &g, int v_begin, long long n_total,
                         int *overflow_flag, unsigned blocks, int threads, cudaStream_t s) {
   const size_t per_warp = std::max(general_bytes_host(g), fast_scratch_bytes<Real>(g.n_rb, g.n_sb));
   const size_t smem = per_warp * (threads / 32);
-  cudaError_t e = cudaFuncSetAttribute(traverse_fast_kernel<Real, VR, SPH_ITERS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-  if (e != cudaSuccess) return e;
-  traverse_fast_kernel<Real, VR, SPH_ITERS><<<blocks, threads, smem, s>>>(g, v_begin, n_total, rl, out, overflow_flag, (unsigned) per_warp);
+  cudaError_t e;
+  if (VR && g.sph_hdr) {
+    e = cudaFuncSetAttribute(traverse_fast_kernel<Real, VR, SPH_ITERS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    traverse_fast_kernel<Real, VR, SPH_ITERS, true><<<blocks, threads, smem, s>>>(g, v_begin, n_total, rl, out, overflow_flag, (unsigned) per_warp);
+  } else {
+    e = cudaFuncSetAttribute(traverse_fast_kernel<Real, VR, SPH_ITERS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    traverse_fast_kernel<Real, VR, SPH_ITERS, false><<<blocks, threads, smem, s>>>(g, v_begin, n_total, rl, out, overflow_flag, (unsigned) per_warp);
+  }
   return cudaGetLastError();
 }
 
@@ -764,6 +828,7 @@ cudaError_t launch_impl(const GridView<Real> &g, int v_begin, long long n_total,
                         ListView<Real> out, int *overflow_flag, cudaStream_t s) {
   if (n_total <= 0) return cudaSuccess;
   if (2 * (g.n_rb + g.n_sb) + 2 >= (1 << SLOT_BITS)) return cudaErrorInvalidValue;
+  if (VR && n_total >= (1LL << 32)) return cudaErrorInvalidValue;   // ray_scalars divides in 32 bits
   const int threads = 128, warps = threads / 32;
   long long blocks = (n_total + warps - 1) / warps;
   const long long max_blocks = (long long) NUM_SMS * 16;
