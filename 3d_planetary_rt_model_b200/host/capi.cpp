@@ -1,5 +1,6 @@
 // capi.cpp -- flat C handles over the observation_fit facade, for ctypes-driven tests and for bindings
 // that cannot consume C++ (the reference's own binding is Cython on the C++ class, python/py_corona_sim.pyx).
+#include <fstream>
 #include <csignal>
 #include <cstdlib>
 #include <cstring>
@@ -136,6 +137,29 @@ int obsfit_lyman_multiplet_generate_source_function(void *h, double nH, double T
 }
 int obsfit_lyman_singlet_generate_source_function(void *h, double nH, double T, const char *sourcefn_fname) {
   return guard([&] { static_cast<observation_fit *>(h)->lyman_singlet_generate_source_function(nH, T, "", str(sourcefn_fname)); });
+}
+// the writers on plain arrays: q = [n_em][8][n_vox] in the order the file prints them (species density, species
+// single-scattering tau, species cross section, absorber density, absorber tau, absorber cross section, S0, S)
+int obsfit_write_S_file(const char *fname, int n_rb, int n_sb, const double *rb, const double *pts_r, const double *sb,
+                        const double *pts_s, int n_em, const char *const *names, const double *q) {
+  return guard([&] {
+    const size_t n_vox = (size_t) (n_rb - 1) * (n_sb - 1);
+    std::vector<std::vector<std::vector<double>>> Q(n_em, std::vector<std::vector<double>>(8));
+    std::vector<std::string> nm;
+    for (int e = 0; e < n_em; e++) {
+      nm.push_back(names[e]);
+      for (int k = 0; k < 8; k++) Q[e][k].assign(q + ((size_t) e * 8 + k) * n_vox, q + ((size_t) e * 8 + k + 1) * n_vox);
+    }
+    write_S_file(fname, false, n_rb, n_sb, std::vector<double>(rb, rb + n_rb), std::vector<double>(pts_r, pts_r + n_rb - 1),
+                 std::vector<double>(sb, sb + n_sb), std::vector<double>(pts_s, pts_s + n_sb - 1), n_em, nm, Q);
+  });
+}
+int obsfit_write_influence_file(const char *fname, int n_em, const char *const *names, const double *K, int n) {
+  return guard([&] {
+    std::ofstream file(fname);
+    for (int e = 0; e < n_em; e++)
+      write_influence(file, names[e], std::vector<double>(K + (size_t) e * n * n, K + (size_t) (e + 1) * n * n), n);
+  });
 }
 int obsfit_save_influence_matrix_O_1026(void *h, const char *fname) { return guard([&] { static_cast<observation_fit *>(h)->save_influence_matrix_O_1026(fname); }); }
 // options

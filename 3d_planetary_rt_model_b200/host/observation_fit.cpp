@@ -467,44 +467,50 @@ string row(const vector<double> &v) {
 }
 }
 
-void observation_fit::save_S(const string &fname, const set_inputs &in) {
+// grid.save_S + singlet_CFR::save from plain arrays (per emission: 8 arrays of n_vox, in the order the file prints them)
+void write_S_file(const string &fname, bool plane_parallel, int n_rb, int n_sb, const vector<double> &rb,
+                  const vector<double> &pts_r, const vector<double> &sb, const vector<double> &pts_s, int n_em,
+                  const vector<string> &names, const vector<vector<vector<double>>> &q) {
   std::ofstream file(fname.c_str());
   if (!file.is_open()) return;
-  file << "radial boundaries [cm]: " << row(in.rb) << "\n\n";
-  file << "pts radii [cm]: " << row(in.pts_r) << "\n\n";
-  if (!in.plane_parallel) {
-    file << "sza boundaries [rad]: " << row(in.sb) << "\n\n";
-    file << "pts sza [rad]: " << row(in.pts_s) << "\n\n";
+  file << "radial boundaries [cm]: " << row(rb) << "\n\n";
+  file << "pts radii [cm]: " << row(pts_r) << "\n\n";
+  if (!plane_parallel) {
+    file << "sza boundaries [rad]: " << row(sb) << "\n\n";
+    file << "pts sza [rad]: " << row(pts_s) << "\n\n";
   }
-  const char *names[2] = {"H Lyman alpha", "H Lyman beta"};
-  const int ns = in.n_sb - 1, nr = in.n_rb - 1;
-  auto slice = [&](const vector<double> &q, int j) {      // sza_slice: every voxel of SZA column j
+  const int ns = n_sb - 1, nr = n_rb - 1;
+  auto slice = [&](const vector<double> &v, int j) {      // sza_slice: every voxel of SZA column j
     vector<double> r(nr);
-    for (int i = 0; i < nr; i++) r[i] = q[(size_t) i * ns + j];
+    for (int i = 0; i < nr; i++) r[i] = v[(size_t) i * ns + j];
     return r;
   };
-  for (int e = 0; e < n_hydrogen_emissions; e++) {
+  static const char *labels[8] = {"Species density [cm-3]: ", "Species single scattering tau: ", "Species cross section [cm2]: ",
+                                  "Absorber density [cm-3]: ", "Absorber single scattering tau: ", "Absorber cross section [cm2]: ",
+                                  "Species single scattering source function S0: ", "Source function: "};
+  for (int e = 0; e < n_em; e++) {
     // grid_spherical_azimuthally_symmetric.hpp:650-660 ("For <name>" + one block per SZA);
     // grid_plane_parallel.hpp:329-332 ("For <name>," + one block)
-    file << "For " << names[e] << (in.plane_parallel ? ",\n" : "\n");
-    vector<double> sig(in.n_vox), asig(in.n_vox, in.abs_sigma[e]);
-    for (int v = 0; v < in.n_vox; v++) sig[v] = in.sigma_ref[e] * std::sqrt(in.tabs[e][0][v]);
+    file << "For " << names[e] << (plane_parallel ? ",\n" : "\n");
     for (int j = 0; j < ns; j++) {
-      if (!in.plane_parallel) file << "  For SZA = " << in.pts_s[j] << ": \n";
-      file << "    Species density [cm-3]: " << row(slice(in.tabs[e][1], j)) << "\n"
-           << "    Species single scattering tau: " << row(slice(in.tau_sp[e], j)) << "\n"
-           << "    Species cross section [cm2]: " << row(slice(sig, j)) << "\n"
-           << "    Absorber density [cm-3]: " << row(slice(in.vox[4], j)) << "\n"
-           << "    Absorber single scattering tau: " << row(slice(in.tau_abs[e], j)) << "\n"
-           << "    Absorber cross section [cm2]: " << row(slice(asig, j)) << "\n"
-           << "    Species single scattering source function S0: " << row(slice(in.S0[e], j)) << "\n"
-           << "    Source function: " << row(slice(in.S[e], j)) << "\n\n";
+      if (!plane_parallel) file << "  For SZA = " << pts_s[j] << ": \n";
+      for (int k = 0; k < 8; k++) file << "    " << labels[k] << row(slice(q[e][k], j)) << (k == 7 ? "\n\n" : "\n");
     }
   }
 }
 
+void observation_fit::save_S(const string &fname, const set_inputs &in) {
+  vector<vector<vector<double>>> q(n_hydrogen_emissions, vector<vector<double>>(8));
+  for (int e = 0; e < n_hydrogen_emissions; e++) {
+    vector<double> sig(in.n_vox), asig(in.n_vox, in.abs_sigma[e]);
+    for (int v = 0; v < in.n_vox; v++) sig[v] = in.sigma_ref[e] * std::sqrt(in.tabs[e][0][v]);
+    q[e] = {in.tabs[e][1], in.tau_sp[e], sig, in.vox[4], in.tau_abs[e], asig, in.S0[e], in.S[e]};
+  }
+  write_S_file(fname, in.plane_parallel, in.n_rb, in.n_sb, in.rb, in.pts_r, in.sb, in.pts_s, n_hydrogen_emissions,
+               {"H Lyman alpha", "H Lyman beta"}, q);
+}
+
 // emission_voxels::save_influence (emission_voxels.hpp:235-238) for every emission of a model
-namespace {
 void write_influence(std::ofstream &file, const string &name, const vector<double> &K, int n) {
   file << "Here is the influence matrix for " << name << ":\n";
   // Eigen prints a matrix with every coefficient padded to the widest one of the whole matrix
@@ -524,7 +530,6 @@ void write_influence(std::ofstream &file, const string &name, const vector<doubl
     file << "\n";
   }
   file << "\n";
-}
 }
 
 void observation_fit::save_influence_matrix(const string fname) {

@@ -24,6 +24,7 @@
 // brightness per parameter set -- over all GPUs with several contexts each, instead of the reference's Python loop over
 // generate_source_function + brightness.
 #pragma once
+#include <fstream>
 #include <string>
 #include <vector>
 #include "atmosphere.hpp"
@@ -182,3 +183,11 @@ private:
   singlet_model &singlet(int which);
   double batch_seconds = 0;
 };
+// the ASCII writers on plain arrays (what save_S / save_influence_matrix print; observation_fit.cpp), exposed so that
+// their output can be compared byte for byte with the reference's own writers
+void write_S_file(const std::string &fname, bool plane_parallel, int n_rb, int n_sb, const std::vector<double> &rb,
+                  const std::vector<double> &pts_r, const std::vector<double> &sb, const std::vector<double> &pts_s, int n_em,
+                  const std::vector<std::string> &names, const std::vector<std::vector<std::vector<double>>> &q);
+void write_influence(std::ofstream &file, const std::string &name, const std::vector<double> &K, int n);
+
+

@@ -49,6 +49,8 @@ SIGNATURES = {
     "obsfit_Tconv": (C.c_int, [_vp, C.c_int, C.c_double, C.POINTER(C.c_double)]),
     "obsfit_source_function_ex": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "obsfit_radial_boundaries_ex": (C.c_int, [_vp, C.c_int, _dp]),
+    "obsfit_write_S_file": (C.c_int, [C.c_char_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_char_p), _dp]),
+    "obsfit_write_influence_file": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.c_int]),
     "obsfit_multiplet_source_function": (C.c_int, [_vp, C.c_int, _dp, C.c_int, C.POINTER(C.c_int)]),
 }
 MODEL_H, MODEL_D, MODEL_H_PP, MODEL_D_PP = 0, 1, 2, 3
@@ -67,6 +69,27 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def write_S_file(fname, rb, pts_r, sb, pts_s, names, q):
+    """the facade's save_S writer on plain arrays: q[n_em][8][n_vox] (order of the printed blocks)"""
+    lib = load()
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    nm = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    rc = lib.obsfit_write_S_file(os.fsencode(fname), len(rb), len(sb), np.ascontiguousarray(rb, dtype=np.float64),
+                                 np.ascontiguousarray(pts_r, dtype=np.float64), np.ascontiguousarray(sb, dtype=np.float64),
+                                 np.ascontiguousarray(pts_s, dtype=np.float64), len(names), nm, q)
+    if rc != 0:
+        raise RuntimeError(lib.obsfit_last_error().decode())
+
+
+def write_influence_file(fname, names, K):
+    """the facade's save_influence_matrix writer on plain arrays: K[n_em][n][n]"""
+    lib = load()
+    K = np.ascontiguousarray(K, dtype=np.float64)
+    nm = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    if lib.obsfit_write_influence_file(os.fsencode(fname), len(names), nm, K, K.shape[-1]) != 0:
+        raise RuntimeError(lib.obsfit_last_error().decode())
 
 
 def atmosphere_tables(nH, nCO2, T, n_rb=40, n_sb=20, rmethod=0):

@@ -82,6 +82,9 @@ struct ref_model {
   virtual double brightness(int n, const double *loc, const double *dir, int n_subsamples, double *out) = 0;
   virtual int n_voxels() = 0;
   virtual int n_rays() = 0;
+  // the reference's own ASCII writers (RT_grid.hpp:221-230): 0 = done, -1 = not available on this model
+  virtual int save_S(const char *) { return -1; }
+  virtual int save_influence(const char *) { return -1; }
 };
 
 template <int NR, int NSZA, int NTH, int NPH, int NEM>
@@ -152,6 +155,8 @@ struct ref_model_impl : ref_model {
     for (int i=0;i<NR;i++) rad_b[i]=g.radial_boundaries[i];
   }
   void get_arrays(int e, double *out) override { em[e].dump_arrays(out); }
+  int save_S(const char *fname) override { RT->save_S(fname); return 0; }
+  int save_influence(const char *fname) override { RT->save_influence(fname); return 0; }
 
   long dump_stepper(const stepper_type &st, long pos, long cap, int *len, int *exits_bottom,
 		    int *entering, double *distance) {
@@ -491,6 +496,8 @@ void ref_set_sourcefn(void *h, int e, const double *S) { static_cast<ref_model*>
 double ref_brightness(void *h, int n, const double *loc, const double *dir, int n_subsamples, double *out) {
   return static_cast<ref_model*>(h)->brightness(n, loc, dir, n_subsamples, out);
 }
+int ref_save_S(void *h, const char *fname) { return static_cast<ref_model*>(h)->save_S(fname); }
+int ref_save_influence(void *h, const char *fname) { return static_cast<ref_model*>(h)->save_influence(fname); }
 int ref_omp_threads() { return omp_get_max_threads(); }
 // torchrun exports OMP_NUM_THREADS=1: the caller pins the thread count of the CPU arm explicitly
 void ref_set_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); }

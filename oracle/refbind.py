@@ -57,6 +57,9 @@ def _load(precision: str):
     lib.ref_brightness.restype = C.c_double
     lib.ref_brightness.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp]
     lib.ref_omp_threads.restype = C.c_int
+    if hasattr(lib, "ref_save_S"):
+        lib.ref_save_S.argtypes = [C.c_void_p, C.c_char_p]
+        lib.ref_save_influence.argtypes = [C.c_void_p, C.c_char_p]
     if hasattr(lib, "ref_set_omp_threads"):
         lib.ref_set_omp_threads.argtypes = [C.c_int]
     lib.ref_real_bytes.restype = C.c_int
@@ -168,6 +171,16 @@ class RefModel:
         t = self.lib.ref_brightness(self.h, n, np.ascontiguousarray(locs, dtype=np.float64),
                                     np.ascontiguousarray(dirs, dtype=np.float64), n_subsamples, out)
         return t, out
+
+    def save_S(self, fname: str) -> None:
+        """RT_grid::save_S (RT_grid.hpp:228-230): the reference's own ASCII writer"""
+        if self.lib.ref_save_S(self.h, os.fsencode(fname)) != 0:
+            raise RuntimeError("save_S not available on this reference model")
+
+    def save_influence(self, fname: str) -> None:
+        """RT_grid::save_influence (RT_grid.hpp:221-227)"""
+        if self.lib.ref_save_influence(self.h, os.fsencode(fname)) != 0:
+            raise RuntimeError("save_influence not available on this reference model")
 
     def omp_threads(self) -> int:
         return self.lib.ref_omp_threads()

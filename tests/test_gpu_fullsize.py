@@ -16,6 +16,71 @@ def big(synth, binding):
     return scn, G
 
 
+# the other builds of the same grid: Real = float (the precision of the reference's own GPU module; bar 1e-4) and the
+# two-emission model observation_fit drives (H Ly alpha + Ly beta in one pass)
+@pytest.mark.parametrize("prec,n_em", [("f32", 1), ("f64", 2), ("f32", 2)])
+def test_fullsize_other_builds(synth, binding, oraclebind, prec, n_em):
+    from util import TOL, TOL_AUX, UNDERFLOW
+    tol = TOL[prec]
+    scn = synth.make_scenario(100, 60, 24, 16, n_em=n_em, rmax=synth.rMars + 50000e5, sza_T_contrast=0.1)
+    G = binding.GpuModel(scn, prec)
+    O = oraclebind.OracleModel(scn, prec)
+    rows = list(range(3, scn.n_vox, 731))
+    for v in rows:                                           # traversal: bit-exact in both precisions
+        assert_lists_equal(O.traverse_voxel_rays(v, v + 1), G.traverse_voxel_rays(v, v + 1))
+    G.build_rows()
+    O.build_rows(3, scn.n_vox, 731)
+    floor = 1e-290 if prec == "f64" else 1e-30
+    for e in range(n_em):
+        Ko, Kg = O.K(e), G.K(e)
+        for v in rows:
+            a, b = np.where(np.abs(Ko[v]) > floor, Ko[v], 0.0), np.where(np.abs(Kg[v]) > floor, Kg[v], 0.0)
+            assert np.array_equal(a != 0, b != 0)
+            assert rel_err(a, b) < tol, (e, v)
+        vo, vg = O.vectors(e), G.vectors(e, want_S=False)
+        assert rel_err(vo["S0"][rows], vg["S0"][rows], floor=UNDERFLOW[prec]) < tol
+    res = G.solve()
+    assert max(res) < 1e-12                                  # the solve is FP64 in both builds
+    locs, dirs = synth.random_los(1500, seed=17)
+    assert_lists_equal(O.traverse_los(locs, dirs)[:4], G.traverse_los(locs, dirs)[:4])
+    for e in range(n_em):
+        O.set_sourcefn(e, G.vectors(e)["S"])
+    _, bo = O.brightness(locs, dirs, 10)
+    _, bg = G.brightness(locs, dirs, 10)
+    for q in range(4):
+        assert rel_err(bo[:, q], bg[:, q], floor=1e-300) < (tol if q == 0 else TOL_AUX[prec]), q
+
+
+def test_fullsize_multiplet_sample(synth, binding):
+    """a multiplet emission (H Lyman singlet-via-multiplet, 2 upper states: 11,682 unknowns) on the 100x60 grid:
+    sampled influence rows, single scattering and a brightness sample against the oracle"""
+    from oracle import multbind
+    scn = synth.make_multiplet_scenario(2, 100, 60, 8, 8, sza_T_contrast=0.1)
+    G = binding.GpuMultiplet(scn, "f64")
+    O = multbind.OracleMultiplet(scn, "f64")
+    G.build_rows()
+    O.build_rows(5, scn.n_vox, 977)
+    vox = list(range(5, scn.n_vox, 977))
+    Ko, Kg = O.K(), G.K()
+    nu = G.n_upper
+    for v in vox:
+        for u in range(nu):
+            a, b = Ko[v * nu + u], Kg[v * nu + u]
+            a, b = np.where(np.abs(a) > 1e-290, a, 0.0), np.where(np.abs(b) > 1e-290, b, 0.0)
+            assert rel_err(a, b) < 1e-6, (v, u)
+    del Ko, Kg
+    vo, vg = O.vectors(), G.vectors(want_S=False)
+    idx = np.array([v * nu + u for v in vox for u in range(nu)])
+    assert rel_err(vo["S0"][idx], vg["S0"][idx], floor=1e-300) < 1e-6
+    assert G.solve() < 1e-12
+    S = G.vectors()["S"]
+    O.set_sourcefn(S)
+    locs, dirs = synth.random_los(800, seed=23)
+    bo, bg = O.brightness(locs, dirs, 10), G.brightness(locs, dirs, 10)
+    for k in bo:
+        assert rel_err(bo[k], bg[k], floor=1e-300) < 1e-6, k
+
+
 def test_sampled_rows_match_oracle(big, oraclebind):
     scn, G = big
     O = oraclebind.OracleModel(scn, "f64")
