@@ -31,6 +31,9 @@
 #include "emission/singlet_CFR.hpp"
 #include "observation.hpp"
 #include "ref_table_atmosphere.hpp"
+#ifdef RT_B200
+#include "RT_b200.hpp"   // integration/: the reference-side binding of libb200rt.so (defines the RT_grid *_gpu members)
+#endif
 
 namespace {
 
@@ -83,6 +86,10 @@ struct ref_model {
   virtual int n_voxels() = 0;
   virtual int n_rays() = 0;
   // the reference's own ASCII writers (RT_grid.hpp:221-230): 0 = done, -1 = not available on this model
+  // RT_grid::generate_S_gpu / brightness_gpu through integration/RT_b200.hpp (-DRT_B200 builds only): -1 = not built in
+  virtual int generate_S_gpu() { return -1; }
+  virtual int brightness_gpu(int, const double *, const double *, int, double *) { return -1; }
+  virtual int influence_to_host() { return -1; }
   virtual int save_S(const char *) { return -1; }
   virtual int save_influence(const char *) { return -1; }
 };
@@ -157,6 +164,24 @@ struct ref_model_impl : ref_model {
   void get_arrays(int e, double *out) override { em[e].dump_arrays(out); }
   int save_S(const char *fname) override { RT->save_S(fname); return 0; }
   int save_influence(const char *fname) override { RT->save_influence(fname); return 0; }
+#ifdef RT_B200
+  int generate_S_gpu() override { RT->generate_S_gpu(); return 0; }
+  int influence_to_host() override { RT->emissions_influence_to_host(); return 0; }
+  int brightness_gpu(int n, const double *loc, const double *dir, int n_subsamples, double *out) override {
+    std::vector<std::vector<Real>> L(n, std::vector<Real>(3)), D(n, std::vector<Real>(3));
+    for (int i=0;i<n;i++) for (int k=0;k<3;k++) { L[i][k]=(Real) loc[3*i+k]; D[i][k]=(Real) dir[3*i+k]; }
+    obs->add_MSO_observation(L, D);
+    RT->brightness_gpu(*obs, n_subsamples);
+    for (int e=0;e<NEM;e++)
+      for (int i=0;i<n;i++) {
+	out[((size_t)e*4+0)*n+i]=obs->los[e][i].brightness;
+	out[((size_t)e*4+1)*n+i]=obs->los[e][i].tau_species_final;
+	out[((size_t)e*4+2)*n+i]=obs->los[e][i].tau_absorber_final;
+	out[((size_t)e*4+3)*n+i]=obs->los[e][i].species_col_dens;
+      }
+    return 0;
+  }
+#endif
 
   long dump_stepper(const stepper_type &st, long pos, long cap, int *len, int *exits_bottom,
 		    int *entering, double *distance) {
@@ -495,6 +520,11 @@ void ref_get_vectors(void *h, int e, double *S0, double *tsp, double *tab, doubl
 void ref_set_sourcefn(void *h, int e, const double *S) { static_cast<ref_model*>(h)->set_sourcefn(e, S); }
 double ref_brightness(void *h, int n, const double *loc, const double *dir, int n_subsamples, double *out) {
   return static_cast<ref_model*>(h)->brightness(n, loc, dir, n_subsamples, out);
+}
+int ref_generate_S_gpu(void *h) { try { return static_cast<ref_model*>(h)->generate_S_gpu(); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return -3; } }
+int ref_influence_to_host(void *h) { try { return static_cast<ref_model*>(h)->influence_to_host(); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return -3; } }
+int ref_brightness_gpu(void *h, int n, const double *loc, const double *dir, int n_subsamples, double *out) {
+  try { return static_cast<ref_model*>(h)->brightness_gpu(n, loc, dir, n_subsamples, out); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return -3; }
 }
 int ref_save_S(void *h, const char *fname) { return static_cast<ref_model*>(h)->save_S(fname); }
 int ref_save_influence(void *h, const char *fname) { return static_cast<ref_model*>(h)->save_influence(fname); }

@@ -16,21 +16,24 @@ _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
-def lib_path(precision: str = "f64") -> str:
-    return os.path.join(HERE, "_ref", f"libref_{precision}.so")
+def lib_path(precision: str = "f64", variant: str = "") -> str:
+    """variant "b200": the same harness built with -DRT_B200, i.e. the reference's RT_grid with its *_gpu members
+    bound to libb200rt.so by integration/RT_b200.hpp (oracle/Makefile ref_b200)"""
+    return os.path.join(HERE, "_ref", f"libref_{variant + '_' if variant else ''}{precision}.so")
 
 
-def available(precision: str = "f64") -> bool:
-    return os.path.exists(lib_path(precision))
+def available(precision: str = "f64", variant: str = "") -> bool:
+    return os.path.exists(lib_path(precision, variant))
 
 
 _libs = {}
 
 
-def _load(precision: str):
-    if precision in _libs:
-        return _libs[precision]
-    lib = C.CDLL(lib_path(precision))
+def _load(precision: str, variant: str = ""):
+    key = precision + variant
+    if key in _libs:
+        return _libs[key]
+    lib = C.CDLL(lib_path(precision, variant))
     lib.ref_create.restype = C.c_void_p
     lib.ref_create.argtypes = [C.c_int] * 5
     lib.ref_create_pp.restype = C.c_void_p
@@ -63,15 +66,19 @@ def _load(precision: str):
     if hasattr(lib, "ref_set_omp_threads"):
         lib.ref_set_omp_threads.argtypes = [C.c_int]
     lib.ref_real_bytes.restype = C.c_int
-    _libs[precision] = lib
+    if hasattr(lib, "ref_generate_S_gpu"):
+        lib.ref_generate_S_gpu.argtypes = [C.c_void_p]
+        lib.ref_influence_to_host.argtypes = [C.c_void_p]
+        lib.ref_brightness_gpu.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, _dp]
+    _libs[key] = lib
     return lib
 
 
 class RefModel:
     """One reference RT_grid<singlet_CFR, n_em, spherical_azimuthally_symmetric_grid<...>>."""
 
-    def __init__(self, scn, precision: str = "f64", rmethod_inject: bool = True):
-        self.lib = _load(precision)
+    def __init__(self, scn, precision: str = "f64", rmethod_inject: bool = True, variant: str = ""):
+        self.lib = _load(precision, variant)
         self.scn = scn
         if getattr(scn, "pp", False):      # plane_parallel_grid<n_rb, n_theta>
             self.h = self.lib.ref_create_pp(scn.n_rb, scn.n_theta, scn.n_em)
@@ -171,6 +178,25 @@ class RefModel:
         t = self.lib.ref_brightness(self.h, n, np.ascontiguousarray(locs, dtype=np.float64),
                                     np.ascontiguousarray(dirs, dtype=np.float64), n_subsamples, out)
         return t, out
+
+    # ---- the reference's RT_grid::*_gpu members, bound to libb200rt.so by integration/RT_b200.hpp (variant "b200")
+    def generate_S_gpu(self) -> None:
+        rc = self.lib.ref_generate_S_gpu(self.h)
+        if rc != 0:
+            raise RuntimeError(f"RT_grid::generate_S_gpu failed ({rc}): built without -DRT_B200, or no GPU")
+
+    def influence_to_host(self) -> None:
+        if self.lib.ref_influence_to_host(self.h) != 0:
+            raise RuntimeError("RT_grid::emissions_influence_to_host failed")
+
+    def brightness_gpu(self, locs, dirs, n_subsamples: int = 10):
+        n = len(locs)
+        out = np.zeros((self.scn.n_em, 4, n))
+        rc = self.lib.ref_brightness_gpu(self.h, n, np.ascontiguousarray(locs, dtype=np.float64),
+                                         np.ascontiguousarray(dirs, dtype=np.float64), n_subsamples, out)
+        if rc != 0:
+            raise RuntimeError(f"RT_grid::brightness_gpu failed ({rc})")
+        return out
 
     def save_S(self, fname: str) -> None:
         """RT_grid::save_S (RT_grid.hpp:228-230): the reference's own ASCII writer"""
