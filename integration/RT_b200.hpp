@@ -33,7 +33,10 @@ struct ctx_holder {
     return c;
   }
 };
-inline ctx_holder &holder() { static thread_local ctx_holder h; return h; }
+// (keyed by Real: function-local statics of inline functions are process-wide unique symbols, so a process that loads
+// a float and a double build of the reference side by side must not share one context between them)
+template <class R> inline ctx_holder &holder_of() { static thread_local ctx_holder h; return h; }
+inline ctx_holder &holder() { return holder_of<Real>(); }
 inline void ck(int rc) {
   if (rc != B200RT_OK) throw std::runtime_error(std::string("b200rt status ") + std::to_string(rc) + ": " + b200rt_last_error(holder().c));
 }
