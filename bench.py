@@ -44,6 +44,7 @@ PKG = "3d_planetary_rt_model_b200"
 GRID = dict(n_rb=100, n_sb=60, n_theta=24, n_phi=16)
 FLOP_EQ_PER_EMISSION_STEP = 940.0      # 20 x (exp + div + ~14 flop), phi tabulated
 FLOP_EQ_PER_LOS_SUBSTEP = 1520.0       # 20 x (2 exp + div + ~14 flop) + extend/interp, per emission
+FLOP_EQ_PER_QUADRATIC = 65.0           # sphere / cone intersection: ~25 flop + IEEE sqrt (~14) + 1-2 IEEE divisions (~12 each)
 
 
 def load_peaks():
@@ -167,6 +168,7 @@ def run_ours(args):
         # that stdout stays the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        host_group = dist.new_group(backend="gloo")   # host-only waits (rank 0's in-process arm leaves the other GPUs idle)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
 
@@ -347,54 +349,74 @@ def run_ours(args):
         for p_ in peer_ptrs:
             ctx.ipc_close(p_)
         dist.barrier()
+    dfma = dmma = None
+    if rank == 0:
+        dfma, dmma = ctx.fp64_peaks()
+    final_S = ctx.solution(0)["S"] if rank == 0 else None
+    # every rank frees its GPU before rank 0 drives all of them from one process
+    ctx.close()
+    del flush, K_t
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist.barrier(group=host_group)          # host-side wait: no kernel spins on this GPU meanwhile
+        dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (device time from CUDA events on the ctx stream)
+    # ---- rooflines (device times from CUDA events on the ctx stream; SURVEY.md 8(d) algorithmic work per unit)
     hbm_peak, peak_kind = load_peaks()
-    dfma, dmma = ctx.fp64_peaks()
-    march_s = sum(r["march"] for r in recs) / K
-    bright_s = sum(r["brightness"] for r in recs) / K
-    traffic = None
+    fp64_peak = max(dfma, dmma)     # the FP64 pipe: the DFMA probe reads ~10 % below the DMMA probe on the same pipe
+    K = len(recs)
+    mean = lambda k: sum(r[k] for r in recs) / K
+    traffic = {}
     tj = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tj):
         traffic = json.load(open(tj))
-    steps_rank = recs[-1]["steps"]
-    substeps_rank = recs[-1]["substeps"]
-    if bright_s >= march_s:
-        n_l = max(1, recs[-1]["brightness_launches"])
-        dur = bright_s / n_l
-        flop = substeps_rank * FLOP_EQ_PER_LOS_SUBSTEP / n_l     # per sub-step, one emission
-        alg = (l1 - l0) * (6 * 8 + 4 * 8) / n_l                 # per LOS: 6 Reals in, 4 Reals out per emission
-        roof = {"kernel": "brightness_kernel<double,1>", "bound": "fp64", "achieved": flop / dur / 1e12, "peak": dfma,
-                "unit": "TFLOP/s", "frac": flop / dur / 1e12 / dfma, "peak_kind": "measured in this run (DFMA)",
-                "units_per_launch": {"los_substeps": substeps_rank / n_l, "flop_eq_per_substep": FLOP_EQ_PER_LOS_SUBSTEP},
-                "launch_ms": dur * 1e3, "traffic": (traffic or {}).get("brightness_kernel"),
-                "hbm": {"achieved": alg / dur / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg / dur / 1e9 / hbm_peak,
-                        "peak_kind": peak_kind}}
-    else:
-        n_l = max(1, recs[-1]["march_launches"])
-        dur = march_s / n_l
-        flop = steps_rank * FLOP_EQ_PER_EMISSION_STEP / n_l
-        alg = n_rows_mine * n_vox * 8 / n_l                        # K rows written once
-        roof = {"kernel": "march_kernel<double,0>", "bound": "fp64", "achieved": flop / dur / 1e12, "peak": dfma,
-                "unit": "TFLOP/s", "frac": flop / dur / 1e12 / dfma, "peak_kind": "measured in this run (DFMA)",
-                "units_per_launch": {"ray_voxel_steps": steps_rank / n_l, "flop_eq_per_step": FLOP_EQ_PER_EMISSION_STEP},
-                "launch_ms": dur * 1e3, "traffic": (traffic or {}).get("march_kernel"),
-                "hbm": {"achieved": alg / dur / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg / dur / 1e9 / hbm_peak,
-                        "peak_kind": peak_kind}}
-    roof["note"] = ("FP64-instruction bound kernels (SURVEY.md 8(d)): the binding roofline is the FP64 pipe; the HBM "
-                    "fraction under roofline.hbm is small by construction and that is the healthy reading")
+    steps_rank, substeps_rank = recs[-1]["steps"], recs[-1]["substeps"]
+    n_rays_rank = n_rows_mine * scn.n_rays + n_vox                   # voxel-origin rays + the sun-ward rays
+    quad = GRID["n_rb"] + GRID["n_sb"] - 2                           # primitives a ray is tested against
+
+    def roof(kernel, seconds, flop, alg_bytes, units, key, launches=1):
+        dur = seconds / max(1, launches)
+        return {"kernel": kernel, "bound": "fp64", "achieved": flop / seconds / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": flop / seconds / 1e12 / fp64_peak, "peak_kind": "FP64 pipe, measured in this run (max of the DFMA and DMMA probes)",
+                "frac_of_dfma_probe": flop / seconds / 1e12 / dfma, "units_per_launch": units, "launch_ms": dur * 1e3,
+                "traffic": traffic.get(key),
+                "hbm": {"achieved": alg_bytes / seconds / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / seconds / 1e9 / hbm_peak, "peak_kind": peak_kind}}
+
+    rooflines = {
+        "brightness": roof("brightness_kernel<double,1>", mean("brightness"), substeps_rank * FLOP_EQ_PER_LOS_SUBSTEP,
+                           (l1 - l0) * (6 * 8 + 4 * 8), {"los_substeps": substeps_rank, "flop_eq_per_substep": FLOP_EQ_PER_LOS_SUBSTEP},
+                           "brightness_kernel", recs[-1]["brightness_launches"]),
+        "march": roof("march_kernel<double,0>", mean("march"), steps_rank * FLOP_EQ_PER_EMISSION_STEP, n_rows_mine * n_vox * 8,
+                      {"ray_voxel_steps": steps_rank, "flop_eq_per_step": FLOP_EQ_PER_EMISSION_STEP}, "march_kernel",
+                      max(1, recs[-1]["march_launches"])),
+        # traversal: (n_rb + n_sb - 2) quadratics per ray, each ~25 flop + an IEEE sqrt (~14 FP64 instructions) and one or
+        # two IEEE divisions (~12 each): FLOP_EQ_PER_QUADRATIC; the ordering / merge is integer work on top
+        "traverse_voxel_rays": roof("traverse_fast_kernel<double,voxel rays>", mean("traverse"),
+                                    n_rays_rank * quad * FLOP_EQ_PER_QUADRATIC, steps_rank * 12.0,
+                                    {"rays": n_rays_rank, "quadratics_per_ray": quad, "flop_eq_per_quadratic": FLOP_EQ_PER_QUADRATIC},
+                                    "traverse_kernel"),
+        "traverse_los": roof("traverse_fast_kernel<double,lines of sight>", mean("los_traverse"),
+                             (l1 - l0) * quad * FLOP_EQ_PER_QUADRATIC, substeps_rank / 9.0 * 12.0,
+                             {"rays": l1 - l0, "quadratics_per_ray": quad, "flop_eq_per_quadratic": FLOP_EQ_PER_QUADRATIC}, None),
+    }
+    if t_solve > 0:
+        sv = t_solve / K
+        rooflines["solve"] = {"kernel": "block LU (gemm128 DMMA.8x8x4 + cluster Gauss-Jordan)", "bound": "fp64 tensor",
+                              "achieved": (2.0 / 3.0 * n_vox ** 3) / sv / 1e12, "peak": dmma, "unit": "TFLOP/s",
+                              "frac": (2.0 / 3.0 * n_vox ** 3) / sv / 1e12 / dmma, "peak_kind": "DMMA.8x8x4, measured in this run",
+                              "launch_ms": sv * 1e3, "traffic": traffic.get("gemm128_kernel")}
+    dominant = max(("brightness", "march", "traverse_voxel_rays", "traverse_los"), key=lambda k: rooflines[k]["launch_ms"])
+    roofl = dict(rooflines[dominant])
+    roofl["note"] = ("FP64-instruction bound kernels (SURVEY.md 8(d)): achieved = algorithmic flop-equivalents / measured time; "
+                     "ncu's executed-instruction view of the same kernel (FP64 pipe active) is in profiles/ and is lower "
+                     "(brightness 0.65): the flop-equivalent count prices exp and division at the library's instruction "
+                     "counts.  roofline.hbm is small by construction")
     fp64 = {"dfma_peak_tflops": dfma, "dmma_peak_tflops": dmma,
-            "march_flop_eq_tflops": steps_rank * FLOP_EQ_PER_EMISSION_STEP / march_s / 1e12,
-            "march_frac_of_dfma": steps_rank * FLOP_EQ_PER_EMISSION_STEP / march_s / 1e12 / dfma,
-            "brightness_flop_eq_tflops": substeps_rank * FLOP_EQ_PER_LOS_SUBSTEP / bright_s / 1e12,
-            "brightness_frac_of_dfma": substeps_rank * FLOP_EQ_PER_LOS_SUBSTEP / bright_s / 1e12 / dfma,
+            "march_flop_eq_tflops": rooflines["march"]["achieved"], "brightness_flop_eq_tflops": rooflines["brightness"]["achieved"],
             "los_substeps": substeps_rank,
-            "solve_tflops": (2.0 / 3.0 * n_vox ** 3) / (t_solve / K) / 1e12 if t_solve > 0 else None,
-            "solve_frac_of_dmma": (2.0 / 3.0 * n_vox ** 3) / (t_solve / K) / 1e12 / dmma if t_solve > 0 else None}
+            "solve_tflops": rooflines.get("solve", {}).get("achieved"), "solve_frac_of_dmma": rooflines.get("solve", {}).get("frac")}
 
     line = {"metric": "influence-matrix ray-voxel steps/s + observation LOS/s", "value": value,
             "unit": "ray-voxel steps/s", "los_per_s": los_per_s, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -404,17 +426,31 @@ def run_ours(args):
                                    f"{n_los} IUVS-like LOS brightness, n_subsamples=10",
                        "grid": GRID, "n_emissions": 1, "n_los": n_los, "ray_voxel_steps": int(steps_total),
                        "l2": "256 MB buffer written between timed iterations (L2 flush); K is 273 MB > L2",
-                       "partition": "rows by source voxel (pushed to rank 0 over peer memory while marching), LOS by index" if world > 1 else "single GPU"},
-            "phases_ms": {"influence_traverse+march": t_infl / K * 1e3, "row_exchange": t_exch / K * 1e3,
-                          "solve": t_solve / K * 1e3, "brightness_traverse+march": t_bright / K * 1e3},
+                       "partition": ("one process per GPU: rows by source voxel (pushed to rank 0 over peer memory while "
+                                     "marching), LOS by index; the in-process form of the same partition (one handle, "
+                                     "b200rt_create_multi, what observation_fit uses) is timed under in_process")
+                       if world > 1 else "single GPU"},
+            "phases_ms": {"influence_traverse+march": t_infl / K * 1e3, "influence_traverse": mean("traverse") * 1e3,
+                          "influence_march": mean("march") * 1e3, "row_exchange": t_exch / K * 1e3,
+                          "solve": t_solve / K * 1e3, "brightness_traverse+march": t_bright / K * 1e3,
+                          "los_traverse": mean("los_traverse") * 1e3, "los_order": mean("order") * 1e3,
+                          "brightness_march": mean("brightness") * 1e3, "note": "rank 0 where per-kernel"},
             "exchange_detail_ms": {"influence_call_minus_kernels": sum(r["influence_tail"] for r in recs) / K * 1e3,
                                    "barrier": sum(r["barrier"] for r in recs) / K * 1e3, "note": "rank 0"},
             "solve_gflops": fp64["solve_tflops"] * 1e3 if fp64["solve_tflops"] else None,
-            "roofline": roof, "fp64": fp64,
+            "roofline": roofl, "rooflines": rooflines, "fp64": fp64,
             "e2e": {"value": steps_total * Ke / e_infl, "unit": "ray-voxel steps/s", "los_per_s": n_los * Ke / e_bright,
                     "job_ms": e_total / Ke * 1e3, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": launches,
             "clocks": sampler.summary() if sampler else None}
+
+    # ---- the same job through ONE handle in ONE process (b200rt_create_multi: what observation_fit and the RT_grid
+    # binding use): rank 0 drives all N GPUs, host buffers in and out; the other ranks' GPUs are free by now
+    if world > 1 and not args.no_in_process:
+        try:
+            line["in_process"] = run_in_process(binding, torch, scn, tabs, (b_, T_, s_, g_), los_all, world, max(2, min(args.steps, 3)))
+        except Exception as ex:
+            line["in_process"] = {"error": str(ex)}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own source, bounded sample
     if world == 1 and not args.no_cpu_baseline:
@@ -422,43 +458,80 @@ def run_ours(args):
             from oracle import refbind
             if refbind.available("f64"):
                 R = refbind.RefModel(scn, "f64")
-                R.use_all_cores()
+                cores = R.use_all_cores()
                 tb, ns = R.build_rows(0, n_vox, args.ref_stride)
-                R.set_sourcefn(0, ctx.solution(0)["S"])
+                R.set_sourcefn(0, final_S)
                 tl, _ = R.brightness(locs[:args.ref_los], dirs[:args.ref_los], 10)
                 line["cpu_baseline"] = {"value": ns / tb, "unit": "ray-voxel steps/s", "los_per_s": args.ref_los / tl,
-                                        "cores": R.omp_threads(), "kind": "reference",
+                                        "cores": cores, "kind": "reference",
                                         "sample": f"every {args.ref_stride}th source-voxel row ({ns} steps, {tb:.1f} s) and "
                                                   f"{args.ref_los} lines of sight ({tl:.1f} s)"}
             else:
                 from oracle import oraclebind
                 O = oraclebind.OracleModel(scn, "f64")
                 tb, ns = O.build_rows(0, n_vox, args.ref_stride)
-                O.set_sourcefn(0, ctx.solution(0)["S"])
+                O.set_sourcefn(0, final_S)
                 tl, _ = O.brightness(locs[:args.ref_los], dirs[:args.ref_los], 10)
                 line["cpu_baseline"] = {"value": ns / tb, "unit": "ray-voxel steps/s", "los_per_s": args.ref_los / tl,
                                         "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"every {args.ref_stride}th source-voxel row ({ns} steps) and {args.ref_los} LOS"}
         except Exception as ex:   # the baseline is a reported number, never a reason to lose the bench line
             line["cpu_baseline"] = {"error": str(ex)}
-    # ---- the other two configs of BASELINE.json that are not part of the timed step: the Quemerais IPH
-    # background for the same number of lines of sight, and the 512-set (nH, T) sweep on grid D (N = 1 only)
-    if world == 1 and not args.no_extras:
+    # ---- the other configs of BASELINE.json that are not part of the timed step: the Quemerais IPH background for the
+    # same lines of sight (real table, LOS split over the GPUs) and the 512-set (nH, T) sweep on grid D (sets over the
+    # GPUs); at N = 1 also the multiplet emissions and the float build of the job
+    if not args.no_extras:
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import extra_bench
-            del ctx
-            ex = extra_bench.iph(n_los)
-            ex.update(extra_bench.sweep(512, 10000, 4, 1))
-            ex.update(extra_bench.multiplet(0))
-            ex.update(extra_bench.multiplet(1))
-            ex.update(extra_bench.float_job(n_los))
+            ex = extra_bench.iph(n_los, world)
+            ex.update(extra_bench.sweep(512, 10000, 4, world))
+            if world == 1:
+                ex.update(extra_bench.multiplet(0))
+                ex.update(extra_bench.multiplet(1))
+                ex.update(extra_bench.float_job(n_los))
             line["extras"] = ex
         except Exception as exn:
             line["extras"] = {"error": str(exn)}
     print(json.dumps(line))
     if world > 1:
+        dist.barrier(group=host_group)
         dist.destroy_process_group()
+
+
+def run_in_process(binding, torch, scn, tabs, scalars, los_all, n_dev, reps):
+    """source function + brightness through ONE handle over n_dev GPUs of this process, host buffers in and out"""
+    b_, T_, s_, g_ = scalars
+    ctx = binding.Context(precision=binding.F64, devices=list(range(n_dev)))
+    g = ctx.make_grid(scn.n_rb, scn.n_sb, scn.n_theta, scn.n_phi, scn.rb, scn.szamethod, scn.raymethod)
+    ctx.set_grid(g)
+    n_los = len(los_all[0])
+    los_pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in los_all]
+    out_pin = [torch.empty((1, n_los), dtype=torch.float64).pin_memory().numpy() for _ in range(4)]
+    rec = []
+    for it in range(1 + reps):
+        w0 = time.perf_counter()
+        ctx.set_singlet(0, 1, b_, T_, s_, g_, tabs)             # H2D: 8 tables, every device
+        ctx.generate_S()                                        # rows on every device -> device 0's K, solve, S to all
+        sol = ctx.solution(0)                                   # D2H: S, S0, optical depths
+        w1 = time.perf_counter()
+        ph = {k: ctx.kernel_ms(p)[0] for k, p in (("traverse", binding.PH_TRAVERSE), ("march", binding.PH_INFLUENCE),
+                                                   ("solve", binding.PH_SOLVE))}
+        steps = ctx.last_step_count()
+        out = ctx.brightness(los_pin, 10, out=out_pin)          # H2D 9 arrays / kernels / D2H 4 arrays, per device slice
+        w2 = time.perf_counter()
+        ph.update({k: ctx.kernel_ms(p)[0] for k, p in (("los_traverse", binding.PH_TRAVERSE), ("brightness", binding.PH_BRIGHTNESS))})
+        assert np.isfinite(out["brightness"]).all() and sol["S0"].max() <= 1.0
+        if it >= 1:
+            rec.append(dict(source_function_ms=(w1 - w0) * 1e3, brightness_ms=(w2 - w1) * 1e3, job_ms=(w2 - w0) * 1e3, steps=steps, **ph))
+    ctx.close()
+    m = lambda k: sum(r[k] for r in rec) / len(rec)
+    return {"n_devices": n_dev, "job_ms": m("job_ms"), "source_function_ms": m("source_function_ms"), "brightness_ms": m("brightness_ms"),
+            "value": rec[-1]["steps"] / (m("source_function_ms") * 1e-3), "unit": "ray-voxel steps/s (source function wall time incl. solve and copies)",
+            "los_per_s": n_los / (m("brightness_ms") * 1e-3),
+            "kernel_ms_slowest_device": {k: m(k) for k in ("traverse", "march", "solve", "los_traverse", "brightness")},
+            "partition": "in-process: one handle (b200rt_create_multi), rows by source voxel into device 0's K over peer "
+                         "memory, solve on device 0, S to all, LOS by index; host buffers in and out"}
 
 
 def main():
@@ -472,6 +545,7 @@ def main():
     ap.add_argument("--ref-los", type=int, default=50000, help="CPU sample: lines of sight per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the IPH and sweep measurements")
+    ap.add_argument("--no-in-process", action="store_true", help="N > 1: skip the one-handle in-process arm on rank 0")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,20 +14,37 @@ sys.path.insert(0, ROOT)
 PKG = "3d_planetary_rt_model_b200"
 
 
-def iph(n_los):
+def real_iph_table():
+    """the reference's Quemerais table (tests/golden/iph_real_table.npz holds its values); the synthetic table of
+    synth.make_iph_table where the fixture is absent"""
+    p = os.path.join(ROOT, "tests", "golden", "iph_real_table.npz")
+    if not os.path.exists(p):
+        return importlib.import_module(PKG + ".synth").make_iph_table(), "synthetic"
+    z = np.load(p)
+    tab = {k[4:]: z[k] for k in z.files if k.startswith("tab_")}
+    for k in ("kmax", "lmax", "ninf"):
+        tab[k] = int(tab[k])
+    tab["temp"] = float(tab["temp"])
+    return tab, "reference table (fsm99td12v20t80)"
+
+
+def iph(n_los, n_gpus=1):
+    """IPH background of n_los lines of sight, split over n_gpus devices of this process (one handle)"""
     synth = importlib.import_module(PKG + ".synth")
     binding = importlib.import_module(PKG + ".binding")
-    ctx = binding.Context(0, binding.F64)
-    ctx.iph_set_table(synth.make_iph_table())
+    ctx = binding.Context(0, binding.F64) if n_gpus <= 1 else binding.Context(precision=binding.F64, devices=list(range(n_gpus)))
+    tab, which = real_iph_table()
+    ctx.iph_set_table(tab)
     ra, dec = synth.random_sky(n_los)
     g, pos = synth.lyman_alpha_typical_g_factor, synth.MARS_ECLIPTIC_POS
-    ctx.iph_model(g, pos, ra[:1000], dec[:1000])                       # warm-up
+    ctx.iph_model(g, pos, ra[:1000 * max(1, n_gpus)], dec[:1000 * max(1, n_gpus)])   # warm-up
+    ctx.iph_model(g, pos, ra, dec)
     t0 = time.perf_counter()
     out = ctx.iph_model(g, pos, ra, dec)
     wall = time.perf_counter() - t0
     ms, _ = ctx.kernel_ms(binding.PH_IPH)
-    return {"iph_n_los": n_los, "iph_kernel_ms": ms, "iph_los_per_s_kernel": n_los / (ms * 1e-3),
-            "iph_los_per_s_e2e": n_los / wall, "iph_mean_kR": float(out.mean())}
+    return {"iph_n_los": n_los, "iph_n_gpus": n_gpus, "iph_table": which, "iph_kernel_ms": ms,
+            "iph_los_per_s_kernel": n_los / (ms * 1e-3), "iph_los_per_s_e2e": n_los / wall, "iph_mean_kR": float(out.mean())}
 
 
 def sweep(n_sets, n_los, contexts, gpus):
@@ -45,7 +62,7 @@ def sweep(n_sets, n_los, contexts, gpus):
     t0 = time.perf_counter()
     b = F.brightness_batch(NH, TT, contexts, gpus)
     wall = time.perf_counter() - t0
-    return {"sweep_sets": len(NH), "sweep_los_per_set": n_los, "sweep_contexts_per_gpu": contexts,
+    return {"sweep_sets": len(NH), "sweep_los_per_set": n_los, "sweep_contexts_per_gpu": contexts, "sweep_n_gpus": gpus,
             "sweep_seconds": wall, "sweep_sets_per_s": len(NH) / wall, "sweep_finite": bool(np.isfinite(b).all())}
 
 
@@ -112,7 +129,7 @@ def main():
     a = ap.parse_args()
     out = {}
     if a.iph_los > 0:
-        out.update(iph(a.iph_los))
+        out.update(iph(a.iph_los, max(1, a.gpus)))
     if a.sets > 0:
         out.update(sweep(a.sets, a.sweep_los, a.contexts, a.gpus))
     if a.multiplet:
