@@ -118,8 +118,13 @@ void observation_fit::add_observation(const vector<vector<Real>> &MSO_locations,
       loc[3 * (size_t) i + k] = MSO_locations[i].at(k);
       dir[3 * (size_t) i + k] = MSO_directions[i].at(k);
     }
+  add_observation(loc.data(), dir.data(), n);
+}
+
+void observation_fit::add_observation(const double *loc, const double *dir, int n) {
+  if (n < 0 || (n > 0 && (!loc || !dir))) throw std::invalid_argument("add_observation: bad arguments");
   for (auto &a : los) a.assign(n, 0.0);
-  int rc = b200rt_los_from_MSO(B200RT_F64, n, loc.data(), dir.data(), los[0].data(), los[1].data(), los[2].data(),
+  int rc = b200rt_los_from_MSO(B200RT_F64, n, loc, dir, los[0].data(), los[1].data(), los[2].data(),
                                los[3].data(), los[4].data(), los[5].data(), los[6].data(), los[7].data(), los[8].data());
   if (rc != B200RT_OK) throw std::runtime_error("b200rt_los_from_MSO failed");
   for (singlet_model *m : {H, D, H_pp, D_pp})

@@ -51,6 +51,9 @@ public:
 
   void add_observation(const std::vector<std::vector<Real>> &MSO_locations,
                        const std::vector<std::vector<Real>> &MSO_directions);
+  // the same from flat [n][3] arrays: what a buffer-protocol caller (the Cython fast path, host/py_corona_sim_b200.pyx)
+  // hands over without building 2 n small vectors
+  void add_observation(const double *MSO_locations, const double *MSO_directions, int n);
   void get_unextincted_iph();
   void set_g_factor(std::vector<Real> &g);
   void simulate_iph(const bool sim_iphh);

@@ -156,6 +156,13 @@ def cuda_array(ptr, shape, dtype="<f8"):
 
 
 def run_ours(args):
+    # stdout carries exactly one JSON line: everything a library prints there (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     import torch
     import torch.distributed as dist
 
@@ -493,7 +500,7 @@ def run_ours(args):
             line["extras"] = ex
         except Exception as exn:
             line["extras"] = {"error": str(exn)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier(group=host_group)
         dist.destroy_process_group()

@@ -22,16 +22,24 @@ PKG = os.path.join(ROOT, "3d_planetary_rt_model_b200")
 MODULE = "py_corona_sim_gpu"
 
 
-def build(verbose=True):
-    if not os.path.exists(PYX):
-        raise FileNotFoundError(PYX)
+FAST_PYX = os.path.join(PKG, "host", "py_corona_sim_b200.pyx")
+FAST_OUT = os.path.join(HERE, "_ref", "py_corona_sim_fast")
+
+
+def build(verbose=True, fast=False):
+    """fast=False: the reference's .pyx unchanged.  fast=True: host/py_corona_sim_b200.pyx, which INCLUDES the reference's
+    .pyx from the reference tree (Cython include path) and adds the buffer-protocol / nogil subclass; same module name
+    (the reference's __cinit__ locates the IPH table through it), its own output directory."""
+    PYX, OUT = (FAST_PYX, FAST_OUT) if fast else (globals()["PYX"], globals()["OUT"])
+    if not os.path.exists(globals()["PYX"]):
+        raise FileNotFoundError(globals()["PYX"])
     import numpy
     from Cython.Compiler.Main import CompilationOptions, default_options, compile as cy_compile
     os.makedirs(OUT, exist_ok=True)
     cpp = os.path.join(OUT, MODULE + ".cpp")
     so = os.path.join(OUT, MODULE + sysconfig.get_config_var("EXT_SUFFIX"))
-    deps = [PYX, os.path.join(PKG, "host", "observation_fit.hpp"), os.path.join(PKG, "host", "atmosphere.hpp"),
-            os.path.join(PKG, "libb200rt_host.so"), __file__]
+    deps = [PYX, globals()["PYX"], os.path.join(PKG, "host", "observation_fit.hpp"), os.path.join(PKG, "host", "atmosphere.hpp"),
+            os.path.join(PKG, "host", "fast_binding.hpp"), os.path.join(PKG, "libb200rt_host.so"), __file__]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return so
     try:
@@ -39,6 +47,7 @@ def build(verbose=True):
     except Exception:
         git_hash = ""
     opts = CompilationOptions(default_options, cplus=True, language_level=3, output_file=cpp,
+                              include_path=[os.path.join(REF, "python")],
                               compile_time_env={"RT_FLOAT": False, "CPP_GIT_HASH": "b200rt-" + (git_hash or "unknown")})
     res = cy_compile(PYX, opts, full_module_name=MODULE)
     if res.num_errors:
@@ -58,3 +67,4 @@ def build(verbose=True):
 
 if __name__ == "__main__":
     print(build())
+    print(build(fast=True))
