@@ -28,7 +28,8 @@ inline int n_obs(const observation_fit *o) { return o->n_obs(); }
 
 // which: 0 brightness, 1 species_col_dens, 2 tau_species_final, 3 tau_absorber_final, 4 iph_brightness_observed,
 // 5 iph_brightness_unextincted, 6 D_brightness, 7 D_col_dens, 8 tau_D_final -> rows of the result, out[rows][n_obs]
-// (out may be null to ask for the row count only).  The IPH getters of the reference are [n_obs][n_emissions]: kept.
+// (every getter of the reference is [n_emissions][n_obs], observation_fit.cpp:491-575; out may be null to ask for the
+// row count only)
 inline int fetch(observation_fit *o, int which, double *out) {
   std::vector<std::vector<double>> v;
   switch (which) {
@@ -48,8 +49,6 @@ inline int fetch(observation_fit *o, int which, double *out) {
   }
   return (int) v.size();
 }
-inline int fetch_cols(observation_fit *o, int which) {   // length of one row of fetch(which)
-  return (which == 4 || which == 5) ? observation_fit::n_hydrogen_emissions : o->n_obs();
-}
+inline int fetch_cols(observation_fit *o, int) { return o->n_obs(); }   // length of one row of fetch(which)
 
 }  // namespace b200_fast

@@ -366,6 +366,9 @@ void observation_fit::model_brightness(singlet_model &m) {
   if (!m.have_S) throw std::runtime_error("observation_fit: generate a source function before asking for brightness");
   if (n_obs() == 0) throw std::runtime_error("there must be at least one observation to simulate");
   if (m.brightness_done) return;
+  if (sim_iph && (int) iph_unextincted.size() != n_obs())
+    throw std::runtime_error("observation_fit: the IPH coordinates belong to an earlier set of observations "
+                             "(call add_observation_ra_dec after add_observation, or simulate_iph(false))");
   run_brightness(m.ctx, !m.los_uploaded, m.out_q);
   m.los_uploaded = true;
   m.iph_observed.assign(n_obs(), vector<Real>(n_hydrogen_emissions, 0.0));

@@ -70,7 +70,7 @@ cdef class Pyobservation_fit_b200(Pyobservation_fit):
     cdef _fetch(self, int which):
         cdef int rows
         cdef int cols = b200_fetch_cols(self.thisptr, which)
-        cdef int n_rows = b200_n_obs(self.thisptr) if which in (4, 5) else 2     # IPH getters are [n_obs][n_emissions]
+        cdef int n_rows = 2                                                       # every getter is [n_emissions][n_obs]
         out = np.empty((max(n_rows, 1), max(cols, 1)), dtype=np.float64)
         cdef double[:, ::1] O = out
         with nogil:

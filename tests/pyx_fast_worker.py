@@ -42,6 +42,7 @@ out["iph_equal"] = bool(np.array_equal(np.asarray(slow.iph_brightness_unextincte
 out["iph_shape"] = list(fast.iph_brightness_unextincted().shape)
 
 # the GIL is released: a Python thread makes progress while generate_source_function + brightness run
+fast.simulate_iph(False)              # the IPH coordinates above belong to the smaller set
 fast.add_observation(locs, dirs)
 ticks, stop = [0], [False]
 

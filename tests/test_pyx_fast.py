@@ -41,7 +41,7 @@ def test_fast_binding_on_the_device():
     assert r.returncode == 0, r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
     out = json.loads(line[len("RESULT "):])
-    assert out["brightness_shape"] == [2, 20000] and out["iph_shape"] == [20000, 2]
+    assert out["brightness_shape"] == [2, 20000] and out["iph_shape"] == [2, 20000]
     assert out["brightness_max_rel"] < 1e-12 and out["col_dens_max_rel"] < 1e-12 and out["iph_equal"] and out["finite"]
     # ingest: the reference binding's Python loops cost seconds per 1e6 lines of sight; the buffer path tens of ms
     assert out["add_observation_s_per_1e6_fast_binding"] < 0.25
