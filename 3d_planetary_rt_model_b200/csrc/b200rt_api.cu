@@ -118,9 +118,12 @@ long long batch_capacity(b200rt_ctx *c, size_t real_bytes) {
 }
 
 int check_overflow(b200rt_ctx *c) {
-  int flag = 0;
-  B200RT_CUDA(c, cudaMemcpyAsync(&flag, c->work_counter.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, c->host_words.ensure(4 * sizeof(unsigned long long)));
+  int *flag_p = c->host_words.as<int>();
+  *flag_p = 0;
+  B200RT_CUDA(c, cudaMemcpyAsync(flag_p, c->work_counter.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int flag = *flag_p;
   if (flag)
     return fail(c, B200RT_ERR_CAPACITY, "a ray crossed more than 2*n_rb+n_sb boundaries (crossing list capacity)");
   return B200RT_OK;
@@ -256,9 +259,11 @@ int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges
       DBG(c, "single scattering march");
     }
   }
-  unsigned long long steps = 0;
-  B200RT_CUDA(c, cudaMemcpyAsync(&steps, c->step_counter.p, sizeof(steps), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, c->host_words.ensure(4 * sizeof(unsigned long long)));
+  unsigned long long *steps_p = c->host_words.as<unsigned long long>() + 1;
+  B200RT_CUDA(c, cudaMemcpyAsync(steps_p, c->step_counter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   const int rc_overflow = check_overflow(c);   // synchronises
+  const unsigned long long steps = *steps_p;
   if (pushing) B200RT_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the rows have landed on the solving GPU
   if (rc_overflow) return rc_overflow;
   PhaseTimer::collect(c);
@@ -332,6 +337,24 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
   B200RT_CUDA(c, c->los_out.ensure((size_t) c->n_em * 4 * n * sizeof(Real)));
   B200RT_CUDA(c, c->los_order.ensure(((size_t) per_batch + 2 * (size_t) (c->hg.cap + 1)) * sizeof(int)));
   const Real *li = c->los_in.as<Real>();
+  // Results for PAGEABLE caller arrays are downloaded into page-locked scratch and copied out after the stream has
+  // drained: a device-to-host copy into pageable memory blocks inside the runtime until the kernels before it have
+  // finished, holding a lock that stalls every other context of the process (the sweep's contexts ran their brightness
+  // calls one after the other because of it).  Page-locked caller arrays (the bench's) are written directly.
+  double *stage_out = nullptr;
+  if (io) {
+    bool pageable = false;
+    for (int q = 0; q < 4 && !pageable; q++)
+      if (io->dst[q]) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, io->dst[q]) != cudaSuccess) { cudaGetLastError(); pageable = true; }
+        else pageable = (at.type == cudaMemoryTypeUnregistered);
+      }
+    if (pageable) {
+      B200RT_CUDA(c, c->host_out.ensure((size_t) c->n_em * 4 * n * sizeof(double)));
+      stage_out = c->host_out.as<double>();
+    }
+  }
   std::vector<cudaEvent_t> io_events;
   struct EventGuard {
     std::vector<cudaEvent_t> &v;
@@ -413,16 +436,25 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
       for (int e = 0; e < c->n_em; e++)
         for (int q = 0; q < 4; q++)
           if (io->dst[q])
-            B200RT_CUDA(c, cudaMemcpyAsync(io->dst[q] + (size_t) e * io->out_stride + io->out_offset + first,
+            B200RT_CUDA(c, cudaMemcpyAsync(stage_out ? stage_out + ((size_t) e * 4 + q) * n + first
+                                                     : io->dst[q] + (size_t) e * io->out_stride + io->out_offset + first,
                                            c->los_out.as<double>() + ((size_t) e * 4 + q) * n + first,
                                            (size_t) count * sizeof(double), cudaMemcpyDeviceToHost, c->out_stream));
     }
   }
-  unsigned long long substeps = 0;
-  B200RT_CUDA(c, cudaMemcpyAsync(&substeps, c->step_counter.p, sizeof(substeps), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, c->host_words.ensure(4 * sizeof(unsigned long long)));
+  unsigned long long *substeps_p = c->host_words.as<unsigned long long>() + 1;
+  B200RT_CUDA(c, cudaMemcpyAsync(substeps_p, c->step_counter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   const int rc_overflow = check_overflow(c);
+  const unsigned long long substeps = *substeps_p;
   if (io) B200RT_CUDA(c, cudaStreamSynchronize(c->out_stream));   // nothing is in flight into the caller's arrays at return
   if (rc_overflow) return rc_overflow;
+  if (stage_out)
+    for (int e = 0; e < c->n_em; e++)
+      for (int q = 0; q < 4; q++)
+        if (io->dst[q])
+          std::memcpy(io->dst[q] + (size_t) e * io->out_stride + io->out_offset, stage_out + ((size_t) e * 4 + q) * n,
+                      (size_t) n * sizeof(double));
   PhaseTimer::collect(c);
   c->last_substeps = (long long) substeps;
   c->los_done = true;
@@ -684,9 +716,11 @@ int mult_influence_impl(b200rt_ctx *c, int v_begin, int v_end) {
       DBG(c, "multiplet single scattering");
     }
   }
-  unsigned long long steps = 0;
-  B200RT_CUDA(c, cudaMemcpyAsync(&steps, c->step_counter.p, sizeof(steps), cudaMemcpyDeviceToHost, c->stream));
+  B200RT_CUDA(c, c->host_words.ensure(4 * sizeof(unsigned long long)));
+  unsigned long long *steps_p = c->host_words.as<unsigned long long>() + 1;
+  B200RT_CUDA(c, cudaMemcpyAsync(steps_p, c->step_counter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   if (int rc = check_overflow(c)) return rc;
+  const unsigned long long steps = *steps_p;
   PhaseTimer::collect(c);
   c->last_steps = (long long) steps;
   M.have_K = true; M.have_S = false;
@@ -871,6 +905,9 @@ int b200rt_destroy(b200rt_ctx *c) {
                     &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->los_order, &c->lu, &c->lu_dinv, &c->lu_flag,
                     &c->iph.dev, &c->iph.io, &c->vox_map, &c->sph_table};
   for (DevBuf *b : bufs) b->release();
+  c->host_scratch.release();
+  c->host_words.release();
+  c->host_out.release();
   for (int e = 0; e < MAX_EMISSIONS; e++) {
     Emission &E = c->em[e];
     DevBuf *eb[] = {&E.tabs, &E.phi, &E.mrec, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real, &E.rec_pt, &E.rec_avg};

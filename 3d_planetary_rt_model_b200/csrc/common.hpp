@@ -30,6 +30,25 @@ struct DevBuf {
   template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
+// page-locked host scratch for the small read-backs of a call (row margins, residuals, counters, flags).  A copy into
+// PAGEABLE memory makes the runtime wait for the stream inside the call, holding a lock that stalls the launches of
+// every other context of the process: measured on the 40x20 sweep, four contexts ran their solves strictly one after
+// the other (1.2e3 solves/s with 1, 2 or 4 threads) until these read-backs went through page-locked memory.
+struct PinnedBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes && p) return cudaSuccess;
+    if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+    if (need < 4096) need = 4096;
+    cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
 // ------------------------------------------------------------------ grid tables (device view)
 // Everything the traversal, the interpolation and the ray construction read.
 // All of it is computed on the host (grid_host.cpp) with the libm calls the
@@ -198,6 +217,9 @@ struct b200rt_ctx {
   long long batch_rays = 0;
   b200rt::DevBuf work_counter;      // 2 ints: dynamic work index, capacity-overflow flag
   b200rt::DevBuf step_counter;      // unsigned long long
+  b200rt::PinnedBuf host_scratch;   // solve read-backs (margins, residuals)
+  b200rt::PinnedBuf host_out;       // brightness results on their way to PAGEABLE caller arrays (b200rt_brightness)
+  b200rt::PinnedBuf host_words;     // counters and flags: [0] overflow flag (int), [1] step / sub-step counter (u64)
   long long last_steps = 0;
   long long last_substeps = 0;      // line-of-sight sub-steps of the last singlet brightness call
 

@@ -814,8 +814,10 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   prepare_kernel<<<np, 256, 0, st>>>(K, n, np, branching, S0, A, b, margin);
   launches++;
   B200RT_CUDA(c, cudaGetLastError());
-  std::vector<double> hm(np);
-  B200RT_CUDA(c, cudaMemcpyAsync(hm.data(), margin, np * sizeof(double), cudaMemcpyDeviceToHost, st));
+  // read-backs go through page-locked scratch (common.hpp, PinnedBuf): hm = margins [np], then hy / hr / hs0 [n] each
+  B200RT_CUDA(c, c->host_scratch.ensure(4 * (size_t) np * sizeof(double)));
+  double *hm = c->host_scratch.as<double>(), *hy = hm + np, *hr = hy + np, *hs0 = hr + np;
+  B200RT_CUDA(c, cudaMemcpyAsync(hm, margin, np * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200RT_CUDA(c, cudaStreamSynchronize(st));
   // NaN-safe: std::min / std::max drop a NaN operand, so a non-finite margin is tested for explicitly (a NaN row must
   // fail the dominance test AND the certificate, never slip through them)
@@ -837,8 +839,9 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     // matrix row dominant).  x / rabs / margin are free at this point and serve as scratch.
     bool certified = false;
     double kmin = 0, ymax = 1e300;
-    std::vector<double> hy(n, 1.0);
-    B200RT_CUDA(c, cudaMemcpyAsync(x, hy.data(), n * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < n; i++) hy[i] = 1.0;
+    B200RT_CUDA(c, cudaMemcpyAsync(x, hy, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    B200RT_CUDA(c, cudaStreamSynchronize(st));     // hy is read back into below
     double *ya = x, *yb = rabs;
     const int max_iter = 2048;
     for (int it = 0; it < max_iter && !certified; it++) {
@@ -846,7 +849,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
       launches++;
       std::swap(ya, yb);
       if (it == 0) {
-        B200RT_CUDA(c, cudaMemcpyAsync(hm.data(), margin, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        B200RT_CUDA(c, cudaMemcpyAsync(hm, margin, n * sizeof(double), cudaMemcpyDeviceToHost, st));
         B200RT_CUDA(c, cudaStreamSynchronize(st));
         for (int i = 0; i < n; i++) {
           if (!std::isfinite(hm[i])) { kmin = -INFINITY; break; }
@@ -855,7 +858,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
         if (!(kmin >= 0.0) || !(branching >= 0.0)) break;
       }
       if ((it & 7) == 7 || it == 0) {
-        B200RT_CUDA(c, cudaMemcpyAsync(hy.data(), ya, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        B200RT_CUDA(c, cudaMemcpyAsync(hy, ya, n * sizeof(double), cudaMemcpyDeviceToHost, st));
         B200RT_CUDA(c, cudaStreamSynchronize(st));
         ymax = 0;
         for (int i = 0; i < n; i++) {
@@ -1031,9 +1034,8 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   residual_kernel<<<(n + 7) / 8, 256, 0, st>>>(K, n, branching, S0, S, rabs);
   launches++;
   B200RT_CUDA(c, cudaGetLastError());
-  std::vector<double> hr(n), hs0(n);
-  B200RT_CUDA(c, cudaMemcpyAsync(hr.data(), rabs, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-  B200RT_CUDA(c, cudaMemcpyAsync(hs0.data(), S0, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200RT_CUDA(c, cudaMemcpyAsync(hr, rabs, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B200RT_CUDA(c, cudaMemcpyAsync(hs0, S0, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   B200RT_CUDA(c, cudaStreamSynchronize(st));
   if (trace && !marks.empty()) {
     cudaStreamSynchronize(sB);
