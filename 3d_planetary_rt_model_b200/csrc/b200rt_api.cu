@@ -926,6 +926,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   if (c->out_stream) cudaStreamDestroy(c->out_stream);
   if (c->ev_rows) cudaEventDestroy(c->ev_rows);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
   cudaStreamDestroy(c->stream);
   delete c;
   return B200RT_OK;

@@ -232,7 +232,8 @@ struct b200rt_ctx {
 
   // dense solve workspace
   b200rt::DevBuf lu, lu_dinv, lu_flag;
-  cudaStream_t stream2 = nullptr;            // look-ahead stream of the LU
+  cudaStream_t stream2 = nullptr;            // chain stream of the LU (diagonal-block inverse + panel), high priority
+  cudaStream_t stream3 = nullptr;            // stream of the L-shaped update next to the diagonal, high priority
   std::vector<cudaEvent_t> lu_events;
   cudaGraphExec_t lu_graph = nullptr;        // the factorisation + back substitution of one (np, workspace), replayed
   int lu_graph_np = 0, lu_graph_launches = 0;

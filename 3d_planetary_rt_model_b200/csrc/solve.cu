@@ -889,6 +889,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
   B200RT_CUDA(c, cudaFuncSetAttribute(backsolve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (TB * TB * sizeof(double))));
   const int quarter_below = 36;      // block columns left: (2 m1 - 1) x 4 CTAs <= 2 per SM
+  static const int beside_above = getenv("B200RT_LU_BESIDE_ABOVE") ? atoi(getenv("B200RT_LU_BESIDE_ABOVE")) : (1 << 30);
 
   // second stream + events for the look-ahead
   if (!c->stream2) {   // the chain is the critical path: give its stream the highest priority
@@ -896,12 +897,17 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     B200RT_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     B200RT_CUDA(c, cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi));
   }
-  while ((int) c->lu_events.size() < 2 * nK + 1) {
+  while ((int) c->lu_events.size() < 3 * nK + 2) {
     cudaEvent_t ev;
     B200RT_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     c->lu_events.push_back(ev);
   }
-  cudaStream_t sB = c->stream2;
+  if (!c->stream3) {
+    int lo = 0, hi = 0;
+    B200RT_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B200RT_CUDA(c, cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, hi));
+  }
+  cudaStream_t sB = c->stream2, sU = c->stream3;
   const int launches_before = launches;
   // B200RT_SOLVE_TRACE=1: timestamp every chain / update of the factorisation (development aid)
   static const bool trace = getenv("B200RT_SOLVE_TRACE") != nullptr;
@@ -953,41 +959,59 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   // of short kernels, and the graph removes the host launch gaps between them.
   auto record = [&]() -> cudaError_t {
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
-    cudaEvent_t ev_start = c->lu_events[2 * nK];
+    // Three streams.  sB (high priority): the chain -- diagonal-block inverse + panel of block column KB+1.  sU (high
+    // priority): the L-shaped update next to the diagonal that the chain waits for.  st: right-hand side + the bulk update.
+    // The bulk update of block column KB needs only the panel of KB (evP[KB]), so it COULD run beside the L-shaped update
+    // of KB (which, alone on the machine, costs 20-33 us of every bulk-bound step: tools/dev/solve_trace.py) -- measured,
+    // it must not: with the bulk update's CTAs resident (two per SM, the whole register file) the L-shaped update and
+    // the cluster launch of the next inverse wait for SMs to drain, and the solve goes 6.36 -> 7.13 ms, monotonically in
+    // the number of block columns handled that way (B200RT_LU_BESIDE_ABOVE, tools/dev/README.md).  Default: never.
+    // Events: evP[KB] = lu_events[3 KB] (panel of KB ready), evU[KB] = [3 KB + 1] (L-shaped update of KB done),
+    // evB[KB] = [3 KB + 2] (bulk update + right-hand side of KB done).
+    cudaEvent_t ev_start = c->lu_events[3 * nK];
     CK(cudaEventRecord(ev_start, st));
     CK(cudaStreamWaitEvent(sB, ev_start, 0));
+    CK(cudaStreamWaitEvent(sU, ev_start, 0));
     mark("start", 0, st);
     mark("chain_begin", 0, sB);
     chain(0, sB);
     mark("chain_end", 0, sB);
     CK(cudaEventRecord(c->lu_events[0], sB));            // evP[0]
     for (int KB = 0; KB < nK; KB++) {
-      CK(cudaStreamWaitEvent(st, c->lu_events[2 * KB], 0)); // block column KB factored
       const int m1 = nK - KB - 1;                                       // block columns after KB
       if (m1 > 0) {
-        mark("ui_begin", KB, st);
-        if (m1 <= quarter_below) gemm128_kernel<0, 2><<<dim3(2 * m1 - 1, 4), 256, gemm_smem_q, st>>>(A, np, KB, dinv, Lbuf(KB));
-        else gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, st>>>(A, np, KB, dinv, Lbuf(KB));
-        mark("ui_end", KB, st);
+        // L-shaped update: block column KB+1 from the diagonal down, block row KB+1 right of it.  Its tiles were last
+        // written by the bulk update of KB-1; its L panel buffer is the one chain KB+1 will overwrite afterwards.
+        CK(cudaStreamWaitEvent(sU, c->lu_events[3 * KB], 0));
+        if (KB > 0) CK(cudaStreamWaitEvent(sU, c->lu_events[3 * (KB - 1) + 2], 0));
+        mark("ui_begin", KB, sU);
+        if (m1 <= quarter_below) gemm128_kernel<0, 2><<<dim3(2 * m1 - 1, 4), 256, gemm_smem_q, sU>>>(A, np, KB, dinv, Lbuf(KB));
+        else gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, sU>>>(A, np, KB, dinv, Lbuf(KB));
+        mark("ui_end", KB, sU);
         launches++;
-        CK(cudaEventRecord(c->lu_events[2 * KB + 1], st));  // evU[KB]
-        CK(cudaStreamWaitEvent(sB, c->lu_events[2 * KB + 1], 0));
-        // forward substitution of the right-hand side: off the critical path (the next chain does not need it), on
-        // the update stream, in block-column order
-        rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, st>>>(Lbuf(KB), np, KB, b);
-        launches++;
+        CK(cudaEventRecord(c->lu_events[3 * KB + 1], sU));  // evU[KB]
+        CK(cudaStreamWaitEvent(sB, c->lu_events[3 * KB + 1], 0));
         mark("chain_begin", KB + 1, sB);
         chain(KB + 1, sB);
         mark("chain_end", KB + 1, sB);
-        CK(cudaEventRecord(c->lu_events[2 * KB + 2], sB));  // evP[KB+1]
+        CK(cudaEventRecord(c->lu_events[3 * KB + 3], sB));  // evP[KB+1]
+        // right-hand side and bulk update of KB: beside the two above while the bulk update is the longer leg; once the
+        // trailing matrix is small the chain is the critical path and the bulk update queues behind the L-shaped update
+        CK(cudaStreamWaitEvent(st, c->lu_events[3 * KB + (m1 > beside_above ? 0 : 1)], 0));
+        rhs128_kernel<<<(m1 * TB + 7) / 8, 256, 0, st>>>(Lbuf(KB), np, KB, b);
+        launches++;
         const int m2 = m1 - 1;
         if (m2 > 0) {
           gemm128_kernel<1, 4, KC_BULK, STAGES_BULK><<<dim3(m2 * m2, 2), 256, gemm_smem, st>>>(A, np, KB, dinv, Lbuf(KB));
           mark("uii_end", KB, st);
           launches++;
         }
+        CK(cudaEventRecord(c->lu_events[3 * KB + 2], st));  // evB[KB]
       }
     }
+    CK(cudaStreamWaitEvent(st, c->lu_events[3 * (nK - 1)], 0));   // the last diagonal block is inverted: join the chain
+    CK(cudaEventRecord(c->lu_events[3 * nK + 1], sU));              // ... and the update stream (a capture must be rejoined)
+    CK(cudaStreamWaitEvent(st, c->lu_events[3 * nK + 1], 0));
     mark("factor_end", 0, st);
     if (nK <= NUM_SMS) {     // every CTA resident at once: the fused back substitution
       CK(cudaMemsetAsync(flags, 0, nK * sizeof(int), st));
