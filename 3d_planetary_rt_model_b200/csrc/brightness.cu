@@ -123,8 +123,11 @@ template <> struct LineShape<float> {
   }
 };
 
+#ifndef BR_MIN_BLOCKS
+#define BR_MIN_BLOCKS 4
+#endif
 template <class Real, int NEM>
-__global__ void __launch_bounds__(128, (NEM == 2 && sizeof(Real) == 8) ? 3 : 4)
+__global__ void __launch_bounds__(128, (NEM == 2 && sizeof(Real) == 8) ? 3 : BR_MIN_BLOCKS)
 brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> em1,
                   const Real *__restrict__ los_in, long long los_stride, long long first, long long count,
                   ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total,
@@ -387,7 +390,7 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
   const size_t smem = GeomTables<Real>::doubles(g.n_rb, g.n_sb) * sizeof(Real);
   const long long groups = (count + 0);
   long long blocks = (groups * LPR + threads - 1) / threads;
-  const long long persistent = (long long) NUM_SMS * 4;   // __launch_bounds__(128, 4)
+  const long long persistent = (long long) NUM_SMS * BR_MIN_BLOCKS;   // __launch_bounds__(128, BR_MIN_BLOCKS)
   if (blocks > persistent) blocks = persistent;
   if (n_em == 1) {
     e = cudaFuncSetAttribute(brightness_kernel<Real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

@@ -494,7 +494,11 @@ rhs128_kernel(const double *__restrict__ Lbuf, int np, int KB, double *__restric
 constexpr int TM = 128, TN = 128, TK = 128;
 constexpr int KC_DEFAULT = 16;         // k-chunk per pipeline stage
 constexpr int STAGES_DEFAULT = 4;
-constexpr int KC_BULK = 8, STAGES_BULK = 4;
+#ifndef KC_BULK_V
+#define KC_BULK_V 8
+#define STAGES_BULK_V 4
+#endif
+constexpr int KC_BULK = KC_BULK_V, STAGES_BULK = STAGES_BULK_V;
 constexpr size_t gemm_smem_bytes(int kc, int stages, int tn) { return (size_t) stages * (TM * (kc + 4) + kc * (tn + 4)) * sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {

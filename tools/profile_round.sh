@@ -10,8 +10,12 @@ $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain
 tail -c 600 $OUT/plain_$TAG.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
-for K in ${KERNELS:-brightness_kernel march_kernel traverse_kernel gemm128_kernel}; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -f -o $OUT/prof_${K}_$TAG $CMD > $OUT/ncu_${K}_$TAG.log 2>&1
+# name -> kernel regex (the voxel-ray and the line-of-sight instantiations of the traversal are captured separately)
+# ncu matches -k against the function name without template arguments unless --kernel-name-base demangled is given
+declare -A RX=( [brightness_kernel]="brightness_kernel" [march_kernel]="march_kernel" [traverse_kernel]="traverse_fast_kernel<double, .bool.1"
+                [traverse_los]="traverse_fast_kernel<double, .bool.0" [gemm128_kernel]="gemm128_kernel<.int.1, " )
+for K in ${KERNELS:-brightness_kernel march_kernel traverse_kernel traverse_los gemm128_kernel}; do
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:${RX[$K]}" -c 1 -f -o $OUT/prof_${K}_$TAG $CMD > $OUT/ncu_${K}_$TAG.log 2>&1
   echo "$K rc=$?"
 done
 ls -la $OUT | head -30
