@@ -492,12 +492,22 @@ rhs128_kernel(const double *__restrict__ Lbuf, int np, int KB, double *__restric
 
 // ---- 128x128x128 tile products on the FP64 tensor pipe
 constexpr int TM = 128, TN = 128, TK = 128;
-constexpr int KC_DEFAULT = 16;         // k-chunk per pipeline stage
-constexpr int STAGES_DEFAULT = 4;
+// Pipeline shapes (overridable for experiments).  Measured on the n = 5841 solve of the bench (ms; first pair = bulk
+// update, second = the chain's panel / L-shaped update kernels, (k-chunk, cp.async stages)):
+//   (8,4)+(16,4) 6.35   (8,3)+(16,4) 5.98   (8,2) 6.36   (16,3) 6.34   (16,2) 6.21   (8,6) 6.70
+//   (8,3)+(16,3) 5.90   (8,3)+(16,2) 5.88   (8,3)+(32,2) 5.97
+// A shorter pipeline fill per tile beats deeper prefetch: the bulk update has two CTAs per SM covering each other's load
+// latency, and the chain kernels are latency-bound tiles whose first DMMA waits for STAGES-1 chunks.
 #ifndef KC_BULK_V
 #define KC_BULK_V 8
-#define STAGES_BULK_V 4
+#define STAGES_BULK_V 3
 #endif
+#ifndef KC_CHAIN_V
+#define KC_CHAIN_V 16
+#define STAGES_CHAIN_V 2
+#endif
+constexpr int KC_DEFAULT = KC_CHAIN_V;         // k-chunk per pipeline stage (must be a multiple of 16 for the quarter tiles)
+constexpr int STAGES_DEFAULT = STAGES_CHAIN_V;
 constexpr int KC_BULK = KC_BULK_V, STAGES_BULK = STAGES_BULK_V;
 constexpr size_t gemm_smem_bytes(int kc, int stages, int tn) { return (size_t) stages * (TM * (kc + 4) + kc * (tn + 4)) * sizeof(double); }
 
