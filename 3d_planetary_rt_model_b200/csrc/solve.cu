@@ -902,7 +902,10 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
   B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
   B200RT_CUDA(c, cudaFuncSetAttribute(backsolve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (TB * TB * sizeof(double))));
-  const int quarter_below = 36;      // block columns left: (2 m1 - 1) x 4 CTAs <= 2 per SM
+  static const int quarter_below = getenv("B200RT_LU_QUARTER_BELOW") ? atoi(getenv("B200RT_LU_QUARTER_BELOW")) : 1024;
+  // (quarter-width tiles for the chain kernels whenever fewer block columns than this remain.  Measured, n = 5841:
+  //  never 6.15 ms, below 20: 5.94, below 36: 5.88, always: 5.80 -- with 58 kB of shared memory per CTA several quarter
+  //  tiles share an SM, and 2 (2 m1 - 1) half tiles left a second, nearly empty wave)
   static const int beside_above = getenv("B200RT_LU_BESIDE_ABOVE") ? atoi(getenv("B200RT_LU_BESIDE_ABOVE")) : (1 << 30);
 
   // second stream + events for the look-ahead
