@@ -518,9 +518,10 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// MODE 0: update, the L-shaped set of tiles next to the diagonal (block column KB+1 from the diagonal
-//         down, block row KB+1 right of the diagonal) -- what the next chain needs:  C -= L21 * A12
-// MODE 1: update, the square (i, j >= KB+2)
+// MODE 0: update, block column KB+1 from the diagonal down -- what the next chain needs:  C -= L21 * A12.  (With
+//         gridDim.x = 2 m1 - 1 it also covers block row KB+1 right of the diagonal; the factorisation launches m1
+//         blocks: that row is only read by the updates of the NEXT block column, so it rides with the bulk update)
+// MODE 1: update, the rest: block rows i >= KB+1, block columns j >= KB+2
 // MODE 2: panel,  tile (KB+1+blockIdx.x, KB):  L21 = A21 * A_KK^-1 -> Lbuf[row][0..127] (the L panels live in
 //         a double-buffered side array: the updates of block column KB read one half while chain KB+1 fills the other)
 // NT = DMMA n-tiles per warp: 8 -> 128x128 output tile per CTA (bulk update), 4 -> 128x64 (the two
@@ -543,9 +544,9 @@ gemm128_kernel(double *__restrict__ A, int np, int KB, const double *__restrict_
     const int ncol = nB - KB - 1;
     if ((int) blockIdx.x < ncol) { ti = KB + 1 + blockIdx.x; tj = KB + 1; }
     else { ti = KB + 1; tj = KB + 2 + (blockIdx.x - ncol); }
-  } else if (MODE == 1) {
+  } else if (MODE == 1) {      // rows from KB+1 (the block row next to the diagonal is not on the critical path), columns from KB+2
     const int m = nB - KB - 2;
-    ti = KB + 2 + blockIdx.x / m;
+    ti = KB + 1 + blockIdx.x / m;
     tj = KB + 2 + blockIdx.x % m;
   } else {
     ti = KB + 1 + blockIdx.x;
@@ -1002,8 +1003,8 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
         CK(cudaStreamWaitEvent(sU, c->lu_events[3 * KB], 0));
         if (KB > 0) CK(cudaStreamWaitEvent(sU, c->lu_events[3 * (KB - 1) + 2], 0));
         mark("ui_begin", KB, sU);
-        if (m1 <= quarter_below) gemm128_kernel<0, 2><<<dim3(2 * m1 - 1, 4), 256, gemm_smem_q, sU>>>(A, np, KB, dinv, Lbuf(KB));
-        else gemm128_kernel<0, 4><<<dim3(2 * m1 - 1, 2), 256, gemm_smem_h, sU>>>(A, np, KB, dinv, Lbuf(KB));
+        if (m1 <= quarter_below) gemm128_kernel<0, 2><<<dim3(m1, 4), 256, gemm_smem_q, sU>>>(A, np, KB, dinv, Lbuf(KB));
+        else gemm128_kernel<0, 4><<<dim3(m1, 2), 256, gemm_smem_h, sU>>>(A, np, KB, dinv, Lbuf(KB));
         mark("ui_end", KB, sU);
         launches++;
         CK(cudaEventRecord(c->lu_events[3 * KB + 1], sU));  // evU[KB]
@@ -1019,7 +1020,7 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
         launches++;
         const int m2 = m1 - 1;
         if (m2 > 0) {
-          gemm128_kernel<1, 4, KC_BULK, STAGES_BULK><<<dim3(m2 * m2, 2), 256, gemm_smem, st>>>(A, np, KB, dinv, Lbuf(KB));
+          gemm128_kernel<1, 4, KC_BULK, STAGES_BULK><<<dim3((m2 + 1) * m2, 2), 256, gemm_smem, st>>>(A, np, KB, dinv, Lbuf(KB));
           mark("uii_end", KB, st);
           launches++;
         }
