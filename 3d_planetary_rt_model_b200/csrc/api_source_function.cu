@@ -1,0 +1,200 @@
+// api_source_function.cu -- influence build with row sinks, single scattering, dense solve, singlet emission tables
+// (one of the translation units behind the C ABI; see api_internal.hpp)
+#include "api_internal.hpp"
+
+namespace b200rt {
+namespace api {
+namespace {
+
+// ------------------------------------------------------------------ influence
+// ranges: the source-voxel ranges [begin, end) this call builds rows for (one range for a single GPU or a contiguous
+// shard; several for the interleaved shards that balance the cost of low- and high-altitude rows across ranks)
+template <class Real>
+int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges) {
+  GridView<Real> &g = gv<Real>(c);
+  const int n_vox = g.n_vox;
+  PhaseTimer::reset(c);
+  B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
+  B200RT_CUDA(c, cudaMemsetAsync(c->step_counter.p, 0, sizeof(unsigned long long), c->stream));
+  int n_rows = 0;
+  for (auto &r : ranges) n_rows += r.second - r.first;
+  for (int e = 0; e < c->n_em; e++) {
+    Emission &E = c->em[e];
+    if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
+    for (auto &r : ranges)
+      if (r.second > r.first)
+        B200RT_CUDA(c, cudaMemsetAsync(E.K.as<double>() + (size_t) r.first * n_vox, 0,
+                                       (size_t) (r.second - r.first) * n_vox * sizeof(double), c->stream));
+  }
+  // Local slots 0 .. n_rows-1 run over the ranges in order.  One range: slot i is voxel first + i.  Several ranges
+  // (interleaved multi-GPU shards): the slot -> voxel map goes to the device, so that a batch -- one traversal launch
+  // + one march launch -- spans shard boundaries and the launch count does not grow with the number of shards.
+  const bool mapped = ranges.size() > 1;
+  std::vector<int> vox_of;
+  if (mapped) {
+    vox_of.reserve(n_rows);
+    for (auto &r : ranges) for (int v = r.first; v < r.second; v++) vox_of.push_back(v);
+    B200RT_CUDA(c, c->vox_map.ensure((size_t) n_rows * sizeof(int)));
+    B200RT_CUDA(c, cudaMemcpyAsync(c->vox_map.p, vox_of.data(), (size_t) n_rows * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
+  const int first_voxel = ranges.empty() ? 0 : ranges[0].first;
+  const long long cap_rays = batch_capacity(c, sizeof(Real));
+  int vox_per_batch = (int) std::max<long long>(1, std::min<long long>(cap_rays / g.n_rays, std::max(n_rows, 1)));
+  bool pushing = false;
+  for (int e = 0; e < c->n_em; e++) {
+    if (c->row_sink[e] && c->row_sink_n_vox[e] != n_vox)
+      return fail(c, B200RT_ERR_STATE, "row sink was named for a different grid (b200rt_set_row_sink after the grid is set)");
+    pushing = pushing || c->row_sink[e] != nullptr;
+  }
+  if (pushing && n_rows > 0) {     // several batches, so that the DMA of one overlaps the march of the next
+    if (const char *env = getenv("B200RT_ROW_PUSH_BATCHES")) c->row_push_batches = std::max(1, atoi(env));
+    vox_per_batch = std::max(1, std::min(vox_per_batch, (n_rows + c->row_push_batches - 1) / c->row_push_batches));
+    if (!c->copy_stream) B200RT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->ev_rows) B200RT_CUDA(c, cudaEventCreateWithFlags(&c->ev_rows, cudaEventDisableTiming));
+  }
+  ListView<Real> lv;
+  const long long need = std::max<long long>((long long) vox_per_batch * g.n_rays, n_vox);
+  if (int rc = ensure_lists<Real>(c, need, &lv)) return rc;
+  int *overflow = c->work_counter.as<int>() + 1;
+
+  for (int lb = 0; lb < n_rows; lb += vox_per_batch) {
+    const int le = std::min(n_rows, lb + vox_per_batch);
+    GridView<Real> gb = g;
+    int vb = first_voxel + lb, ve = first_voxel + le;      // unmapped: the voxel range itself
+    if (mapped) { gb.vox_map = c->vox_map.as<int>() + lb; vb = 0; ve = le - lb; }
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_voxel_rays<Real>(gb, vb, ve, lv, overflow, c->stream));
+      t.stop(1);
+      DBG(c, "traverse_voxel_rays");
+    }
+    for (int e = 0; e < c->n_em; e++) {
+      PhaseTimer t(c, PH_INFLUENCE);
+      B200RT_CUDA(c, launch_influence<Real>(gb, em_view<Real>(c, e), vb, ve, lv, c->em[e].K.as<double>(),
+                                            c->work_counter.as<int>(),
+                                            e == 0 ? c->step_counter.as<unsigned long long>() : nullptr, c->stream));
+      t.stop(1);
+      DBG(c, "influence march");
+    }
+    if (pushing) {   // the rows of this batch are final: hand them to the solving GPU (peer memory, copy engine, NVLink)
+      B200RT_CUDA(c, cudaEventRecord(c->ev_rows, c->stream));
+      B200RT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rows, 0));
+      int run_lo = lb;                                      // contiguous runs of voxels inside the batch
+      while (run_lo < le) {
+        int run_hi = run_lo + 1;
+        const int v_lo = mapped ? vox_of[run_lo] : first_voxel + run_lo;
+        while (run_hi < le && (mapped ? vox_of[run_hi] : first_voxel + run_hi) == v_lo + (run_hi - run_lo)) run_hi++;
+        for (int e = 0; e < c->n_em; e++)
+          if (c->row_sink[e])
+            B200RT_CUDA(c, cudaMemcpyAsync(static_cast<double *>(c->row_sink[e]) + (size_t) v_lo * n_vox,
+                                           c->em[e].K.as<double>() + (size_t) v_lo * n_vox,
+                                           (size_t) (run_hi - run_lo) * n_vox * sizeof(double), cudaMemcpyDeviceToDevice,
+                                           c->copy_stream));
+        run_lo = run_hi;
+      }
+    }
+  }
+  // single scattering: one sun-ward ray per voxel (every rank computes all of them: n_vox rays)
+  {
+    const Real *sp = c->sun_rays.as<Real>();
+    RayList<Real> rl;
+    rl.r = sp + 0 * (size_t) n_vox; rl.z = sp + 1 * (size_t) n_vox; rl.t = sp + 2 * (size_t) n_vox;
+    rl.cost = sp + 3 * (size_t) n_vox; rl.lz = sp + 4 * (size_t) n_vox;
+    const int *ip = reinterpret_cast<const int *>(sp + 5 * (size_t) n_vox);
+    rl.i_voxel = ip;
+    const int *shadow = ip + n_vox;
+    {
+      PhaseTimer t(c, PH_TRAVERSE);
+      B200RT_CUDA(c, launch_traverse_list<Real>(g, rl, n_vox, lv, overflow, c->stream));
+      t.stop(1);
+      DBG(c, "traverse sun rays");
+    }
+    for (int e = 0; e < c->n_em; e++) {
+      PhaseTimer t(c, PH_INFLUENCE);
+      Emission &E = c->em[e];
+      B200RT_CUDA(c, launch_single_scattering<Real>(g, em_view<Real>(c, e), lv, shadow, E.S0.as<double>(),
+                                                    E.tau_sp.as<double>(), E.tau_abs.as<double>(),
+                                                    c->work_counter.as<int>(), c->stream));
+      t.stop(1);
+      DBG(c, "single scattering march");
+    }
+  }
+  B200RT_CUDA(c, c->host_words.ensure(4 * sizeof(unsigned long long)));
+  unsigned long long *steps_p = c->host_words.as<unsigned long long>() + 1;
+  B200RT_CUDA(c, cudaMemcpyAsync(steps_p, c->step_counter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  const int rc_overflow = check_overflow(c);   // synchronises
+  const unsigned long long steps = *steps_p;
+  if (pushing) B200RT_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the rows have landed on the solving GPU
+  if (rc_overflow) return rc_overflow;
+  PhaseTimer::collect(c);
+  c->last_steps = (long long) steps;
+  for (int e = 0; e < c->n_em; e++) { c->em[e].have_K = true; c->em[e].have_S = false; }
+  return B200RT_OK;
+}
+
+int solve_impl(b200rt_ctx *c, bool reset_timer) {
+  const int n = c->hg.n_vox;
+  if (reset_timer) PhaseTimer::reset(c);
+  for (int e = 0; e < c->n_em; e++) {
+    Emission &E = c->em[e];
+    if (!E.have_K) return fail(c, B200RT_ERR_STATE, "b200rt_solve: influence matrix not built");
+    PhaseTimer t(c, PH_SOLVE);
+    SolveResult r = {0, 0, 0};
+    if (int rc = solve_dense(c, n, E.K.as<double>(), E.branching, E.S0.as<double>(), E.S.as<double>(), &r)) return rc;
+    t.stop(r.launches);
+    E.residual = r.residual;
+    if (c->precision == B200RT_F64)
+      B200RT_CUDA(c, launch_convert<double>(E.S.as<double>(), E.S_real.as<double>(), n, c->stream));
+    else
+      B200RT_CUDA(c, launch_convert<float>(E.S.as<double>(), E.S_real.as<float>(), n, c->stream));
+    E.have_S = true;
+    E.rec_dirty = true;
+  }
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  PhaseTimer::collect(c);
+  return B200RT_OK;
+}
+
+template <class Real>
+int set_singlet_impl(b200rt_ctx *c, int e, const double *const arr[8]) {
+  const int n = c->hg.n_vox;
+  Emission &E = c->em[e];
+  B200RT_CUDA(c, E.tabs.ensure((size_t) 8 * n * sizeof(Real)));
+  B200RT_CUDA(c, E.phi.ensure((size_t) n * N_LAMBDA * sizeof(Real)));
+  B200RT_CUDA(c, E.mrec.ensure((size_t) n * 2 * N_LAMBDA * sizeof(Real)));
+  B200RT_CUDA(c, E.K.ensure((size_t) n * n * sizeof(double)));
+  B200RT_CUDA(c, E.S0.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.tau_sp.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.tau_abs.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.S.ensure(n * sizeof(double)));
+  B200RT_CUDA(c, E.S_real.ensure(n * sizeof(Real)));
+  B200RT_CUDA(c, E.rec_pt.ensure((size_t) n * 8 * sizeof(Real)));
+  B200RT_CUDA(c, E.rec_avg.ensure((size_t) n * 8 * sizeof(Real)));
+  E.rec_dirty = true;
+  DevBuf stage;
+  int rc = B200RT_OK;
+  for (int a = 0; a < 8 && rc == B200RT_OK; a++)
+    rc = upload_real<Real>(c, arr[a], E.tabs.as<Real>() + (size_t) a * n, n, stage);
+  if (rc == B200RT_OK) {
+    cudaError_t er = launch_phi_table<Real>(E.tabs.as<Real>(), E.tabs.as<Real>() + 2 * (size_t) n, E.tabs.as<Real>() + 3 * (size_t) n, n,
+                                            E.phi.as<Real>(), E.mrec.as<Real>(), c->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(c->stream);
+    if (er != cudaSuccess) rc = fail(c, B200RT_ERR_CUDA, cudaGetErrorString(er));
+  }
+  stage.release();
+  return rc;
+}
+
+
+}  // namespace
+
+int influence(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges) {
+  return is64(c) ? influence_impl<double>(c, ranges) : influence_impl<float>(c, ranges);
+}
+int solve(b200rt_ctx *c, bool reset_timer) { return solve_impl(c, reset_timer); }
+int set_singlet(b200rt_ctx *c, int e, const double *const arr[8]) {
+  return is64(c) ? set_singlet_impl<double>(c, e, arr) : set_singlet_impl<float>(c, e, arr);
+}
+
+}  // namespace api
+}  // namespace b200rt
