@@ -492,7 +492,8 @@ def run_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import extra_bench
             ex = extra_bench.iph(n_los, world)
-            ex.update(extra_bench.sweep(512, 10000, 4, world))
+            # worker threads = contexts x GPUs: no more of them than host cores (a set is host-latency bound)
+            ex.update(extra_bench.sweep(512, 10000, max(1, min(4, (os.cpu_count() or 16) // world)), world))
             if world == 1:
                 ex.update(extra_bench.multiplet(0))
                 ex.update(extra_bench.multiplet(1))
