@@ -406,7 +406,7 @@ def run_ours(args):
                                     "traverse_kernel"),
         "traverse_los": roof("traverse_fast_kernel<double,lines of sight>", mean("los_traverse"),
                              (l1 - l0) * quad * FLOP_EQ_PER_QUADRATIC, substeps_rank / 9.0 * 12.0,
-                             {"rays": l1 - l0, "quadratics_per_ray": quad, "flop_eq_per_quadratic": FLOP_EQ_PER_QUADRATIC}, None),
+                             {"rays": l1 - l0, "quadratics_per_ray": quad, "flop_eq_per_quadratic": FLOP_EQ_PER_QUADRATIC}, "traverse_los"),
     }
     if t_solve > 0:
         sv = t_solve / K
