@@ -44,6 +44,11 @@ struct install_handler {
 
 extern "C" {
 const char *obsfit_last_error() { return g_err.c_str(); }
+void *obsfit_create_ex(const char *iph_fname, int device, int single_precision) {
+  observation_fit *o = nullptr;
+  if (guard([&] { o = new observation_fit(iph_fname ? iph_fname : "", device, single_precision != 0); })) return nullptr;
+  return o;
+}
 void *obsfit_create(const char *iph_fname, int device) {
   observation_fit *o = nullptr;
   if (guard([&] { o = new observation_fit(iph_fname ? iph_fname : "", device); })) return nullptr;

@@ -62,7 +62,7 @@ b200rt_ctx *observation_fit::make_ctx() const {
   b200rt_ctx *c = nullptr;
   int rc;
   if (device >= 0) {
-    rc = b200rt_create(device, B200RT_F64, &c);
+    rc = b200rt_create(device, precision, &c);
   } else {
     std::vector<int> ids;
     if (const char *env = getenv("B200RT_DEVICES")) {
@@ -75,15 +75,20 @@ b200rt_ctx *observation_fit::make_ctx() const {
         p = (*end == ',') ? end + 1 : end;
       }
     }
-    rc = b200rt_create_multi((int) ids.size(), ids.empty() ? nullptr : ids.data(), B200RT_F64, &c);
+    rc = b200rt_create_multi((int) ids.size(), ids.empty() ? nullptr : ids.data(), precision, &c);
   }
   if (rc != B200RT_OK)
     throw std::runtime_error("observation_fit: no usable CUDA device (this library has no CPU path)");
   return c;
 }
 
-observation_fit::observation_fit(const string iph_sfn_fnamee, int devicee)
-    : device(devicee), iph_sfn_fname(iph_sfn_fnamee) {
+observation_fit::observation_fit(const string iph_sfn_fnamee, int devicee, bool single_precision)
+    : device(devicee), precision(single_precision ? B200RT_F32 : B200RT_F64), iph_sfn_fname(iph_sfn_fnamee) {
+  // Real = float is the only precision the reference's own GPU module is built in (makefile:80,230; parity bar 1e-4);
+  // the facade's interface stays double, the device arithmetic (traversal, march, brightness) runs in float, the solve in
+  // FP64.  B200RT_FACADE_REAL=float selects it for callers that cannot pass the argument (the unchanged .pyx).
+  if (const char *env = getenv("B200RT_FACADE_REAL"))
+    if (string(env) == "float" || string(env) == "f32") precision = B200RT_F32;
   CO2_exobase_density = default_CO2_exobase_density;
   g_factor[0] = lyman_alpha_typical_g_factor;
   g_factor[1] = lyman_beta_typical_g_factor;
@@ -124,7 +129,7 @@ void observation_fit::add_observation(const vector<vector<Real>> &MSO_locations,
 void observation_fit::add_observation(const double *loc, const double *dir, int n) {
   if (n < 0 || (n > 0 && (!loc || !dir))) throw std::invalid_argument("add_observation: bad arguments");
   for (auto &a : los) a.assign(n, 0.0);
-  int rc = b200rt_los_from_MSO(B200RT_F64, n, loc, dir, los[0].data(), los[1].data(), los[2].data(),
+  int rc = b200rt_los_from_MSO(precision, n, loc, dir, los[0].data(), los[1].data(), los[2].data(),
                                los[3].data(), los[4].data(), los[5].data(), los[6].data(), los[7].data(), los[8].data());
   if (rc != B200RT_OK) throw std::runtime_error("b200rt_los_from_MSO failed");
   for (singlet_model *m : {H, D, H_pp, D_pp})
@@ -181,7 +186,7 @@ void observation_fit::build_inputs(const atmosphere_model &atm, const Real &Texo
     in.rb = atm.radial_boundaries(n_radial_boundaries, 0);                  // rmethod_altitude, observation_fit.cpp:34
     in.sb.assign(in.n_sb, 0); in.pts_r.assign(in.n_rb - 1, 0); in.pts_s.assign(in.n_sb - 1, 0);
     in.ray_t.assign(in.n_rays, 0); in.ray_p.assign(in.n_rays, 0); in.ray_w.assign(in.n_rays, 0);
-    int rc = b200rt_make_grid_sph(B200RT_F64, in.n_rb, in.n_sb, n_rays_theta, n_rays_phi, in.rb.data(), szamethod,
+    int rc = b200rt_make_grid_sph(precision, in.n_rb, in.n_sb, n_rays_theta, n_rays_phi, in.rb.data(), szamethod,
                                   1 /* raymethod_theta_uniform */, in.sb.data(), in.pts_r.data(), in.pts_s.data(),
                                   in.ray_t.data(), in.ray_p.data(), in.ray_w.data());
     if (rc != B200RT_OK) throw std::runtime_error("b200rt_make_grid_sph failed");
@@ -191,7 +196,7 @@ void observation_fit::build_inputs(const atmosphere_model &atm, const Real &Texo
     in.sb = {0.0, pi}; in.pts_s = {0.0};
     in.pts_r.assign(in.n_rb - 1, 0);
     in.ray_t.assign(in.n_rays, 0); in.ray_p.assign(in.n_rays, 0); in.ray_w.assign(in.n_rays, 0);
-    int rc = b200rt_make_grid_pp(B200RT_F64, in.n_rb, n_rays_pp, in.rb.data(), in.pts_r.data(), in.ray_t.data(), in.ray_w.data());
+    int rc = b200rt_make_grid_pp(precision, in.n_rb, n_rays_pp, in.rb.data(), in.pts_r.data(), in.ray_t.data(), in.ray_w.data());
     if (rc != B200RT_OK) throw std::runtime_error("b200rt_make_grid_pp failed");
   }
   in.n_vox = (in.n_rb - 1) * (in.n_sb - 1);
@@ -576,14 +581,14 @@ void observation_fit::generate_multiplet(multiplet_model &m, int kind, atmospher
   g.rb = atm.radial_boundaries(n_radial_boundaries, kind == B200RT_MULT_O1026 ? 1 : 0);
   g.sb.assign(g.n_sb, 0); g.pts_r.assign(g.n_rb - 1, 0); g.pts_s.assign(g.n_sb - 1, 0);
   g.ray_t.assign(g.n_rays, 0); g.ray_p.assign(g.n_rays, 0); g.ray_w.assign(g.n_rays, 0);
-  if (b200rt_make_grid_sph(B200RT_F64, g.n_rb, g.n_sb, n_rays_theta, n_rays_phi, g.rb.data(), szamethod, 1, g.sb.data(),
+  if (b200rt_make_grid_sph(precision, g.n_rb, g.n_sb, n_rays_theta, n_rays_phi, g.rb.data(), szamethod, 1, g.sb.data(),
                            g.pts_r.data(), g.pts_s.data(), g.ray_t.data(), g.ray_p.data(), g.ray_w.data()) != B200RT_OK)
     throw std::runtime_error("b200rt_make_grid_sph failed");
   g.n_vox = (g.n_rb - 1) * (g.n_sb - 1);
   atm.voxel_tables(g.rb, g.pts_r, g.sb, g.pts_s, g.vox);
   check(b200rt_set_grid_sph(m.ctx, g.n_rb, g.n_sb, g.n_rays, g.rb.data(), g.sb.data(), g.pts_r.data(), g.pts_s.data(),
                             g.ray_t.data(), g.ray_p.data(), g.ray_w.data()), m.ctx);
-  if (b200rt_multiplet_desc_init(kind, B200RT_F64, &m.desc) != B200RT_OK) throw std::runtime_error("b200rt_multiplet_desc_init failed");
+  if (b200rt_multiplet_desc_init(kind, precision, &m.desc) != B200RT_OK) throw std::runtime_error("b200rt_multiplet_desc_init failed");
   for (int l = 0; l < m.desc.n_lines; l++)
     m.desc.solar_flux[l] = (kind == B200RT_MULT_O1026 || m.desc.multiplet_index[l] == 0) ? solar[0] : solar[1];
   const int nv = g.n_vox, nl = m.desc.n_lower;
@@ -742,7 +747,7 @@ vector<vector<vector<observation_fit::Real>>> observation_fit::brightness_batch(
   auto work = [&](int w) {
     b200rt_ctx *c = nullptr;
     try {
-      if (b200rt_create(w % n_gpus, B200RT_F64, &c) != B200RT_OK) throw std::runtime_error("b200rt_create failed");
+      if (b200rt_create(w % n_gpus, precision, &c) != B200RT_OK) throw std::runtime_error("b200rt_create failed");
       bool first = true;
       set_inputs in;
       for (int i = next++; i < n_sets; i = next++) {

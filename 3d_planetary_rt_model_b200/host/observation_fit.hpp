@@ -42,7 +42,8 @@ public:
   static const int n_hydrogen_emissions = 2;
   static const int n_voxels = (n_radial_boundaries - 1) * (n_sza_boundaries - 1);
 
-  explicit observation_fit(const std::string iph_sfn_fnamee, int device = -1);   // -1: every visible GPU (one handle)
+  explicit observation_fit(const std::string iph_sfn_fnamee, int device = -1,   // -1: every visible GPU (one handle)
+                           bool single_precision = false);                     // device arithmetic in float (the reference GPU build's Real)
   ~observation_fit();
   observation_fit(const observation_fit &) = delete;
   observation_fit &operator=(const observation_fit &) = delete;
@@ -164,6 +165,7 @@ private:
   void save_S(const std::string &fname, const set_inputs &in);
 
   int device;
+  int precision;           // B200RT_F64 or B200RT_F32: arithmetic of the device kernels
   b200rt_host::H_cross_sections H_cross_section_options;
   const Real default_CO2_exobase_density = 2e8;
   Real CO2_exobase_density;

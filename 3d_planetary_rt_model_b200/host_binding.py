@@ -18,6 +18,7 @@ _vp = C.c_void_p
 SIGNATURES = {
     "obsfit_last_error": (C.c_char_p, []),
     "obsfit_create": (_vp, [C.c_char_p, C.c_int]),
+    "obsfit_create_ex": (_vp, [C.c_char_p, C.c_int, C.c_int]),
     "obsfit_destroy": (None, [_vp]),
     "obsfit_add_observation": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "obsfit_set_g_factor": (C.c_int, [_vp, C.c_double, C.c_double]),
@@ -106,9 +107,9 @@ class Pyobservation_fit:
     n_emissions, n_rb, n_sb = 2, 40, 20
     n_vox = (n_rb - 1) * (n_sb - 1)
 
-    def __init__(self, iph_table_fname="", device=-1):
+    def __init__(self, iph_table_fname="", device=-1, single_precision=False):
         self.lib = load()
-        self.h = self.lib.obsfit_create(os.fsencode(iph_table_fname), device)
+        self.h = self.lib.obsfit_create_ex(os.fsencode(iph_table_fname), device, int(single_precision))
         if not self.h:
             raise RuntimeError(self.lib.obsfit_last_error().decode())
         self.n_obs = 0

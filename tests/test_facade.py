@@ -109,3 +109,21 @@ def test_batch_equals_sequential(synth, hb):
     for i in range(len(nH)):
         F.generate_source_function(nH[i], T[i])
         assert rel_err(F.brightness(), batch[i], floor=1e-300) < 1e-12, i
+
+
+@pytest.mark.gpu
+def test_facade_single_precision_device_arithmetic(synth):
+    """observation_fit with Real = float on the device (the reference GPU build's only precision, makefile:80,230): same
+    interface, brightness within the float bar of the double run"""
+    import importlib
+    hb = importlib.import_module("3d_planetary_rt_model_b200.host_binding")
+    locs, dirs = synth.random_los(800, seed=6)
+    out = []
+    for single in (False, True):
+        F = hb.Pyobservation_fit(device=0, single_precision=single)
+        F.add_observation(locs, dirs)
+        F.generate_source_function(2e5, 250.0)
+        out.append(np.asarray(F.brightness()))
+    rel = np.abs(out[0] - out[1]) / np.maximum(np.abs(out[0]), 1e-300)
+    assert rel.max() < 3e-4, rel.max()          # 1e-4 against the float reference; here float vs double inputs as well
+    assert not np.array_equal(out[0], out[1])    # it really ran in another arithmetic
