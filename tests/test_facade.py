@@ -125,5 +125,8 @@ def test_facade_single_precision_device_arithmetic(synth):
         F.generate_source_function(2e5, 250.0)
         out.append(np.asarray(F.brightness()))
     rel = np.abs(out[0] - out[1]) / np.maximum(np.abs(out[0]), 1e-300)
-    assert rel.max() < 3e-4, rel.max()          # 1e-4 against the float reference; here float vs double inputs as well
+    # the float and the double build of the REFERENCE differ at the 1e-3 level by construction: Real.hpp sets EPS = 1e-3
+    # for float and 1e-6 for double, and RT_grid::brightness insets / shrinks every sub-step by EPS (RT_grid.hpp:268-271).
+    # Each build is pinned to its own reference at 1e-4 / 1e-6 elsewhere (test_gpu_parity, test_gpu_fullsize)
+    assert rel.max() < 3e-3, rel.max()
     assert not np.array_equal(out[0], out[1])    # it really ran in another arithmetic
