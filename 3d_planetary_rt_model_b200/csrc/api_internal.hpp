@@ -154,6 +154,7 @@ inline bool is64(const b200rt_ctx *c) { return c->precision == B200RT_F64; }
 // ---- api_source_function.cu
 int influence(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges);
 int solve(b200rt_ctx *c, bool reset_timer);
+int solve_emission(b200rt_ctx *c, int e);   // one singlet emission only (device group: emission e on its owner device)
 int set_singlet(b200rt_ctx *c, int e, const double *const arr[8]);
 // ---- api_brightness.cu  (los_download_slice / brightness_slice are declared in common.hpp)
 int brightness_resident(b200rt_ctx *c, int n_subsamples);

@@ -132,10 +132,12 @@ int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges
   return B200RT_OK;
 }
 
-int solve_impl(b200rt_ctx *c, bool reset_timer) {
+// only_e >= 0: that emission alone (a device group solves emission e on the device that gathered its rows)
+int solve_impl(b200rt_ctx *c, bool reset_timer, int only_e = -1) {
   const int n = c->hg.n_vox;
   if (reset_timer) PhaseTimer::reset(c);
   for (int e = 0; e < c->n_em; e++) {
+    if (only_e >= 0 && e != only_e) continue;
     Emission &E = c->em[e];
     if (!E.have_K) return fail(c, B200RT_ERR_STATE, "b200rt_solve: influence matrix not built");
     PhaseTimer t(c, PH_SOLVE);
@@ -192,6 +194,11 @@ int influence(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges) {
   return is64(c) ? influence_impl<double>(c, ranges) : influence_impl<float>(c, ranges);
 }
 int solve(b200rt_ctx *c, bool reset_timer) { return solve_impl(c, reset_timer); }
+int solve_emission(b200rt_ctx *c, int e) {
+  if (e < 0 || e >= c->n_em) return fail(c, B200RT_ERR_ARG, "bad emission index");
+  cudaSetDevice(c->device);
+  return solve_impl(c, true, e);
+}
 int set_singlet(b200rt_ctx *c, int e, const double *const arr[8]) {
   return is64(c) ? set_singlet_impl<double>(c, e, arr) : set_singlet_impl<float>(c, e, arr);
 }

@@ -267,7 +267,7 @@ int b200rt_last_substep_count(b200rt_ctx *c, long long *n) {
 
 int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp, double *tab) {
   if (!c) return B200RT_ERR_ARG;
-  GROUP_DISPATCH(c, group_forward(c, b200rt_get_solution(group_primary(c), e, S, S0, tsp, tab)));
+  GROUP_DISPATCH(c, group_forward(c, b200rt_get_solution(group_owner(c, e), e, S, S0, tsp, tab)));
   if (c->mult.defined) {
     if (e != 0) return B200RT_ERR_ARG;
     cudaSetDevice(c->device);
@@ -302,7 +302,7 @@ int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp
 
 int b200rt_get_influence(b200rt_ctx *c, int e, int layout, double *K) {
   if (!c || !K) return B200RT_ERR_ARG;
-  GROUP_DISPATCH(c, group_forward(c, b200rt_get_influence(group_primary(c), e, layout, K)));
+  GROUP_DISPATCH(c, group_forward(c, b200rt_get_influence(group_owner(c, e), e, layout, K)));
   const bool mm = c->mult.defined;
   if (mm ? e != 0 : (e < 0 || e >= c->n_em)) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
@@ -353,7 +353,7 @@ int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
 
 int b200rt_last_residual(b200rt_ctx *c, int e, double *r) {
   if (!c || !r) return B200RT_ERR_ARG;
-  GROUP_DISPATCH(c, group_forward(c, b200rt_last_residual(group_primary(c), e, r)));
+  GROUP_DISPATCH(c, group_forward(c, b200rt_last_residual(group_owner(c, e), e, r)));
   if (c->mult.defined) { *r = c->mult.residual; return e == 0 ? B200RT_OK : B200RT_ERR_ARG; }
   if (e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
   *r = c->em[e].residual;
@@ -362,7 +362,7 @@ int b200rt_last_residual(b200rt_ctx *c, int e, double *r) {
 
 int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, void **tab) {
   if (!c) return B200RT_ERR_ARG;
-  GROUP_DISPATCH(c, group_forward(c, b200rt_influence_dev(group_primary(c), e, K, S0, tsp, tab)));
+  GROUP_DISPATCH(c, group_forward(c, b200rt_influence_dev(group_owner(c, e), e, K, S0, tsp, tab)));
   if (c->mult.defined) {
     if (e != 0) return B200RT_ERR_ARG;
     Multiplet &M = c->mult;
@@ -387,7 +387,7 @@ int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, 
 // ---- peer-memory row exchange (one process per GPU): the solving rank exports its K, the others open it and
 // name it as the sink of their row batches
 int b200rt_ipc_export_influence(b200rt_ctx *c, int e, void *handle64) {
-  if (c && c->group) return group_forward(c, b200rt_ipc_export_influence(group_primary(c), e, handle64));
+  if (c && c->group) return group_forward(c, b200rt_ipc_export_influence(group_owner(c, e), e, handle64));
   if (!c || !handle64 || e < 0 || e >= c->n_em || c->mult.defined) return B200RT_ERR_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   cudaSetDevice(c->device);
@@ -427,7 +427,7 @@ int b200rt_set_row_sink(b200rt_ctx *c, int e, void *peer_K_dev) {
 }
 
 int b200rt_sourcefn_dev(b200rt_ctx *c, int e, void **S) {
-  if (c && c->group) return group_forward(c, b200rt_sourcefn_dev(group_primary(c), e, S));
+  if (c && c->group) return group_forward(c, b200rt_sourcefn_dev(group_owner(c, e), e, S));
   if (c && S && c->mult.defined && e == 0) { *S = c->mult.S.p; return B200RT_OK; }
   if (!c || e < 0 || e >= c->n_em || !S) return B200RT_ERR_ARG;
   *S = c->em[e].S.p;

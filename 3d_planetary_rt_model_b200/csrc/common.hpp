@@ -364,6 +364,7 @@ int brightness_slice(b200rt_ctx *c, int n, const double *const src[9], int n_sub
 
 // ---- device_group.cu: one handle, several devices of one process (b200rt_create_multi)
 b200rt_ctx *group_primary(b200rt_ctx *g);
+b200rt_ctx *group_owner(b200rt_ctx *g, int i_emission);   // the member that gathered (and solves) emission e's rows
 int group_forward(b200rt_ctx *g, int rc);      // rc of a call on the primary member; copies its error text on failure
 int group_destroy(b200rt_ctx *g);
 int group_synchronize(b200rt_ctx *g);

@@ -23,7 +23,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
-#include "common.hpp"
+#include "api_internal.hpp"
 
 namespace b200rt {
 
@@ -101,6 +101,9 @@ struct Group {
   float phase_ms[PH_COUNT] = {0, 0, 0, 0, 0, 0};
   int phase_launches[PH_COUNT] = {0, 0, 0, 0, 0, 0};
   long long last_steps = 0, last_substeps = 0;
+  // the member that gathered the rows of emission e in the last build and solves it (with several
+  // emissions and several devices the dense solves run side by side, one emission per device)
+  int owner[MAX_EMISSIONS] = {0, 0};
   // fan-out thresholds
   long long min_rays = 262144, min_los = 65536;
   int chunks_per_member = 8;
@@ -167,6 +170,8 @@ int influence_rows(b200rt_ctx *g, int n_ranges, const int *vb, const int *ve) {
   // fan-out: both stay on the primary
   const bool split = !p->mult.defined && n_rows * p->hg.n_rays >= gr->min_rays && n_rows >= 2 * n_mem;
   if (!split) {
+    for (int e = 0; e < MAX_EMISSIONS; e++) gr->owner[e] = 0;
+    for (int e = 0; e < p->n_em && !p->mult.defined; e++) b200rt_set_row_sink(p, e, nullptr);
     int rc;
     if (p->mult.defined) {
       if (n_ranges != 1) return fail(g, B200RT_ERR_STATE, "b200rt_influence_ranges: singlet emissions only");
@@ -204,9 +209,13 @@ int influence_rows(b200rt_ctx *g, int n_ranges, const int *vb, const int *ve) {
       base += len;
     }
   }
-  for (int i = 1; i < n_mem; i++)
+  // emission e's rows are gathered on member e mod n_mem (one emission: the primary): every other member names that
+  // member's resident K as its sink for e
+  for (int e = 0; e < MAX_EMISSIONS; e++) gr->owner[e] = (e < p->n_em) ? e % n_mem : 0;
+  for (int i = 0; i < n_mem; i++)
     for (int e = 0; e < p->n_em; e++) {
-      const int rc = b200rt_set_row_sink(gr->m[i], e, p->em[e].K.p);
+      b200rt_ctx *own = gr->m[gr->owner[e]];
+      const int rc = b200rt_set_row_sink(gr->m[i], e, gr->owner[e] == i ? nullptr : own->em[e].K.p);
       if (rc != B200RT_OK) { g->err = gr->m[i]->err; return rc; }
     }
   const int rc = all(g, [&](int i) {
@@ -222,18 +231,33 @@ int influence_rows(b200rt_ctx *g, int n_ranges, const int *vb, const int *ve) {
 int solve_and_share(b200rt_ctx *g) {
   Group *gr = G(g);
   b200rt_ctx *p = gr->m[0];
-  int rc = b200rt_solve(p);
-  if (rc != B200RT_OK) { g->err = p->err; return rc; }
-  collect_phases(gr, 1);
-  // the other members integrate lines of sight with the same source function
   const int n_mem = (int) gr->m.size();
   const int n_e = p->mult.defined ? 1 : p->n_em;
   const size_t n_el = p->mult.defined ? (size_t) p->hg.n_vox * p->mult.d.n_upper : (size_t) p->hg.n_vox;
+  bool spread = false;
+  for (int e = 0; e < n_e; e++) spread = spread || gr->owner[e] != 0;
+  if (!spread) {
+    const int rc = b200rt_solve(p);
+    if (rc != B200RT_OK) { g->err = p->err; return rc; }
+    collect_phases(gr, 1);
+  } else {
+    // one emission per owner device, side by side
+    const int rc = run_members(g, n_mem, [&](int i) {
+      for (int e = 0; e < n_e; e++)
+        if (gr->owner[e] == i)
+          if (int r = api::solve_emission(gr->m[i], e)) return r;
+      return (int) B200RT_OK;
+    });
+    if (rc != B200RT_OK) return rc;
+    collect_phases(gr, n_mem);
+  }
+  // every member integrates lines of sight with the same source function
   std::vector<double> S(n_el);
   for (int e = 0; e < n_e; e++) {
-    rc = b200rt_get_solution(p, e, S.data(), nullptr, nullptr, nullptr);
-    if (rc != B200RT_OK) { g->err = p->err; return rc; }
-    rc = run_members(g, n_mem, [&](int i) { return i == 0 ? (int) B200RT_OK : b200rt_set_sourcefn(gr->m[i], e, S.data()); });
+    b200rt_ctx *own = gr->m[p->mult.defined ? 0 : gr->owner[e]];
+    int rc = b200rt_get_solution(own, e, S.data(), nullptr, nullptr, nullptr);
+    if (rc != B200RT_OK) { g->err = own->err; return rc; }
+    rc = run_members(g, n_mem, [&](int i) { return gr->m[i] == own ? (int) B200RT_OK : b200rt_set_sourcefn(gr->m[i], e, S.data()); });
     if (rc != B200RT_OK) return rc;
   }
   return B200RT_OK;
@@ -242,9 +266,16 @@ int solve_and_share(b200rt_ctx *g) {
 }  // namespace
 
 b200rt_ctx *group_primary(b200rt_ctx *g) { return G(g)->m[0]; }
+b200rt_ctx *group_owner(b200rt_ctx *g, int e) {
+  Group *gr = G(g);
+  if (e < 0 || e >= MAX_EMISSIONS || gr->m[0]->mult.defined) return gr->m[0];
+  return gr->m[gr->owner[e]];
+}
 
 int group_forward(b200rt_ctx *g, int rc) {
-  if (rc != B200RT_OK) g->err = G(g)->m[0]->err;
+  if (rc != B200RT_OK) {      // the member that failed left its message; report the first non-empty one
+    for (b200rt_ctx *m : G(g)->m) if (!m->err.empty()) { g->err = m->err; break; }
+  }
   return rc;
 }
 

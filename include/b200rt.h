@@ -52,9 +52,11 @@ int b200rt_device_count(void);
  * each call out itself and every other entry point of this header takes it unchanged:
  *   geometry, emission tables, source function: replicated on every device;
  *   b200rt_generate_S / b200rt_influence*:      source-voxel rows split into interleaved shards; the devices write
- *                                               their finished row batches into the first device's resident K over
- *                                               peer memory (copy engines, NVLink) while marching the next batch;
- *   b200rt_solve:                               on the first device, S handed to the others;
+ *                                               their finished row batches into the resident K of the device that
+ *                                               solves that emission (emission e: device e mod n; one emission: the
+ *                                               first device) over peer memory (copy engines, NVLink) while marching
+ *                                               the next batch;
+ *   b200rt_solve:                               each emission on its device, side by side; S handed to the others;
  *   b200rt_brightness*, b200rt_iph_*:           lines of sight split by index, results at their offsets in the
  *                                               caller's arrays; counters add up, b200rt_last_kernel_ms is the
  *                                               slowest device's time.
