@@ -97,8 +97,11 @@ template <> struct Rec2<double> { typedef double2 type; };
 template <> struct Rec2<float> { typedef float2 type; };
 
 // MODE 0: rows of the influence matrix (voxel-origin rays); MODE 1: sun-ward rays -> S0, tau
+#ifndef MARCH_MIN_BLOCKS
+#define MARCH_MIN_BLOCKS 2
+#endif
 template <class Real, int MODE, bool PP>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, MARCH_MIN_BLOCKS)
 march_kernel(GridView<Real> g, EmissionView<Real> em, int v_begin, long long n_rays_total,
              ListView<Real> lists, const int *__restrict__ shadow, double *__restrict__ K,
              double *__restrict__ S0, double *__restrict__ tau_sp_out, double *__restrict__ tau_abs_out,
