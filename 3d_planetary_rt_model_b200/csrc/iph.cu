@@ -253,6 +253,8 @@ iph_kernel(IphConst c, const float *__restrict__ g_alt, const float *__restrict_
   const float RR = sqrtf(X * X + Y * Y + Z * Z);
   if (RR <= t.alt[t.kmax - 1]) {
     float YP = Y, R = RR, XAV = X, YAV = Y, ZAV = Z;
+    float FOO = 0.f;   // IPAL3M zeroes F and CT before its early return but not FOO (:685-690): inside the innermost node and
+                       // at the outer edge the caller's FOO keeps the value of the previous step
     for (;;) {
       const float TETA = acos_poly(YP / R) / c.dpi;
       int KO;
@@ -273,7 +275,7 @@ iph_kernel(IphConst c, const float *__restrict__ g_alt, const float *__restrict_
       if (R > t.alt[t.kmax - 1]) break;
       const float TETA2 = acos_poly(YP / R) / c.dpi;
       // IPAL3M :659-741 for the output density index
-      float FOO = 0.f, FN = 0.f;
+      float FN = 0.f;
       if (!(R < t.alt[0] || R >= t.alt[t.kmax - 1])) {
         int ll, llp, kk, kkp;
         float dt, du;

@@ -244,7 +244,7 @@ static float iph_den(const iph_model *m, float Z, float T, int *ko) {
 
 /* IPAL3M (:659-741) for one density index */
 static void iph_ipal3m(const iph_model *m, float R, float T, int imd, float *foo, float *fn) {
-  *foo = 0.f; *fn = 0.f;
+  *fn = 0.f;     /* F and CT are zeroed before the early return, FOO is NOT (:685-690): the caller's value survives */
   if (R < m->alt[0] || R >= m->alt[m->kmax - 1]) return;
   int ll, llp, kk, kkp;
   float dt, du;
@@ -342,6 +342,7 @@ static float iph_intens(const iph_model *m, float GRAL, float X, float Y, float 
   const float RR = sqrtf(X * X + Y * Y + Z * Z);
   if (RR > m->alt[m->kmax - 1]) return 0.f;
   float YP = Y, R = RR, XAV = X, YAV = Y, ZAV = Z;
+  float FOO = 0.f;   /* FOO(5) is zeroed once per line of sight (:577-585) and then only written by IPAL3M */
   for (;;) {
     const float TETA = iph_acosf(YP / R) / m->dpi;
     int KO;
@@ -361,7 +362,7 @@ static float iph_intens(const iph_model *m, float GRAL, float X, float Y, float 
     R = sqrtf(XP * XP + YP * YP + ZP * ZP);
     if (R > m->alt[m->kmax - 1]) break;
     const float TETA2 = iph_acosf(YP / R) / m->dpi;
-    float FOO, FN;
+    float FN;
     iph_ipal3m(m, R, TETA2, iout, &FOO, &FN);
     const float DTT = iph_top(m, XAV, YAV, ZAV, XP, YP, ZP, idb);
     const float cosff = (U * XP + V * YP + W * ZP) / R;

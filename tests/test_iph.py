@@ -110,8 +110,8 @@ def test_second_restatement_agrees_with_the_oracle():
     fn2 = IphNumpy(tab).background(3e11, z["marspos"], u, v, w)
     assert (np.abs(fo - fn2) / np.abs(fo)).max() < 1e-2
     # lines of sight that pass inside the innermost node (0.2 AU): there IPAL3M returns early and the Fortran leaves FOO
-    # at its previous value (:685-690 zero F and CT only), which iph_numpy follows while iph_oracle.c and the device
-    # kernel zero it -- a documented deviation that the reference's table makes immaterial (SO is 0 on the inner node)
+    # at its previous value (:685-690 zero F and CT only) -- a corner the numpy restatement caught in iph_oracle.c and
+    # the device kernel (they zeroed it; now all three follow the Fortran)
     pos = np.asarray(z["marspos"], dtype=np.float64)
     rng = np.random.default_rng(1)
     D = -pos / np.linalg.norm(pos) + 0.08 * rng.normal(size=(24, 3))
