@@ -296,7 +296,6 @@ int group_synchronize(b200rt_ctx *g) {
 
 int group_set_grid_sph(b200rt_ctx *g, int n_rb, int n_sb, int n_rays, const double *rb, const double *sb, const double *pts_r,
                        const double *pts_s, const double *ray_t, const double *ray_p, const double *ray_domega) {
-  G(g)->los_members = 0;
   return all(g, [&](int i) {
     return b200rt_set_grid_sph(G(g)->m[i], n_rb, n_sb, n_rays, rb, sb, pts_r, pts_s, ray_t, ray_p, ray_domega);
   });
@@ -304,7 +303,6 @@ int group_set_grid_sph(b200rt_ctx *g, int n_rb, int n_sb, int n_rays, const doub
 
 int group_set_grid_pp(b200rt_ctx *g, int n_rb, int n_rays, const double *rb, const double *pts_r, const double *ray_t,
                       const double *ray_domega) {
-  G(g)->los_members = 0;
   return all(g, [&](int i) { return b200rt_set_grid_pp(G(g)->m[i], n_rb, n_rays, rb, pts_r, ray_t, ray_domega); });
 }
 

@@ -88,6 +88,28 @@ def test_group_generate_S_shares_the_source_function(synth, binding, split_every
     assert rel_err(b1[:, 0], bN[:, 0]) < 1e-9
 
 
+def test_group_keeps_lines_of_sight_across_a_regrid(synth, binding, split_everything):
+    """resident lines of sight survive b200rt_set_grid_* on a plain context (observation_fit re-grids on every parameter
+    set and uploads its observations once); the group handle must behave the same"""
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=1)
+    locs, dirs = synth.random_los(700, seed=8)
+    res = []
+    for devices in (None, group_devices(binding)):
+        M = binding.GpuModel(scn, "f64", device=0, devices=devices)
+        M.ctx.los_upload(M.ctx.los_from_MSO(locs, dirs))
+        M.ctx.generate_S()
+        M.ctx.brightness_resident(10)
+        first = M.ctx.los_download()["brightness"].copy()
+        M.ctx.set_grid(M.g)                                    # re-grid + new tables, no new upload
+        b, T, s, g = (float(x) for x in scn.em_scalars[0])
+        M.ctx.set_singlet(0, 1, b, T, s, g, binding.define_singlet_tables(scn, 0))
+        M.ctx.generate_S()
+        M.ctx.brightness_resident(10)
+        assert rel_err(first, M.ctx.los_download()["brightness"]) < 1e-9
+        res.append(first)
+    assert rel_err(res[0], res[1]) < 1e-9          # (S differs in the last bits: the order of the REDs into K)
+
+
 def test_group_small_work_stays_on_first_device(synth, binding):
     """default thresholds: a 12x8 grid and 500 lines of sight are not worth the fan-out"""
     scn = synth.make_scenario(12, 8, 5, 6, n_em=1)
