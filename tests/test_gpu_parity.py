@@ -203,3 +203,34 @@ def test_not_dominant_is_reported(synth, binding):
     G.build_rows()
     with pytest.raises(binding.B200RTError, match="dominant"):
         G.solve()
+
+
+def test_traversal_special_lines_of_sight(synth, binding, oraclebind):
+    """hand-made lines of sight through the corners of the fast traversal path: origins on the Mars-Sun axis, exactly
+    on a radial boundary and on a voxel point; directions exactly radial (out / in), exactly along +-z and tangent to a
+    boundary sphere; origins below the grid and beyond it.  Lists must be the oracle's, bit for bit, in both
+    precisions (rays the fast path cannot verify fall back to the exact ranking)."""
+    for shape in ((12, 8, 5, 6), (40, 20, 7, 12)):
+        scn = synth.make_scenario(*shape, n_em=1)
+        rb = np.asarray(scn.rb)
+        pts_r = np.sqrt(rb[:-1] * rb[1:])
+        locs, dirs = [], []
+
+        def add(p, d):
+            d = np.asarray(d, dtype=np.float64)
+            locs.append(np.asarray(p, dtype=np.float64))
+            dirs.append(d / np.linalg.norm(d))
+        for r in (pts_r[1], rb[2], pts_r[len(pts_r) // 2], rb[-2], pts_r[-1], 0.9 * rb[0], 1.5 * rb[-1]):
+            for p in ([r, 0, 0], [-r, 0, 0], [0, r, 0], [0, 0, r], [r / np.sqrt(2), 0, r / np.sqrt(2)], [0.3 * r, -0.5 * r, np.sqrt(1 - 0.34) * r]):
+                p = np.asarray(p, dtype=np.float64)
+                n = p / np.linalg.norm(p)
+                t = np.cross(n, [0.3, 0.7, 0.2]); t /= np.linalg.norm(t)
+                for d in (n, -n, t, -t, [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, -1, 0], n + 1e-9 * t, t + 1e-12 * n, 0.6 * n + 0.8 * t):
+                    add(p, d)
+        locs, dirs = np.array(locs), np.array(dirs)
+        for prec in ("f64", "f32"):
+            O = oraclebind.OracleModel(scn, prec)
+            G = binding.GpuModel(scn, prec)
+            a, b = O.traverse_los(locs, dirs), G.traverse_los(locs, dirs)
+            assert_lists_equal(a[:4], b[:4])
+            assert (a[0] == 0).any() and (a[0] > 8).any()           # misses and long lists both occur
