@@ -297,6 +297,9 @@ gj128_kernel(const double *__restrict__ A, int np, int KB, double *__restrict__ 
 // Per step the CTA that owns the pivot rows writes the raw rows J of the next step, and the warp that owns the next
 // pivot block its inverse, into the shared memory of ALL four CTAs (distributed shared memory), every CTA publishes its
 // own part of the columns J locally, and one cluster barrier closes the step.
+#ifndef GJ_CLUSTER
+#define GJ_CLUSTER 4
+#endif
 constexpr int GJC_THREADS = 256;
 template <int GJC_CTAS>
 __global__ void __launch_bounds__(GJC_THREADS)
@@ -942,13 +945,13 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
   // failed launch inside a capture would invalidate it); the one-SM kernel is the form for devices / partitions without
   static const bool use_cluster = [] {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(4); cfg.blockDim = dim3(GJC_THREADS);
+    cfg.gridDim = dim3(GJ_CLUSTER); cfg.blockDim = dim3(GJC_THREADS);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[0].val.clusterDim.x = GJ_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n_clusters = 0;
-    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, gj128_cluster_kernel<4>, &cfg);
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, gj128_cluster_kernel<GJ_CLUSTER>, &cfg);
     if (e != cudaSuccess) { cudaGetLastError(); return false; }
     return n_clusters > 0;
   }();
@@ -956,13 +959,13 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
     const int m1 = nK - KB - 1;
     {   // diagonal-block inverse on a cluster of four SMs (gj128_cluster_kernel); gj128_kernel is the one-SM form
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(4); cfg.blockDim = dim3(GJC_THREADS); cfg.stream = s;
+      cfg.gridDim = dim3(GJ_CLUSTER); cfg.blockDim = dim3(GJC_THREADS); cfg.stream = s;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[0].val.clusterDim.x = GJ_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       const double *Ac = A;
-      if (use_cluster) cudaLaunchKernelEx(&cfg, gj128_cluster_kernel<4>, Ac, np, KB, dinv);
+      if (use_cluster) cudaLaunchKernelEx(&cfg, gj128_cluster_kernel<GJ_CLUSTER>, Ac, np, KB, dinv);
       else gj128_kernel<<<1, GJ_THREADS, 0, s>>>(A, np, KB, dinv);
     }
     launches++;
