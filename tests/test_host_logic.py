@@ -77,3 +77,21 @@ def test_interleaved_partition_covers_every_voxel_once():
                 seen[a:b] += 1
         assert (seen == 1).all()
     assert multi.partition_interleaved(100, 1, 0) == [(0, 100)]
+
+
+def test_reference_arm_uses_every_core_under_torchrun(refbind):
+    """torchrun exports OMP_NUM_THREADS=1; the OpenMP reference arm of bench.py pins its own thread count
+    (round-1 verdict: three of the four scaling ratios were taken against one core)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, os, importlib; sys.path.insert(0, %r); "
+            "synth = importlib.import_module('3d_planetary_rt_model_b200.synth'); from oracle import refbind; "
+            "R = refbind.RefModel(synth.make_scenario(8, 6, 4, 4, n_em=1), 'f64'); "
+            "print(R.omp_threads(), R.use_all_cores(), len(os.sched_getaffinity(0)))" % root)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stderr
+    before, after, cores = (int(x) for x in out.stdout.split())
+    assert before == 1 and after == cores
