@@ -39,6 +39,7 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
     if (!c->em[e].have_S) return fail(c, B200RT_ERR_STATE, "source function not available (solve or set_sourcefn first)");
   GridView<Real> &g = gv<Real>(c);
   PhaseTimer::reset(c);
+  SideStreamDrain drain(c);        // nothing stays in flight from / into the caller's arrays, error returns included
   B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
   B200RT_CUDA(c, cudaMemsetAsync(c->step_counter.p, 0, sizeof(unsigned long long), c->stream));
   const long long n = c->n_los;

@@ -149,6 +149,18 @@ inline int upload_real<float>(b200rt_ctx *c, const double *src, float *dst, size
   return B200RT_OK;
 }
 
+// leaves nothing in flight on the side streams of a call -- peer row pushes, uploads from / downloads into caller arrays
+// -- whichever way the call returns (an early error return included)
+struct SideStreamDrain {
+  b200rt_ctx *c;
+  explicit SideStreamDrain(b200rt_ctx *ctx) : c(ctx) {}
+  SideStreamDrain(const SideStreamDrain &) = delete;
+  ~SideStreamDrain() {
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->out_stream) cudaStreamSynchronize(c->out_stream);
+  }
+};
+
 inline bool is64(const b200rt_ctx *c) { return c->precision == B200RT_F64; }
 
 // ---- api_source_function.cu

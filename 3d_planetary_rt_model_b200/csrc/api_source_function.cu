@@ -14,6 +14,7 @@ int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges
   GridView<Real> &g = gv<Real>(c);
   const int n_vox = g.n_vox;
   PhaseTimer::reset(c);
+  SideStreamDrain drain(c);        // row pushes into a peer's K never outlive the call
   B200RT_CUDA(c, cudaMemsetAsync(c->work_counter.p, 0, 2 * sizeof(int), c->stream));
   B200RT_CUDA(c, cudaMemsetAsync(c->step_counter.p, 0, sizeof(unsigned long long), c->stream));
   int n_rows = 0;
