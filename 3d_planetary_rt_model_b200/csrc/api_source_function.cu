@@ -174,18 +174,23 @@ int set_singlet_impl(b200rt_ctx *c, int e, const double *const arr[8]) {
   B200RT_CUDA(c, E.rec_pt.ensure((size_t) n * 8 * sizeof(Real)));
   B200RT_CUDA(c, E.rec_avg.ensure((size_t) n * 8 * sizeof(Real)));
   E.rec_dirty = true;
-  DevBuf stage;
-  int rc = B200RT_OK;
-  for (int a = 0; a < 8 && rc == B200RT_OK; a++)
-    rc = upload_real<Real>(c, arr[a], E.tabs.as<Real>() + (size_t) a * n, n, stage);
-  if (rc == B200RT_OK) {
-    cudaError_t er = launch_phi_table<Real>(E.tabs.as<Real>(), E.tabs.as<Real>() + 2 * (size_t) n, E.tabs.as<Real>() + 3 * (size_t) n, n,
-                                            E.phi.as<Real>(), E.mrec.as<Real>(), c->stream);
-    if (er == cudaSuccess) er = cudaStreamSynchronize(c->stream);
-    if (er != cudaSuccess) rc = fail(c, B200RT_ERR_CUDA, cudaGetErrorString(er));
+  // the eight tables travel as ONE truly asynchronous copy out of page-locked staging (eight copies out of the caller's
+  // pageable arrays would each be staged by the runtime under a process-wide lock: with many contexts -- the sweep's 8-32
+  // worker threads -- that lock, not the GPUs, set the rate)
+  const size_t bytes = (size_t) 8 * n * sizeof(double);
+  B200RT_CUDA(c, c->host_stage.ensure(bytes));
+  for (int a = 0; a < 8; a++) std::memcpy(c->host_stage.as<double>() + (size_t) a * n, arr[a], (size_t) n * sizeof(double));
+  if (sizeof(Real) == sizeof(double)) {
+    B200RT_CUDA(c, cudaMemcpyAsync(E.tabs.p, c->host_stage.p, bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    B200RT_CUDA(c, c->dev_stage.ensure(bytes));
+    B200RT_CUDA(c, cudaMemcpyAsync(c->dev_stage.p, c->host_stage.p, bytes, cudaMemcpyHostToDevice, c->stream));
+    B200RT_CUDA(c, launch_convert<Real>(c->dev_stage.as<double>(), E.tabs.as<Real>(), (long long) 8 * n, c->stream));
   }
-  stage.release();
-  return rc;
+  B200RT_CUDA(c, launch_phi_table<Real>(E.tabs.as<Real>(), E.tabs.as<Real>() + 2 * (size_t) n, E.tabs.as<Real>() + 3 * (size_t) n, n,
+                                        E.phi.as<Real>(), E.mrec.as<Real>(), c->stream));
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  return B200RT_OK;
 }
 
 

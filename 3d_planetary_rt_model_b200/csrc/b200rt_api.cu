@@ -49,6 +49,8 @@ int b200rt_destroy(b200rt_ctx *c) {
   c->host_scratch.release();
   c->host_words.release();
   c->host_out.release();
+  c->host_stage.release();
+  c->dev_stage.release();
   for (int e = 0; e < MAX_EMISSIONS; e++) {
     Emission &E = c->em[e];
     DevBuf *eb[] = {&E.tabs, &E.phi, &E.mrec, &E.K, &E.S0, &E.tau_sp, &E.tau_abs, &E.S, &E.S_real, &E.rec_pt, &E.rec_avg};
@@ -287,16 +289,20 @@ int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp
   if (e < 0 || e >= c->n_em) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
   Emission &E = c->em[e];
-  const size_t nb = (size_t) c->hg.n_vox * sizeof(double);
-  if (S) {
-    if (!E.have_S) return fail(c, B200RT_ERR_STATE, "source function not solved");
-    B200RT_CUDA(c, cudaMemcpyAsync(S, E.S.p, nb, cudaMemcpyDeviceToHost, c->stream));
-  }
+  const size_t n = (size_t) c->hg.n_vox, nb = n * sizeof(double);
+  if (S && !E.have_S) return fail(c, B200RT_ERR_STATE, "source function not solved");
   if ((S0 || tsp || tab) && !E.have_K) return fail(c, B200RT_ERR_STATE, "influence pass not run");
-  if (S0) B200RT_CUDA(c, cudaMemcpyAsync(S0, E.S0.p, nb, cudaMemcpyDeviceToHost, c->stream));
-  if (tsp) B200RT_CUDA(c, cudaMemcpyAsync(tsp, E.tau_sp.p, nb, cudaMemcpyDeviceToHost, c->stream));
-  if (tab) B200RT_CUDA(c, cudaMemcpyAsync(tab, E.tau_abs.p, nb, cudaMemcpyDeviceToHost, c->stream));
+  // through page-locked staging: a copy into the caller's (pageable) arrays would block inside the runtime under a lock
+  // that stalls the other contexts of the process (common.hpp, PinnedBuf)
+  B200RT_CUDA(c, c->host_stage.ensure(4 * nb));
+  double *hs = c->host_stage.as<double>();
+  double *dst[4] = {S, S0, tsp, tab};
+  const void *src[4] = {E.S.p, E.S0.p, E.tau_sp.p, E.tau_abs.p};
+  for (int q = 0; q < 4; q++)
+    if (dst[q]) B200RT_CUDA(c, cudaMemcpyAsync(hs + q * n, src[q], nb, cudaMemcpyDeviceToHost, c->stream));
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int q = 0; q < 4; q++)
+    if (dst[q]) std::memcpy(dst[q], hs + q * n, nb);
   return B200RT_OK;
 }
 
@@ -342,7 +348,9 @@ int b200rt_set_sourcefn(b200rt_ctx *c, int e, const double *S) {
   Emission &E = c->em[e];
   if (!E.defined) return fail(c, B200RT_ERR_STATE, "emission not defined");
   const int n = c->hg.n_vox;
-  B200RT_CUDA(c, cudaMemcpyAsync(E.S.p, S, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  B200RT_CUDA(c, c->host_stage.ensure((size_t) n * sizeof(double)));
+  std::memcpy(c->host_stage.p, S, (size_t) n * sizeof(double));
+  B200RT_CUDA(c, cudaMemcpyAsync(E.S.p, c->host_stage.p, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (is64(c)) B200RT_CUDA(c, launch_convert<double>(E.S.as<double>(), E.S_real.as<double>(), n, c->stream));
   else B200RT_CUDA(c, launch_convert<float>(E.S.as<double>(), E.S_real.as<float>(), n, c->stream));
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));

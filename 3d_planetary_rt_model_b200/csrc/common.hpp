@@ -219,6 +219,8 @@ struct b200rt_ctx {
   b200rt::DevBuf step_counter;      // unsigned long long
   b200rt::PinnedBuf host_scratch;   // solve read-backs (margins, residuals)
   b200rt::PinnedBuf host_out;       // brightness results on their way to PAGEABLE caller arrays (b200rt_brightness)
+  b200rt::PinnedBuf host_stage;     // small uploads / downloads of caller (pageable) arrays travel through here
+  b200rt::DevBuf dev_stage;         // float builds: the doubles of an upload before they are narrowed on the device
   b200rt::PinnedBuf host_words;     // counters and flags: [0] overflow flag (int), [1] step / sub-step counter (u64)
   long long last_steps = 0;
   long long last_substeps = 0;      // line-of-sight sub-steps of the last singlet brightness call

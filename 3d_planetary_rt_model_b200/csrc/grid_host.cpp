@@ -135,9 +135,14 @@ int upload_grid(b200rt_ctx *c) {
   put(o_vzn, vzn.data(), n_vox * sizeof(Real));
   put(o_cls, rcls.data(), n_rays * sizeof(int));   put(o_clr, cls_ray.data(), n_cls * sizeof(int));
 
+  // the slab and, below, the sun-ward ray block each travel as one asynchronous copy out of page-locked staging (see
+  // set_singlet_impl: copies out of pageable memory are staged by the runtime under a process-wide lock)
+  const size_t rbytes = (size_t) n_vox * sizeof(Real);
+  const size_t sun_bytes = 5 * rbytes + 2 * (size_t) n_vox * sizeof(int);
+  B200RT_CUDA(c, c->host_stage.ensure(slab.size() + sun_bytes));
   B200RT_CUDA(c, c->grid_tables.ensure(slab.size()));
-  B200RT_CUDA(c, cudaMemcpyAsync(c->grid_tables.p, slab.data(), slab.size(), cudaMemcpyHostToDevice, c->stream));
-  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::memcpy(c->host_stage.p, slab.data(), slab.size());
+  B200RT_CUDA(c, cudaMemcpyAsync(c->grid_tables.p, c->host_stage.p, slab.size(), cudaMemcpyHostToDevice, c->stream));
 
   if (c->grid_view) { ::operator delete(c->grid_view); c->grid_view = nullptr; }
   GridView<Real> *g = new GridView<Real>;
@@ -164,21 +169,18 @@ int upload_grid(b200rt_ctx *c) {
     char *tb = static_cast<char *>(c->sph_table.p);
     g->sph_de = (const Real *) (tb + t_de);  g->sph_d = (const Real *) (tb + t_d);
     g->sph_hdr = (const int *) (tb + t_hdr); g->sph_i = (const int *) (tb + t_i);
-    B200RT_CUDA(c, launch_sphere_table<Real>(*g, c->stream));
-    B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    B200RT_CUDA(c, launch_sphere_table<Real>(*g, c->stream));   // (same stream as the slab copy; the sync below covers it)
   }
   c->grid_view = g;
 
   // sun-ward ray descriptors + shadow flags: [r | z | t | cost | lz](Real) [i_voxel | shadow](int)
-  const size_t rbytes = (size_t) n_vox * sizeof(Real);
-  B200RT_CUDA(c, c->sun_rays.ensure(5 * rbytes + 2 * (size_t) n_vox * sizeof(int)));
-  char *sp = static_cast<char *>(c->sun_rays.p);
+  B200RT_CUDA(c, c->sun_rays.ensure(sun_bytes));
+  char *hp = static_cast<char *>(c->host_stage.p) + slab.size();
   const void *srcs[5] = {sr.data(), sz.data(), stt.data(), scost.data(), slz.data()};
-  for (int a = 0; a < 5; a++)
-    B200RT_CUDA(c, cudaMemcpyAsync(sp + a * rbytes, srcs[a], rbytes, cudaMemcpyHostToDevice, c->stream));
-  B200RT_CUDA(c, cudaMemcpyAsync(sp + 5 * rbytes, sidx.data(), n_vox * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  B200RT_CUDA(c, cudaMemcpyAsync(sp + 5 * rbytes + n_vox * sizeof(int), c->shadow.data(), n_vox * sizeof(int),
-                                 cudaMemcpyHostToDevice, c->stream));
+  for (int a = 0; a < 5; a++) std::memcpy(hp + a * rbytes, srcs[a], rbytes);
+  std::memcpy(hp + 5 * rbytes, sidx.data(), n_vox * sizeof(int));
+  std::memcpy(hp + 5 * rbytes + n_vox * sizeof(int), c->shadow.data(), n_vox * sizeof(int));
+  B200RT_CUDA(c, cudaMemcpyAsync(c->sun_rays.p, hp, sun_bytes, cudaMemcpyHostToDevice, c->stream));
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
   return B200RT_OK;
 }

@@ -1,5 +1,6 @@
 // observation_fit.cpp -- see observation_fit.hpp
 #include "observation_fit.hpp"
+#include <cstdio>
 #include <cstdlib>
 #include <atomic>
 #include <chrono>
@@ -744,6 +745,11 @@ vector<vector<vector<observation_fit::Real>>> observation_fit::brightness_batch(
   std::atomic<int> next(0);
   vector<string> errors(n_workers);
   const auto t0 = std::chrono::steady_clock::now();
+  // B200RT_BATCH_PROFILE=1: wall time per stage, summed over the worker threads (development aid)
+  static const bool profile = getenv("B200RT_BATCH_PROFILE") != nullptr;
+  std::atomic<long long> t_stage[5];
+  for (auto &t : t_stage) t = 0;
+  auto now_us = [] { return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   auto work = [&](int w) {
     b200rt_ctx *c = nullptr;
     try {
@@ -751,13 +757,19 @@ vector<vector<vector<observation_fit::Real>>> observation_fit::brightness_batch(
       bool first = true;
       set_inputs in;
       for (int i = next++; i < n_sets; i = next++) {
+        long long ta = profile ? now_us() : 0;
         chamb_diff_1d atm(nHexo[i], CO2_exobase_density, Texo[i]);
         atm.copy_H_options(H_cross_section_options);
+        if (profile) { const long long tb = now_us(); t_stage[0] += tb - ta; ta = tb; }
         build_inputs(atm, Texo[i], false, in);
+        if (profile) { const long long tb = now_us(); t_stage[1] += tb - ta; ta = tb; }
         load_inputs(c, in);
+        if (profile) { const long long tb = now_us(); t_stage[2] += tb - ta; ta = tb; }
         check(b200rt_generate_S(c), c);
+        if (profile) { const long long tb = now_us(); t_stage[3] += tb - ta; ta = tb; }
         vector<vector<Real>> q[4];
         run_brightness(c, first, q);
+        if (profile) { const long long tb = now_us(); t_stage[4] += tb - ta; ta = tb; }
         first = false;
         if (sim_iph)
           for (int e = 0; e < n_hydrogen_emissions; e++)
@@ -776,6 +788,11 @@ vector<vector<vector<observation_fit::Real>>> observation_fit::brightness_batch(
   for (int w = 0; w < n_workers; w++) pool.emplace_back(work, w);
   for (auto &t : pool) t.join();
   batch_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (profile)
+    fprintf(stderr, "brightness_batch: %d sets, %d workers, %.3f s wall; per set (ms, thread time): atmosphere %.3f  build_inputs %.3f  "
+            "load_inputs %.3f  generate_S %.3f  brightness %.3f\n", n_sets, n_workers, batch_seconds,
+            t_stage[0] / 1e3 / n_sets, t_stage[1] / 1e3 / n_sets, t_stage[2] / 1e3 / n_sets, t_stage[3] / 1e3 / n_sets,
+            t_stage[4] / 1e3 / n_sets);
   for (auto &e : errors)
     if (!e.empty()) throw std::runtime_error("brightness_batch: " + e);
   return result;
