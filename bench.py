@@ -492,8 +492,10 @@ def run_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import extra_bench
             ex = extra_bench.iph(n_los, world)
-            # worker threads = contexts x GPUs: no more of them than host cores (a set is host-latency bound)
-            ex.update(extra_bench.sweep(512, 10000, max(1, min(4, (os.cpu_count() or 16) // world)), world))
+            # worker threads = contexts x GPUs.  Measured on an 8-GPU box (tools/dev/sweep_gpus.py): 8 GPUs x 1 / 2 / 3 / 4
+            # contexts 1747 / 1823 / 1520 / 1230 sets/s, 4 GPUs 1185 / 1660 / 1668 / 1594, 1 GPU best at 4: beyond ~16
+            # threads the process-wide host side of the runtime, not the GPUs, sets the rate
+            ex.update(extra_bench.sweep(512, 10000, 4 if world <= 2 else 2, world))
             if world == 1:
                 ex.update(extra_bench.multiplet(0))
                 ex.update(extra_bench.multiplet(1))
