@@ -25,41 +25,41 @@ namespace api {
 // list: 686k LOS in 29.63 ms, 314k in 14.35 ms).  B200RT_SCRATCH_BYTES overrides it (tests force several batches).
 constexpr size_t SCRATCH_BUDGET_BYTES = size_t(1) << 33;
 
+// Events come from a per-context pool (created once, reused by every call): a parameter-set sweep makes ~25 timers per
+// set on each of 8-16 threads, and event creation / destruction goes through process-wide runtime state.
 struct PhaseTimer {
   b200rt_ctx *c;
   int phase;
   cudaEvent_t a, b;
-  bool stopped = false;
-  PhaseTimer(b200rt_ctx *ctx, int ph) : c(ctx), phase(ph) {
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
-    cudaEventRecord(a, c->stream);
+  static cudaEvent_t take(b200rt_ctx *c) {
+    if (c->timer_used == c->timer_events.size()) {
+      cudaEvent_t e = nullptr;
+      cudaEventCreate(&e);
+      c->timer_events.push_back(e);
+    }
+    return c->timer_events[c->timer_used++];
   }
+  PhaseTimer(b200rt_ctx *ctx, int ph) : c(ctx), phase(ph), a(take(ctx)), b(take(ctx)) { cudaEventRecord(a, c->stream); }
   PhaseTimer(const PhaseTimer &) = delete;
-  ~PhaseTimer() {   // an error path returned before stop(): the events are not handed to pending()
-    if (!stopped) { cudaEventDestroy(a); cudaEventDestroy(b); }
-  }
   void stop(int launches) {
     cudaEventRecord(b, c->stream);
     pending().push_back({phase, launches, a, b});
-    stopped = true;
   }
   struct Rec { int phase, launches; cudaEvent_t a, b; };
   static std::vector<Rec> &pending() { static thread_local std::vector<Rec> v; return v; }
   static void reset(b200rt_ctx *c) {
     for (int p = 0; p < PH_COUNT; p++) { c->phase_ms[p] = 0; c->phase_launches[p] = 0; }
-    for (auto &r : pending()) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
-    pending().clear();
+    pending().clear();   // records an error path left behind; their events stay in the pool
+    c->timer_used = 0;
   }
   static void collect(b200rt_ctx *c) {   // call after the stream has been synchronised
     for (auto &r : pending()) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) c->phase_ms[r.phase] += ms;
       c->phase_launches[r.phase] += r.launches;
-      cudaEventDestroy(r.a);
-      cudaEventDestroy(r.b);
     }
     pending().clear();
+    c->timer_used = 0;
   }
 };
 

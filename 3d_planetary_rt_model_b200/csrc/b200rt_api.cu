@@ -64,6 +64,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   }
   if (c->grid_view) ::operator delete(c->grid_view);
   for (cudaEvent_t ev : c->lu_events) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : c->timer_events) cudaEventDestroy(ev);
   if (c->lu_graph) cudaGraphExecDestroy(c->lu_graph);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->out_stream) cudaStreamDestroy(c->out_stream);

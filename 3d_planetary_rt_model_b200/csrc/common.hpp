@@ -237,6 +237,9 @@ struct b200rt_ctx {
   cudaStream_t stream2 = nullptr;            // chain stream of the LU (diagonal-block inverse + panel), high priority
   cudaStream_t stream3 = nullptr;            // stream of the L-shaped update next to the diagonal, high priority
   std::vector<cudaEvent_t> lu_events;
+  std::vector<cudaEvent_t> timer_events;     // PhaseTimer's pool: created on first use, reused by every call
+  size_t timer_used = 0;
+  bool solve_attrs_set = false;              // the LU kernels' dynamic shared memory limits were raised on this device
   cudaGraphExec_t lu_graph = nullptr;        // the factorisation + back substitution of one (np, workspace), replayed
   int lu_graph_np = 0, lu_graph_launches = 0;
   const void *lu_graph_A = nullptr, *lu_graph_dinv = nullptr;

@@ -897,15 +897,18 @@ int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const d
 
   const size_t gemm_smem = gemm_smem_bytes(KC_BULK, STAGES_BULK, TN / 2);             // 128x64 tiles, bulk update
   const size_t gemm_smem_h = gemm_smem_bytes(KC_DEFAULT, STAGES_DEFAULT, TN / 2);     // 128x64 tiles
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1, 4, KC_BULK, STAGES_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
   // quarter-width tiles (128x32) for the two kernels of the critical path once the trailing matrix is small: four
   // times as many CTAs, half the DMMA work each -- the tail of the factorisation is latency, not throughput
   const size_t gemm_smem_q = gemm_smem_bytes(KC_DEFAULT, STAGES_DEFAULT, TN / 4);
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
-  B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
-  B200RT_CUDA(c, cudaFuncSetAttribute(backsolve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (TB * TB * sizeof(double))));
+  if (!c->solve_attrs_set) {   // per device, not per call: a sweep solves thousands of small systems
+    B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
+    B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<1, 4, KC_BULK, STAGES_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem));
+    B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_h));
+    B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
+    B200RT_CUDA(c, cudaFuncSetAttribute(gemm128_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gemm_smem_q));
+    B200RT_CUDA(c, cudaFuncSetAttribute(backsolve_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (TB * TB * sizeof(double))));
+    c->solve_attrs_set = true;
+  }
   static const int quarter_below = getenv("B200RT_LU_QUARTER_BELOW") ? atoi(getenv("B200RT_LU_QUARTER_BELOW")) : 1024;
   // (quarter-width tiles for the chain kernels whenever fewer block columns than this remain.  Measured, n = 5841:
   //  never 6.15 ms, below 20: 5.94, below 36: 5.88, always: 5.80 -- with 58 kB of shared memory per CTA several quarter
