@@ -124,7 +124,9 @@ int brightness_impl(b200rt_ctx *c, int n_subsamples, const HostLos *io = nullptr
     }
     if (io) B200RT_CUDA(c, cudaStreamWaitEvent(c->stream, uploaded_all, 0));
     const int *order = nullptr;
-    if (lv.cap <= LOS_ORDER_MAX_CAP && count >= los_order_min()) {
+    // (a split launch that does not fit the machine at once is ordered too: its second wave then holds the short ones)
+    const bool split_overflows = brightness_splits_emissions(c->n_em, count) && 2 * count > brightness_resident_groups();
+    if (lv.cap <= LOS_ORDER_MAX_CAP && (count >= los_order_min() || split_overflows)) {
       PhaseTimer t(c, PH_ORDER);   // histogram, prefix, scatter: timed and counted apart from the march they feed
       int *bins = c->los_order.as<int>(), *ord = bins + 2 * (lv.cap + 1);
       B200RT_CUDA(c, launch_los_order(lv.len, count, lv.cap, bins, ord, c->stream));
@@ -194,23 +196,31 @@ template <class Real>
 int los_download_impl(b200rt_ctx *c, double *const dst[4], long long stride, long long offset) {
   const long long n = c->n_los;
   const Real *o = c->los_out.as<Real>();
-  DevBuf stage;
+  // results travel to page-locked staging in one burst and are copied out by the host: a device -> pageable copy blocks
+  // inside the runtime one array at a time (and, in float, the widening happens on the way out)
+  int n_arrays = 0;
+  for (int q = 0; q < 4; q++) n_arrays += dst[q] != nullptr;
+  if (n_arrays == 0 || n == 0) return B200RT_OK;
+  B200RT_CUDA(c, c->host_out.ensure((size_t) c->n_em * n_arrays * n * sizeof(Real)));
+  Real *stage = c->host_out.as<Real>();
+  size_t k = 0;
   for (int e = 0; e < c->n_em; e++)
     for (int q = 0; q < 4; q++) {
       if (!dst[q]) continue;
-      const Real *src = o + ((size_t) e * 4 + q) * n;
-      double *out = dst[q] + (size_t) e * stride + offset;
-      if (sizeof(Real) == sizeof(double)) {
-        B200RT_CUDA(c, cudaMemcpyAsync(out, src, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      } else {
-        std::vector<float> tmp(n);
-        B200RT_CUDA(c, cudaMemcpyAsync(tmp.data(), src, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (long long i = 0; i < n; i++) out[i] = tmp[i];
-      }
+      B200RT_CUDA(c, cudaMemcpyAsync(stage + k * n, o + ((size_t) e * 4 + q) * n, n * sizeof(Real), cudaMemcpyDeviceToHost, c->stream));
+      k++;
     }
   B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
-  stage.release();
+  k = 0;
+  for (int e = 0; e < c->n_em; e++)
+    for (int q = 0; q < 4; q++) {
+      if (!dst[q]) continue;
+      double *out = dst[q] + (size_t) e * stride + offset;
+      const Real *src = stage + k * n;
+      if (sizeof(Real) == sizeof(double)) std::memcpy(out, src, n * sizeof(double));
+      else for (long long i = 0; i < n; i++) out[i] = src[i];
+      k++;
+    }
   return B200RT_OK;
 }
 

@@ -126,12 +126,16 @@ template <> struct LineShape<float> {
 #ifndef BR_MIN_BLOCKS
 #define BR_MIN_BLOCKS 4
 #endif
-template <class Real, int NEM>
+template <class Real, int NEM, bool SPLIT = false>
 __global__ void __launch_bounds__(128, (NEM == 2 && sizeof(Real) == 8) ? 3 : BR_MIN_BLOCKS)
 brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> em1,
                   const Real *__restrict__ los_in, long long los_stride, long long first, long long count,
                   ListView<Real> lists, int n_subsamples, Real *__restrict__ out, long long n_los_total,
                   int *queue, unsigned long long *substep_counter, const int *__restrict__ order) {
+  // SPLIT (NEM == 1 only): the queue holds 2 * count items, item t is line of sight t / 2 of emission t % 2
+  // (em0, em1).  A small batch gives every group one line of sight whatever the order, so the launch lasts as long as
+  // its longest line of sight; with the two emissions on different groups that chain is half as long.  The arithmetic
+  // of an (emission, line of sight) pair is the same either way.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GeomTables<Real> T;
   T.load(smem_raw, g);            // axes of the grid + the reciprocal tables of the double path; ends with a barrier
@@ -156,9 +160,14 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
     wgt[m] = (i == 0 || i == N_LAMBDA - 1) ? delta_lambda : Real(2.0) * delta_lambda;
   }
   Real gfac[NEM];
+  const Real *rec_pt[NEM], *rec_avg[NEM];
 #pragma unroll
-  for (int e = 0; e < NEM; e++)
+  for (int e = 0; e < NEM; e++) {
     gfac[e] = em[e].g_factor * em[e].branching / em[e].sigma_ref * (Real) 0.56418958354775628695 / Real(1e9);
+    rec_pt[e] = em[e].rec_pt; rec_avg[e] = em[e].rec_avg;
+  }
+  int e_base = 0;                                    // emission of this group's line of sight when the launch is split
+  const long long n_items = SPLIT ? 2 * count : count;
 
   // group state
   bool have = false, exhausted = false;
@@ -176,7 +185,15 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       int t = 0;
       if (sub == 0) t = atomicAdd(queue, 1);
       t = __shfl_sync(gmask, t, lead);
-      if (t >= count) { exhausted = true; break; }
+      if (t >= n_items) { exhausted = true; break; }
+      if (SPLIT) {
+        e_base = t & 1;
+        t >>= 1;
+        const EmissionView<Real> &E = e_base ? em1 : em0;
+        gfac[0] = E.g_factor * E.branching / E.sigma_ref * (Real) 0.56418958354775628695 / Real(1e9);
+        rec_pt[0] = E.rec_pt;
+        rec_avg[0] = E.rec_avg;
+      }
       if (order) t = order[t];      // longest lines of sight first: the queue drains with short ones (launch_los_order)
       los = first + t;
       const int len = lists.len[t];
@@ -185,12 +202,12 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
 #pragma unroll
           for (int e = 0; e < NEM; e++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) out[((size_t) e * 4 + q) * n_los_total + los] = Real(0);
+            for (int q = 0; q < 4; q++) out[((size_t) (SPLIT ? e_base : e) * 4 + q) * n_los_total + los] = Real(0);
         }
         continue;
       }
       total = (len - 1) * nss;
-      if (sub == 0) my_substeps += (unsigned long long) total;
+      if (sub == 0 && (!SPLIT || e_base == 0)) my_substeps += (unsigned long long) total;
       flagbits = lists.flag[t];
       dl = lists.dist + (size_t) t * lists.cap;
       el = lists.ent + (size_t) t * lists.cap;
@@ -230,7 +247,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       if (!interp) {
 #pragma unroll
         for (int e = 0; e < NEM; e++) {
-          const Real *r = em[e].rec_avg + (size_t) cur * REC;
+          const Real *r = rec_avg[e] + (size_t) cur * REC;
 #pragma unroll
           for (int q = 0; q < 5; q++) my_in[e][q] = r[q];
         }
@@ -240,7 +257,7 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
         const Real dist = d_start + is * d_step;
         substep_interp<Real>(T, cur, px, py, pz, lx, ly, lz, dist, idx, w);
 #pragma unroll
-        for (int e = 0; e < NEM; e++) interp_record<Real>(em[e].rec_pt, idx, w, my_in[e]);
+        for (int e = 0; e < NEM; e++) interp_record<Real>(rec_pt[e], idx, w, my_in[e]);
       }
 #pragma unroll
       for (int e = 0; e < NEM; e++) my_in[e][0] = LineShape<Real>::param(my_in[e][0]);
@@ -294,10 +311,11 @@ brightness_kernel(GridView<Real> g, EmissionView<Real> em0, EmissionView<Real> e
       if (sub == 0) {
 #pragma unroll
         for (int e = 0; e < NEM; e++) {
-          out[((size_t) e * 4 + 0) * n_los_total + los] = acc_B[e];
-          out[((size_t) e * 4 + 1) * n_los_total + los] = acc_tsp[e];
-          out[((size_t) e * 4 + 2) * n_los_total + los] = (flagbits & 1) ? Real(-1.0) : acc_tab[e];   // exits_bottom
-          out[((size_t) e * 4 + 3) * n_los_total + los] = acc_col[e];
+          const size_t eo = (size_t) (SPLIT ? e_base : e) * 4;
+          out[(eo + 0) * n_los_total + los] = acc_B[e];
+          out[(eo + 1) * n_los_total + los] = acc_tsp[e];
+          out[(eo + 2) * n_los_total + los] = (flagbits & 1) ? Real(-1.0) : acc_tab[e];   // exits_bottom
+          out[(eo + 3) * n_los_total + los] = acc_col[e];
         }
       }
       have = false;
@@ -378,6 +396,13 @@ cudaError_t launch_pack_records(const EmissionView<Real> &em, int n_vox, Real *r
   return cudaGetLastError();
 }
 
+bool brightness_splits_emissions(int n_em, long long count) {
+  const char *env = getenv("B200RT_EM_SPLIT_MAX");   // read per call: the parity test switches it between two calls
+  const long long split_max = env ? atoll(env) : brightness_resident_groups();
+  return n_em == 2 && count <= split_max;
+}
+long long brightness_resident_groups() { return (long long) NUM_SMS * BR_MIN_BLOCKS * (128 / LPR); }
+
 template <class Real>
 cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> *em, int n_em, const Real *los_in,
                               long long los_stride, long long first, long long count, ListView<Real> lists,
@@ -388,11 +413,20 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
   if (e != cudaSuccess) return e;
   const int threads = 128;
   const size_t smem = GeomTables<Real>::doubles(g.n_rb, g.n_sb) * sizeof(Real);
-  const long long groups = (count + 0);
+  // two emissions, few lines of sight: one emission per group (see the kernel).  The limit is the number of groups the
+  // machine holds at once: beyond it groups take several lines of sight each and sharing the geometry between the
+  // emissions is worth more than the shorter chain.  B200RT_EM_SPLIT_MAX overrides (0: never).
+  const bool split = brightness_splits_emissions(n_em, count);
+  const long long groups = split ? 2 * count : count;
   long long blocks = (groups * LPR + threads - 1) / threads;
   const long long persistent = (long long) NUM_SMS * BR_MIN_BLOCKS;   // __launch_bounds__(128, BR_MIN_BLOCKS)
   if (blocks > persistent) blocks = persistent;
-  if (n_em == 1) {
+  if (split) {
+    e = cudaFuncSetAttribute(brightness_kernel<Real, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    brightness_kernel<Real, 1, true><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[1], los_in, los_stride, first, count,
+                                                                              lists, n_subsamples, out, n_los_total, queue, substep_counter, order);
+  } else if (n_em == 1) {
     e = cudaFuncSetAttribute(brightness_kernel<Real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     brightness_kernel<Real, 1><<<(unsigned) blocks, threads, smem, s>>>(g, em[0], em[0], los_in, los_stride, first, count,

@@ -323,6 +323,9 @@ cudaError_t launch_brightness(const GridView<Real> &g, const EmissionView<Real> 
                               const int *order, cudaStream_t s);
 // longest-first processing order of the `count` lists (counting sort of their lengths): bins = 2 * (cap + 1) ints of
 // scratch, order = count ints.  Returns cudaErrorInvalidValue when cap is too large for the shared-memory histogram.
+// two emissions and few lines of sight: the brightness launch gives each (line of sight, emission) pair its own group
+bool brightness_splits_emissions(int n_em, long long count);
+long long brightness_resident_groups();   // 4-lane groups the machine holds at once
 cudaError_t launch_los_order(const int *len, long long count, int cap, int *bins, int *order, cudaStream_t s);
 constexpr int LOS_ORDER_MAX_CAP = 8000;
 template <class Real>

@@ -756,6 +756,8 @@ vector<vector<vector<observation_fit::Real>>> observation_fit::brightness_batch(
       if (b200rt_create(w % n_gpus, precision, &c) != B200RT_OK) throw std::runtime_error("b200rt_create failed");
       bool first = true;
       set_inputs in;
+      const int n = n_obs();
+      vector<double> flat_B((size_t) n_hydrogen_emissions * n), flat_tab(sim_iph ? (size_t) n_hydrogen_emissions * n : 0);
       for (int i = next++; i < n_sets; i = next++) {
         long long ta = profile ? now_us() : 0;
         chamb_diff_1d atm(nHexo[i], CO2_exobase_density, Texo[i]);
@@ -767,17 +769,24 @@ vector<vector<vector<observation_fit::Real>>> observation_fit::brightness_batch(
         if (profile) { const long long tb = now_us(); t_stage[2] += tb - ta; ta = tb; }
         check(b200rt_generate_S(c), c);
         if (profile) { const long long tb = now_us(); t_stage[3] += tb - ta; ta = tb; }
-        vector<vector<Real>> q[4];
-        run_brightness(c, first, q);
+        // only what the batch returns travels back: brightness, and the absorber optical depth the IPH term is extincted by
+        if (first)
+          check(b200rt_los_upload(c, n, los[0].data(), los[1].data(), los[2].data(), los[3].data(), los[4].data(),
+                                  los[5].data(), los[6].data(), los[7].data(), los[8].data()), c);
+        check(b200rt_brightness_resident(c, 10), c);
+        check(b200rt_los_download(c, flat_B.data(), nullptr, sim_iph ? flat_tab.data() : nullptr, nullptr), c);
         if (profile) { const long long tb = now_us(); t_stage[4] += tb - ta; ta = tb; }
         first = false;
-        if (sim_iph)
-          for (int e = 0; e < n_hydrogen_emissions; e++)
-            for (int k = 0; k < n_obs(); k++) {
-              const Real ta = q[2][e][k];
-              q[0][e][k] += (ta != -1) ? iph_unextincted[k][e] * std::exp(-ta) : 0.0;
+        vector<vector<Real>> &out = result[i];
+        out.assign(n_hydrogen_emissions, vector<Real>());
+        for (int e = 0; e < n_hydrogen_emissions; e++) {
+          out[e].assign(flat_B.begin() + (size_t) e * n, flat_B.begin() + (size_t) (e + 1) * n);
+          if (sim_iph)
+            for (int k = 0; k < n; k++) {
+              const Real ta = flat_tab[(size_t) e * n + k];
+              out[e][k] += (ta != -1) ? iph_unextincted[k][e] * std::exp(-ta) : 0.0;
             }
-        result[i] = std::move(q[0]);
+        }
       }
     } catch (const std::exception &ex) {
       errors[w] = ex.what();

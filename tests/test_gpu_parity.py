@@ -152,6 +152,36 @@ def test_pipelined_host_brightness_equals_resident(synth, binding):
     assert np.array_equal(a["brightness"], c["brightness"])
 
 
+@pytest.mark.parametrize("n_los", [3000, 12000])
+def test_emission_split_brightness_is_the_same_arithmetic(synth, binding, n_los):
+    """two emissions and few lines of sight: launch_brightness gives every (line of sight, emission) pair its own 4-lane
+    group (brightness.cu, SPLIT) instead of one group per line of sight carrying both emissions.  Bit-identical results,
+    with the launch in input order (3000: fits the machine at once) and longest-first (12000: 24000 items > 18944 groups)"""
+    scn = synth.make_scenario(12, 8, 5, 6, n_em=2, sza_T_contrast=0.1)
+    G = binding.GpuModel(scn, "f64")
+    for e in range(2):
+        G.set_sourcefn(e, np.linspace(1.0, 0.05, scn.n_vox) * (1 + e))
+    locs, dirs = synth.random_los(n_los, seed=11)
+    G.ctx.los_upload(G.ctx.los_from_MSO(locs, dirs))
+    G.ctx.brightness_resident(10)
+    n_order = G.ctx.kernel_ms(binding.PH_ORDER)[1]
+    assert n_order == (3 if n_los == 12000 else 0)
+    steps = G.ctx.last_substep_count()
+    assert steps > 0
+    a = G.ctx.los_download()
+    os.environ["B200RT_EM_SPLIT_MAX"] = "0"
+    try:
+        G.ctx.brightness_resident(10)
+    finally:
+        del os.environ["B200RT_EM_SPLIT_MAX"]
+    assert G.ctx.kernel_ms(binding.PH_ORDER)[1] == 0
+    assert G.ctx.last_substep_count() == steps        # sub-steps are counted once per line of sight either way
+    b = G.ctx.los_download()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.any(a["brightness"][1] != a["brightness"][0])
+
+
 def test_edge_cases(synth, binding, oraclebind):
     scn = synth.make_scenario(12, 8, 5, 6, n_em=2)
     G = binding.GpuModel(scn, "f64")

@@ -1,7 +1,7 @@
-import sys, os, json
+"""sweep rate on one GPU against the number of contexts (worker threads) sharing it: 990 sets x 1e4 lines of sight"""
+import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import extra_bench
-for nlos in (10000, 500):
-    for c in (1, 2, 4, 8):
-        r = extra_bench.sweep(256, nlos, c, 1)
-        print("n_los", nlos, "contexts", c, "sets/s", round(r["sweep_sets_per_s"], 1), "ms/set", round(1e3 / r["sweep_sets_per_s"], 3), flush=True)
+for c in (int(a) for a in sys.argv[1:]) if len(sys.argv) > 1 else (1, 2, 4, 6, 8):
+    r = extra_bench.sweep(1024, 10000, c, 1)
+    print("contexts", c, "sets/s best", round(r["sweep_sets_per_s"], 1), "runs", [round(x) for x in r["sweep_sets_per_s_runs"]], flush=True)
