@@ -43,6 +43,9 @@ SIGNATURES = {
     "b200rt_ipc_open": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_void_p)]),
     "b200rt_ipc_close": (C.c_int, [_vp, _vp]),
     "b200rt_set_row_sink": (C.c_int, [_vp, C.c_int, _vp]),
+    "b200rt_solve_exchange": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.c_char_p]),
+    "b200rt_solve_distributed": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200rt_last_solve_steps": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "b200rt_multiplet_desc_init": (C.c_int, [C.c_int, C.c_int, _vp]),
     "b200rt_set_multiplet": (C.c_int, [_vp, _vp] + [_dp] * 6),
     "b200rt_generate_S": (C.c_int, [_vp]),
@@ -298,6 +301,24 @@ class Context:
 
     def set_row_sink(self, e, ptr):
         self._ck(self.lib.b200rt_set_row_sink(self.h, e, ptr))
+
+    # ---- distributed solve (include/b200rt.h): the rows stay where they were built
+    def solve_exchange(self, want_ipc=False):
+        """-> (device pointer of this context's exchange block, its 64-byte CUDA IPC handle or None)"""
+        p = C.c_void_p()
+        buf = C.create_string_buffer(64) if want_ipc else None
+        self._ck(self.lib.b200rt_solve_exchange(self.h, C.byref(p), buf))
+        return p.value, (buf.raw if want_ipc else None)
+
+    def solve_distributed(self, rank, world, blocks):
+        """blocks[q]: rank q's exchange block as addressable from this process (blocks[rank]: the own one)"""
+        arr = (C.c_void_p * world)(*[C.c_void_p(b) for b in blocks])
+        self._ck(self.lib.b200rt_solve_distributed(self.h, rank, world, arr))
+
+    def last_solve_steps(self):
+        n = C.c_int(0)
+        self._ck(self.lib.b200rt_last_solve_steps(self.h, C.byref(n)))
+        return n.value
 
     # ---- observations
     def los_from_MSO(self, locs, dirs):

@@ -130,6 +130,7 @@ int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges
   PhaseTimer::collect(c);
   c->last_steps = (long long) steps;
   for (int e = 0; e < c->n_em; e++) { c->em[e].have_K = true; c->em[e].have_S = false; }
+  c->built_ranges = ranges;
   return B200RT_OK;
 }
 

@@ -44,7 +44,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->grid_tables, &c->sun_rays, &c->list_dist, &c->list_ent, &c->list_len, &c->list_flag,
                     &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->los_order, &c->lu, &c->lu_dinv, &c->lu_flag,
-                    &c->iph.dev, &c->iph.io, &c->vox_map, &c->sph_table};
+                    &c->iph.dev, &c->iph.io, &c->vox_map, &c->sph_table, &c->kry_xchg, &c->kry_work};
   for (DevBuf *b : bufs) b->release();
   c->host_scratch.release();
   c->host_words.release();
@@ -309,7 +309,7 @@ int b200rt_get_solution(b200rt_ctx *c, int e, double *S, double *S0, double *tsp
 
 int b200rt_get_influence(b200rt_ctx *c, int e, int layout, double *K) {
   if (!c || !K) return B200RT_ERR_ARG;
-  GROUP_DISPATCH(c, group_forward(c, b200rt_get_influence(group_owner(c, e), e, layout, K)));
+  GROUP_DISPATCH(c, group_forward(c, b200rt_get_influence(group_owner_K(c, e), e, layout, K)));
   const bool mm = c->mult.defined;
   if (mm ? e != 0 : (e < 0 || e >= c->n_em)) return B200RT_ERR_ARG;
   cudaSetDevice(c->device);
@@ -371,7 +371,7 @@ int b200rt_last_residual(b200rt_ctx *c, int e, double *r) {
 
 int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, void **tab) {
   if (!c) return B200RT_ERR_ARG;
-  GROUP_DISPATCH(c, group_forward(c, b200rt_influence_dev(group_owner(c, e), e, K, S0, tsp, tab)));
+  GROUP_DISPATCH(c, group_forward(c, b200rt_influence_dev(group_owner_K(c, e), e, K, S0, tsp, tab)));
   if (c->mult.defined) {
     if (e != 0) return B200RT_ERR_ARG;
     Multiplet &M = c->mult;
@@ -396,7 +396,7 @@ int b200rt_influence_dev(b200rt_ctx *c, int e, void **K, void **S0, void **tsp, 
 // ---- peer-memory row exchange (one process per GPU): the solving rank exports its K, the others open it and
 // name it as the sink of their row batches
 int b200rt_ipc_export_influence(b200rt_ctx *c, int e, void *handle64) {
-  if (c && c->group) return group_forward(c, b200rt_ipc_export_influence(group_owner(c, e), e, handle64));
+  if (c && c->group) return group_forward(c, b200rt_ipc_export_influence(group_owner_K(c, e), e, handle64));
   if (!c || !handle64 || e < 0 || e >= c->n_em || c->mult.defined) return B200RT_ERR_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   cudaSetDevice(c->device);
@@ -432,6 +432,33 @@ int b200rt_set_row_sink(b200rt_ctx *c, int e, void *peer_K_dev) {
   }
   c->row_sink[e] = peer_K_dev;
   c->row_sink_n_vox[e] = peer_K_dev ? c->hg.n_vox : 0;
+  return B200RT_OK;
+}
+
+int b200rt_solve_exchange(b200rt_ctx *c, void **block_dev, void *ipc_handle64) {
+  if (!c) return B200RT_ERR_ARG;
+  if (c->group) return fail(c, B200RT_ERR_STATE, "b200rt_solve_exchange: a device group wires its own exchange blocks");
+  cudaSetDevice(c->device);
+  void *p = nullptr;
+  if (int rc = api::exchange_block(c, &p)) return rc;
+  if (block_dev) *block_dev = p;
+  if (ipc_handle64) {
+    cudaIpcMemHandle_t h;
+    B200RT_CUDA(c, cudaIpcGetMemHandle(&h, p));
+    std::memcpy(ipc_handle64, &h, sizeof h);
+  }
+  return B200RT_OK;
+}
+int b200rt_solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks) {
+  if (!c) return B200RT_ERR_ARG;
+  if (c->group) return fail(c, B200RT_ERR_STATE, "b200rt_solve_distributed: a device group does this behind b200rt_solve");
+  if (!c->have_grid || c->n_em < 1) return fail(c, B200RT_ERR_STATE, "grid / emissions not set");
+  cudaSetDevice(c->device);
+  return api::solve_distributed(c, rank, world, blocks, true);
+}
+int b200rt_last_solve_steps(b200rt_ctx *c, int *n_steps) {
+  if (!c || !n_steps) return B200RT_ERR_ARG;
+  *n_steps = c->group ? group_primary(c)->kry_last_iters : c->kry_last_iters;
   return B200RT_OK;
 }
 

@@ -239,6 +239,12 @@ struct b200rt_ctx {
   std::vector<cudaEvent_t> lu_events;
   std::vector<cudaEvent_t> timer_events;     // PhaseTimer's pool: created on first use, reused by every call
   size_t timer_used = 0;
+  // distributed solve (solve_krylov.cu): this context's exchange block (peers write into it), the work area, the source
+  // voxel ranges the last influence call built (= the rows this rank multiplies), the round counter's last value
+  b200rt::DevBuf kry_xchg, kry_work;
+  std::vector<std::pair<int, int>> built_ranges;
+  unsigned long long kry_round_base = 0;
+  int kry_last_iters = 0;
   bool solve_attrs_set = false;              // the LU kernels' dynamic shared memory limits were raised on this device
   cudaGraphExec_t lu_graph = nullptr;        // the factorisation + back substitution of one (np, workspace), replayed
   int lu_graph_np = 0, lu_graph_launches = 0;
@@ -373,6 +379,7 @@ int brightness_slice(b200rt_ctx *c, int n, const double *const src[9], int n_sub
 // ---- device_group.cu: one handle, several devices of one process (b200rt_create_multi)
 b200rt_ctx *group_primary(b200rt_ctx *g);
 b200rt_ctx *group_owner(b200rt_ctx *g, int i_emission);   // the member that gathered (and solves) emission e's rows
+b200rt_ctx *group_owner_K(b200rt_ctx *g, int e);   // ... with every row of K assembled there (gathers after a distributed build)
 int group_forward(b200rt_ctx *g, int rc);      // rc of a call on the primary member; copies its error text on failure
 int group_destroy(b200rt_ctx *g);
 int group_synchronize(b200rt_ctx *g);
@@ -410,6 +417,11 @@ int group_iph_model(b200rt_ctx *g, double g_lya, const double *marspos, int n_lo
 // ---- peaks.cu
 int measure_fp64_peaks(b200rt_ctx *c, double *dfma_tflops, double *dmma_tflops);
 
+// ---- solve_krylov.cu
+namespace api {
+int exchange_block(b200rt_ctx *c, void **dev_ptr);
+int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, bool reset_timer);
+}
 // ---- solve.cu
 struct SolveResult { double residual; double min_margin; int launches; };
 int solve_dense(b200rt_ctx *c, int n, const double *K, double branching, const double *S0,

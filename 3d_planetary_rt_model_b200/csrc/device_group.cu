@@ -107,6 +107,12 @@ struct Group {
   // fan-out thresholds
   long long min_rays = 262144, min_los = 65536;
   int chunks_per_member = 8;
+  // distributed solve (solve_krylov.cu): grids of kry_min_n voxels and more leave the rows on the members that built
+  // them and all members solve together; `shard_b/e` remember who holds which rows (for the rare caller that asks for
+  // the assembled matrix afterwards: rows_gathered)
+  int kry_min_n = 2048;
+  bool distributed = false, rows_gathered = true;
+  std::vector<std::vector<int>> shard_b, shard_e;
 };
 
 namespace {
@@ -169,6 +175,8 @@ int influence_rows(b200rt_ctx *g, int n_ranges, const int *vb, const int *ve) {
   // the multiplet emissions have no row sink (b200rt.h: singlet emissions only), and small builds do not pay for the
   // fan-out: both stay on the primary
   const bool split = !p->mult.defined && n_rows * p->hg.n_rays >= gr->min_rays && n_rows >= 2 * n_mem;
+  gr->distributed = false;
+  gr->rows_gathered = true;
   if (!split) {
     for (int e = 0; e < MAX_EMISSIONS; e++) gr->owner[e] = 0;
     for (int e = 0; e < p->n_em && !p->mult.defined; e++) b200rt_set_row_sink(p, e, nullptr);
@@ -211,11 +219,17 @@ int influence_rows(b200rt_ctx *g, int n_ranges, const int *vb, const int *ve) {
   }
   // emission e's rows are gathered on member e mod n_mem (one emission: the primary): every other member names that
   // member's resident K as its sink for e
-  for (int e = 0; e < MAX_EMISSIONS; e++) gr->owner[e] = (e < p->n_em) ? e % n_mem : 0;
+  // large grids, every row of the grid in this build: the rows stay on their members and the solve is distributed
+  gr->distributed = p->hg.n_vox >= gr->kry_min_n && p->hg.n_vox <= B200RT_KRYLOV_MAX_N && n_mem <= B200RT_KRYLOV_MAX_WORLD &&
+                    n_rows == p->hg.n_vox;
+  gr->rows_gathered = !gr->distributed;
+  gr->shard_b = rb;
+  gr->shard_e = re;
+  for (int e = 0; e < MAX_EMISSIONS; e++) gr->owner[e] = (e < p->n_em && !gr->distributed) ? e % n_mem : 0;
   for (int i = 0; i < n_mem; i++)
     for (int e = 0; e < p->n_em; e++) {
       b200rt_ctx *own = gr->m[gr->owner[e]];
-      const int rc = b200rt_set_row_sink(gr->m[i], e, gr->owner[e] == i ? nullptr : own->em[e].K.p);
+      const int rc = b200rt_set_row_sink(gr->m[i], e, (gr->distributed || gr->owner[e] == i) ? nullptr : own->em[e].K.p);
       if (rc != B200RT_OK) { g->err = gr->m[i]->err; return rc; }
     }
   const int rc = all(g, [&](int i) {
@@ -234,6 +248,21 @@ int solve_and_share(b200rt_ctx *g) {
   const int n_mem = (int) gr->m.size();
   const int n_e = p->mult.defined ? 1 : p->n_em;
   const size_t n_el = p->mult.defined ? (size_t) p->hg.n_vox * p->mult.d.n_upper : (size_t) p->hg.n_vox;
+  if (gr->distributed) {
+    // every member multiplies its own rows; S is resident on every member when the call returns
+    std::vector<void *> blocks(n_mem, nullptr);
+    for (int i = 0; i < n_mem; i++) {
+      cudaSetDevice(gr->m[i]->device);
+      if (int rc = api::exchange_block(gr->m[i], &blocks[i])) { g->err = gr->m[i]->err; return rc; }
+    }
+    const int rc = run_members(g, n_mem, [&](int i) {
+      cudaSetDevice(gr->m[i]->device);
+      return api::solve_distributed(gr->m[i], i, n_mem, blocks.data(), true);
+    });
+    if (rc != B200RT_OK) return rc;
+    collect_phases(gr, n_mem);
+    return B200RT_OK;
+  }
   bool spread = false;
   for (int e = 0; e < n_e; e++) spread = spread || gr->owner[e] != 0;
   if (!spread) {
@@ -266,6 +295,26 @@ int solve_and_share(b200rt_ctx *g) {
 }  // namespace
 
 b200rt_ctx *group_primary(b200rt_ctx *g) { return G(g)->m[0]; }
+// the member whose K holds every row of emission e.  After a distributed build the rows are still on the members that
+// built them: they are copied to the primary here, once, for the caller that wants the assembled matrix
+b200rt_ctx *group_owner_K(b200rt_ctx *g, int e) {
+  Group *gr = G(g);
+  if (gr->distributed && !gr->rows_gathered) {
+    b200rt_ctx *p = gr->m[0];
+    const size_t n = (size_t) p->hg.n_vox;
+    for (size_t i = 1; i < gr->m.size(); i++)
+      for (int em = 0; em < p->n_em; em++)
+        for (size_t k = 0; k < gr->shard_b[i].size(); k++) {
+          const size_t v0 = gr->shard_b[i][k], v1 = gr->shard_e[i][k];
+          cudaMemcpyPeer(p->em[em].K.as<double>() + v0 * n, p->device, gr->m[i]->em[em].K.as<double>() + v0 * n,
+                         gr->m[i]->device, (v1 - v0) * n * sizeof(double));
+        }
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    gr->rows_gathered = true;
+  }
+  return group_owner(g, e);
+}
 b200rt_ctx *group_owner(b200rt_ctx *g, int e) {
   Group *gr = G(g);
   if (e < 0 || e >= MAX_EMISSIONS || gr->m[0]->mult.defined) return gr->m[0];
@@ -512,6 +561,7 @@ int b200rt_create_multi(int n_dev, const int *dev_ids, int precision, b200rt_ctx
   gr->min_rays = env_ll("B200RT_GROUP_MIN_RAYS", gr->min_rays);
   gr->min_los = env_ll("B200RT_GROUP_MIN_LOS", gr->min_los);
   gr->chunks_per_member = (int) std::max(1LL, env_ll("B200RT_GROUP_CHUNKS", gr->chunks_per_member));
+  gr->kry_min_n = (int) env_ll("B200RT_KRYLOV_MIN_N", gr->kry_min_n);
   g->group = gr;
   g->device = ids[0];
   g->precision = precision;

@@ -1,0 +1,674 @@
+// solve_krylov.cu -- (I - w K) S = S0 with the rows of K left on the GPUs that built them (sm_100a).
+//
+// The reference solves the dense system on one device (emission_voxels::solve_gpu, cuSOLVER getrf/getrs,
+// emission_voxels.hpp:293-340); solve.cu is that path here (block LU, DMMA).  With the influence rows built on N GPUs the
+// LU is what the other N-1 wait for, and its input has to be gathered first.  This file is the N-GPU form of the solve:
+// K is the kernel of a second-kind integral equation, its spectrum clusters at 0, so GMRES on I - wK converges in a
+// number of steps that does not grow with the grid (measured with the CPU oracle, tools/dev/krylov_probe.py: 66 steps to
+// 1e-12, 78 to 1e-14 on both the 40x20 and the 100x60 grid; rho(wK) = 0.97, so the plain Neumann series needs ~900).
+// One step = one product with K: every rank multiplies ITS rows (n_vox^2 * 8 / N bytes from HBM, ~6 us on eight B200s),
+// writes its piece of the result straight into every rank's exchange block (peer stores over NVLink: plain peer access
+// inside a process, CUDA IPC between processes) and posts a round counter there; every rank then orthogonalises the
+// assembled vector redundantly with the same kernels in the same order, so the Krylov bases -- and the step at which the
+// iteration stops -- are bit-identical on all ranks and nothing else is ever exchanged.  No row gather, no broadcast of
+// S, no host barrier: the only synchronisation is a kernel of rank r waiting for the round counters of its peers.
+//
+// Per step (4 launches): kry_post<1>  x = w / |w| -> V[j];  (x - w K x)[own rows] -> every block;  post round
+//                        kry_orth<0>  wait for the round;  w = assembled vector;  partial V^T w per slice
+//                        kry_orth<1>  h1 = sum of partials;  w -= V h1;  partial V^T w          (classical Gram-Schmidt, twice)
+//                        kry_orth<2>  h2;  w -= V h2;  |w|^2 partials;  last CTA: Hessenberg column, Givens, residual, stop?
+// All sums run in a fixed order (no floating-point atomics): deterministic, and identical on every rank.
+// The round counters are monotonic over the life of a block and every rank runs the same rounds, so they never need
+// resetting; the vector slots alternate with the round (a rank can be at most one round ahead of a peer that still reads).
+#include <cstddef>
+#include <cstdio>
+#include "api_internal.hpp"
+
+namespace b200rt {
+
+namespace {
+
+constexpr int KRY_MAX_IT = 160;                      // Arnoldi steps (basis vectors) before giving up
+constexpr int KRY_SLICE = 96;                        // elements of the vector one CTA of the orthogonalisation owns
+constexpr int KRY_THREADS = 256;
+constexpr int KRY_WARPS = KRY_THREADS / 32;
+constexpr int KRY_VPT = 8;                            // basis vectors a warp has in flight per trip (L2 latency)
+constexpr int KRY_MAX_N = B200RT_KRYLOV_MAX_N;       // 16384 unknowns: the exchange block has a fixed layout
+constexpr int KRY_MAX_WORLD = B200RT_KRYLOV_MAX_WORLD;
+constexpr int KRY_MAX_B = (KRY_MAX_N + KRY_SLICE - 1) / KRY_SLICE;
+
+struct KryExchange {                                 // one per rank, written by every rank
+  unsigned long long flag[KRY_MAX_WORLD][16];        // flag[q][0]: rounds rank q has completed into THIS block (own 128-byte line)
+  double w[2][KRY_MAX_N];
+};
+static_assert(sizeof(KryExchange) == B200RT_KRYLOV_BLOCK_BYTES, "include/b200rt.h states the size of the exchange block");
+
+struct KryPeers {
+  KryExchange *p[KRY_MAX_WORLD];
+  int rank, world;
+};
+
+struct KryState {
+  unsigned long long round;          // rounds this rank has posted (monotonic; equal on all ranks between solves)
+  int iter, done, error, converged;
+  unsigned int post_tickets, orth_tickets, row_queue;
+  int max_it;
+  double beta, inv_norm, res, true_res, tol;
+};
+
+struct KryWork {                     // device pointers into one allocation
+  KryState *st;
+  double *V;                         // [KRY_MAX_IT + 1][ns]
+  double *wloc, *bvec, *xsol;        // [ns]
+  double *part1, *part2;             // [KRY_MAX_IT + 1][KRY_MAX_B]
+  double *npart;                     // [KRY_MAX_B]
+  double *R;                         // [KRY_MAX_IT + 1][KRY_MAX_IT], upper triangular after the rotations
+  double *cs, *sn, *g, *y;           // [KRY_MAX_IT + 1]
+  int ns;
+};
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_remote(const double *p) {       // written by a peer: never through L1
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_remote(double *p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// MODE 0: the right-hand side (S0 of the own rows, so that every rank starts from the same bits)
+// MODE 1: an Arnoldi step: x = wloc * inv_norm is basis vector `iter`;  (x - w K x)[own rows]
+// MODE 2: the residual check: (x - w K x)[own rows] for x = the solution
+// A CTA takes rows from a queue, one at a time: the row streams from HBM once (evict-first loads, 8 in flight per thread),
+// x (47 kB) is read through L1 where every CTA of the SM finds it; the scale 1/|w| is applied to the sum, not to the
+// 5841 operands.  The grid is as many CTAs as the machine holds (or as there are rows): measured, a warp per row left a
+// quarter-filled second wave running at the latency-bound rate (94 us per product), a CTA per row paid two system-wide
+// fences and a ticket per row (79 us for the 5841 rows of one GPU even without the product).
+template <int MODE>
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_post(const double *__restrict__ K, int n, const int *__restrict__ rows, int n_rows, double branching,
+         const double *__restrict__ S0, KryWork wk, KryPeers pe) {
+  KryState *st = wk.st;
+  if (MODE == 1 && st->done) return;
+  __shared__ double red[KRY_WARPS];
+  __shared__ int sh_row;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long round = st->round;      // (the last CTA advances it after every CTA has taken its ticket)
+  const int slot = (int) (round & 1);
+  const double *src = MODE == 1 ? wk.wloc : wk.xsol;
+  const double scale = MODE == 1 ? st->inv_norm : 1.0;
+  if (MODE == 1) {                                 // the grid stores the new basis vector, a chunk per CTA
+    const int chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * chunk, hi = min(n, lo + chunk);
+    double *Vj = wk.V + (size_t) st->iter * wk.ns;
+    for (int i = lo + tid; i < hi; i += KRY_THREADS) Vj[i] = src[i] * scale;
+  }
+  for (;;) {
+    if (tid == 0) sh_row = (int) atomicAdd(&st->row_queue, 1u);
+    __syncthreads();
+    const int slot_row = sh_row;
+    if (slot_row >= n_rows) break;
+    const int i = rows[slot_row];
+    double val = 0;
+    if (MODE == 0) {
+      val = S0[i];
+    } else {
+      const double *Kr = K + (size_t) i * n;
+      double acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) acc[u] = 0;
+      int col = tid;
+      for (; col + 7 * KRY_THREADS < n; col += 8 * KRY_THREADS) {
+        double k8[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) k8[u] = __ldcs(Kr + col + KRY_THREADS * u);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc[u] = fma(k8[u], __ldg(src + col + KRY_THREADS * u), acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {                  // the last, partial trip
+        const int cc = col + KRY_THREADS * u;
+        if (cc < n) acc[u] = fma(__ldcs(Kr + cc), __ldg(src + cc), acc[u]);
+      }
+      double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) red[warp] = s;
+      __syncthreads();
+      if (tid < 32) {
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < KRY_WARPS; k++) t += red[k];
+        val = scale * (__ldg(src + i) - branching * t);
+      }
+    }
+    if (tid < pe.world) st_remote(&pe.p[tid]->w[slot][i], val);
+    __syncthreads();                               // red[] and sh_row are reused by the next row
+  }
+  if (tid < pe.world) __threadfence_system();      // this CTA's pieces are visible everywhere before its ticket
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(&st->post_tickets, 1u);
+    if (t == gridDim.x - 1) {                      // every CTA's pieces are out: post the round on every rank
+      __threadfence_system();
+      st->post_tickets = 0;
+      st->row_queue = 0;
+      st->round = round + 1;
+      for (int q = 0; q < pe.world; q++) {
+        if (MODE == 0) pe.p[q]->flag[pe.rank][1] = (unsigned long long) n_rows;   // row census, checked by kry_begin
+        st_flag(&pe.p[q]->flag[pe.rank][0], round + 1);
+      }
+    }
+  }
+}
+
+// ---- pieces of the orthogonalisation; a CTA owns elements [lo, lo + len) of the vector, ws[] is its copy
+// partial dot products of the slice with basis vectors 0 .. nv-1 -> part[v][cta]
+__device__ __forceinline__ void slice_dots(const double *ws, const KryWork &wk, int lo, int len, int nv, double *part) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double wr[KRY_SLICE / 32];
+#pragma unroll
+  for (int u = 0; u < KRY_SLICE / 32; u++) wr[u] = (lane + 32 * u < len) ? ws[lane + 32 * u] : 0.0;
+  for (int v0 = warp; v0 < nv; v0 += KRY_VPT * KRY_WARPS) {      // KRY_VPT basis vectors per trip: their loads overlap (L2 latency)
+    double vv[KRY_VPT][KRY_SLICE / 32];
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++) {
+      const int v = v0 + k * KRY_WARPS;
+      const double *Vv = wk.V + (size_t) min(v, nv - 1) * wk.ns + lo;
+#pragma unroll
+      for (int u = 0; u < KRY_SLICE / 32; u++) vv[k][u] = (lane + 32 * u < len) ? Vv[lane + 32 * u] : 0.0;
+    }
+    double s[KRY_VPT];
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++) {
+      s[k] = 0;
+#pragma unroll
+      for (int u = 0; u < KRY_SLICE / 32; u++) s[k] = fma(vv[k][u], wr[u], s[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < KRY_VPT; k++) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++)
+      if (lane == 0 && v0 + k * KRY_WARPS < nv) part[(size_t) (v0 + k * KRY_WARPS) * KRY_MAX_B + blockIdx.x] = s[k];
+  }
+}
+// sum over the CTAs of p[0 .. n_cta): a warp, lane c taking p[c], p[c + 32], ... and a fixed shuffle tree (the same order
+// on every rank); valid on every lane
+__device__ __forceinline__ double warp_sum_partials(const double *p, int n_cta) {
+  const int lane = threadIdx.x & 31;
+  double s = 0;
+  for (int c = lane; c < n_cta; c += 32) s += p[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+// h[v] = sum over the CTAs of part[v][.]
+__device__ __forceinline__ void slice_reduce(const double *part, int nv, int n_cta, double *h) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v0 = warp; v0 < nv; v0 += KRY_VPT * KRY_WARPS) {
+    double s[KRY_VPT];
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++) {
+      const double *p = part + (size_t) min(v0 + k * KRY_WARPS, nv - 1) * KRY_MAX_B;
+      s[k] = 0;
+      for (int c = lane; c < n_cta; c += 32) s[k] += p[c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < KRY_VPT; k++) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++)
+      if (lane == 0 && v0 + k * KRY_WARPS < nv) h[v0 + k * KRY_WARPS] = s[k];
+  }
+}
+// ws -= sum_v h[v] V[v][slice]: warp k sums the vectors v = k mod 8, then the eight partial sums are added in order
+__device__ __forceinline__ void slice_update(double *ws, const KryWork &wk, int lo, int len, int nv, const double *h,
+                                             double (*red)[KRY_SLICE], double sign) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc[KRY_SLICE / 32];
+#pragma unroll
+  for (int u = 0; u < KRY_SLICE / 32; u++) acc[u] = 0;
+  for (int v0 = warp; v0 < nv; v0 += KRY_VPT * KRY_WARPS) {
+    double vv[KRY_VPT][KRY_SLICE / 32], hv[KRY_VPT];
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++) {
+      const int v = v0 + k * KRY_WARPS;
+      const double *Vv = wk.V + (size_t) min(v, nv - 1) * wk.ns + lo;
+      hv[k] = v < nv ? h[v] : 0.0;
+#pragma unroll
+      for (int u = 0; u < KRY_SLICE / 32; u++) vv[k][u] = (lane + 32 * u < len) ? Vv[lane + 32 * u] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++)
+#pragma unroll
+      for (int u = 0; u < KRY_SLICE / 32; u++) acc[u] = fma(hv[k], vv[k][u], acc[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < KRY_SLICE / 32; u++) red[warp][lane + 32 * u] = acc[u];
+  __syncthreads();
+  if ((int) threadIdx.x < len) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < KRY_WARPS; k++) s += red[k][threadIdx.x];
+    ws[threadIdx.x] += sign * s;
+  }
+  __syncthreads();
+}
+// sum over the slice of f, in a fixed order; valid on thread 0
+__device__ __forceinline__ double slice_sum(double f, double *scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = f;
+  __syncthreads();
+  double s = 0;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < KRY_WARPS; k++) s += scratch[k];
+  __syncthreads();
+  return s;
+}
+// thread 0 waits until every rank has posted `round` into this rank's block; false (and st->error) after 4 s
+__device__ __forceinline__ bool wait_round(KryState *st, const KryPeers &pe, unsigned long long round, int *sh_ok) {
+  if (threadIdx.x == 0) {
+    const KryExchange *mine = pe.p[pe.rank];
+    const unsigned long long t0 = global_ns();
+    int ok = 1;
+    for (int q = 0; q < pe.world && ok; q++) {
+      unsigned int spins = 0;
+      while (ld_flag(&mine->flag[q][0]) < round) {
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0 && global_ns() - t0 > 4000000000ull) { ok = 0; break; }
+      }
+    }
+    if (!ok) { st->error = 1; st->done = 1; }
+    *sh_ok = ok;
+  }
+  __syncthreads();
+  return *sh_ok != 0;
+}
+// true on the CTA that finishes last (all threads)
+__device__ __forceinline__ bool last_cta(KryState *st, int *sh_last) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&st->orth_tickets, 1u);
+    *sh_last = (t == gridDim.x - 1);
+    if (*sh_last) { st->orth_tickets = 0; __threadfence(); }
+  }
+  __syncthreads();
+  return *sh_last != 0;
+}
+
+// after kry_post<0>: b = the assembled right-hand side, beta = |b|, first residual vector = b
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_begin(int n, KryWork wk, KryPeers pe, double tol, int max_it) {
+  __shared__ double scratch[KRY_WARPS];
+  __shared__ int sh_flag;
+  KryState *st = wk.st;
+  const int tid = threadIdx.x;
+  const unsigned long long round = st->round;
+  if (!wait_round(st, pe, round, &sh_flag)) return;
+  const int slot = (int) ((round - 1) & 1);
+  const int lo = blockIdx.x * KRY_SLICE, len = min(KRY_SLICE, n - lo);
+  double b = 0;
+  if (tid < len) {
+    b = ld_remote(&pe.p[pe.rank]->w[slot][lo + tid]);
+    wk.bvec[lo + tid] = b;
+    wk.wloc[lo + tid] = b;
+  }
+  const double s = slice_sum(b * b, scratch);
+  if (tid == 0) wk.npart[blockIdx.x] = s;
+  const bool last = last_cta(st, &sh_flag);
+  if (last && tid < 32) {
+    const double t = warp_sum_partials(wk.npart, gridDim.x);
+    if (tid == 0) scratch[0] = t;
+  }
+  __syncthreads();
+  if (last && tid == 0) {
+    const double beta = sqrt(scratch[0]);
+    st->beta = beta;
+    st->inv_norm = beta > 0 ? 1.0 / beta : 0.0;
+    wk.g[0] = beta;
+    st->iter = 0;
+    st->res = 1.0;
+    st->true_res = -1.0;
+    st->tol = tol;
+    st->max_it = max_it;
+    st->converged = beta > 0 ? 0 : 1;       // S0 = 0: S = 0
+    st->done = beta > 0 ? 0 : 1;
+    unsigned long long census = 0;           // the ranks' rows must add up to the grid
+    for (int q = 0; q < pe.world; q++) census += ld_flag(&pe.p[pe.rank]->flag[q][1]);
+    if (census != (unsigned long long) n) { st->error = 2; st->done = 1; }
+  }
+}
+
+// PASS 0: wait, take the assembled vector, first partial V^T w.   PASS 1: w -= V h1, second partial V^T w.
+// PASS 2: w -= V h2, |w|^2; the last CTA closes the step (Hessenberg column, Givens rotation, residual estimate).
+template <int PASS>
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_orth(int n, KryWork wk, KryPeers pe) {
+  __shared__ double ws[KRY_SLICE];
+  __shared__ double red[KRY_WARPS][KRY_SLICE];
+  __shared__ double h[KRY_MAX_IT + 2];
+  __shared__ double scratch[KRY_WARPS];
+  __shared__ int sh_flag;
+  KryState *st = wk.st;
+  if (st->done) return;
+  const int tid = threadIdx.x;
+  const int lo = blockIdx.x * KRY_SLICE, len = min(KRY_SLICE, n - lo);
+  const int j = st->iter, nv = j + 1;          // basis vectors 0 .. j exist
+  if (PASS == 0) {
+    const unsigned long long round = st->round;
+    if (!wait_round(st, pe, round, &sh_flag)) return;
+    const int slot = (int) ((round - 1) & 1);
+    if (tid < len) ws[tid] = ld_remote(&pe.p[pe.rank]->w[slot][lo + tid]);
+    __syncthreads();
+    slice_dots(ws, wk, lo, len, nv, wk.part1);
+    if (tid < len) wk.wloc[lo + tid] = ws[tid];
+    return;
+  }
+  if (tid < len) ws[tid] = wk.wloc[lo + tid];
+  slice_reduce(PASS == 1 ? wk.part1 : wk.part2, nv, gridDim.x, h);
+  __syncthreads();
+  slice_update(ws, wk, lo, len, nv, h, red, -1.0);
+  if (tid < len) wk.wloc[lo + tid] = ws[tid];
+  if (PASS == 1) {
+    slice_dots(ws, wk, lo, len, nv, wk.part2);
+    return;
+  }
+  const double w2 = slice_sum(tid < len ? ws[tid] * ws[tid] : 0.0, scratch);
+  if (tid == 0) wk.npart[blockIdx.x] = w2;
+  if (!last_cta(st, &sh_flag)) return;
+  // ---- close step j: column j of the Hessenberg matrix is h1 + h2 (both Gram-Schmidt passes) and |w|
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    double *h1 = &red[4][0];                         // (red is free here: 8 x 96 doubles)
+    slice_reduce(wk.part1, nv, gridDim.x, h1);       // h still holds h2, the sums of part2
+    __syncthreads();
+    for (int v = tid; v < nv; v += KRY_THREADS) h[v] = h1[v] + h[v];
+    if (warp == 0) {
+      const double t = warp_sum_partials(wk.npart, gridDim.x);
+      if (lane == 0) scratch[0] = t;
+    }
+    double *rot = &red[0][0];                       // the rotations so far, staged for the serial sweep below
+    for (int i = tid; i < j; i += KRY_THREADS) { rot[2 * i] = wk.cs[i]; rot[2 * i + 1] = wk.sn[i]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double *rot = &red[0][0];
+    const double hn = sqrt(scratch[0]);
+    double hi = h[0];                               // the element the next rotation mixes with h[i + 1]
+    for (int i = 0; i < j; i++) {
+      const double c_ = rot[2 * i], s_ = rot[2 * i + 1], up = h[i + 1];
+      h[i] = c_ * hi + s_ * up;
+      hi = -s_ * hi + c_ * up;
+    }
+    const double d = hypot(hi, hn);
+    const double c_ = d > 0 ? hi / d : 1.0, s_ = d > 0 ? hn / d : 0.0;
+    h[j] = d;
+    wk.cs[j] = c_; wk.sn[j] = s_;
+    const double gj = wk.g[j];
+    wk.g[j + 1] = -s_ * gj;
+    wk.g[j] = c_ * gj;
+    const double res = fabs(wk.g[j + 1]) / st->beta;
+    st->res = res;
+    st->iter = j + 1;
+    st->inv_norm = hn > 0 ? 1.0 / hn : 0.0;
+    const bool conv = res <= st->tol || hn == 0.0;
+    st->converged = conv ? 1 : 0;
+    st->done = (conv || j + 1 >= st->max_it) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int i = tid; i <= j; i += KRY_THREADS) wk.R[(size_t) i * KRY_MAX_IT + j] = h[i];
+}
+
+// y = R^-1 g (k = iter unknowns), one warp
+__global__ void kry_backsolve(KryWork wk) {
+  const int k = wk.st->iter, lane = threadIdx.x;
+  for (int i = k - 1; i >= 0; i--) {
+    double s = 0;
+    for (int l = i + 1 + lane; l < k; l += 32) s = fma(wk.R[(size_t) i * KRY_MAX_IT + l], wk.y[l], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) wk.y[i] = (wk.g[i] - s) / wk.R[(size_t) i * KRY_MAX_IT + i];
+    __syncwarp();
+  }
+}
+// S = V y
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_solution(int n, KryWork wk, double *__restrict__ S) {
+  __shared__ double ws[KRY_SLICE];
+  __shared__ double red[KRY_WARPS][KRY_SLICE];
+  __shared__ double h[KRY_MAX_IT + 2];
+  const int tid = threadIdx.x;
+  const int lo = blockIdx.x * KRY_SLICE, len = min(KRY_SLICE, n - lo);
+  const int k = wk.st->iter;
+  for (int v = tid; v < k; v += KRY_THREADS) h[v] = wk.y[v];
+  if (tid < KRY_SLICE) ws[tid] = 0;
+  __syncthreads();
+  slice_update(ws, wk, lo, len, k, h, red, 1.0);
+  if (tid < len) { wk.xsol[lo + tid] = ws[tid]; S[lo + tid] = ws[tid]; }
+}
+// after kry_post<2>: |b - (I - wK) S| / |b|
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_residual(int n, KryWork wk, KryPeers pe) {
+  __shared__ double scratch[KRY_WARPS];
+  __shared__ int sh_flag;
+  KryState *st = wk.st;
+  const int tid = threadIdx.x;
+  const unsigned long long round = st->round;
+  if (st->error) return;
+  if (!wait_round(st, pe, round, &sh_flag)) return;
+  const int slot = (int) ((round - 1) & 1);
+  const int lo = blockIdx.x * KRY_SLICE, len = min(KRY_SLICE, n - lo);
+  double r = 0;
+  if (tid < len) r = wk.bvec[lo + tid] - ld_remote(&pe.p[pe.rank]->w[slot][lo + tid]);
+  const double s = slice_sum(r * r, scratch);
+  if (tid == 0) wk.npart[blockIdx.x] = s;
+  if (last_cta(st, &sh_flag) && tid < 32) {
+    const double t = warp_sum_partials(wk.npart, gridDim.x);
+    if (tid == 0) st->true_res = st->beta > 0 ? sqrt(t) / st->beta : 0.0;
+  }
+}
+
+size_t carve_bytes(size_t &off, size_t bytes) {
+  off = (off + 255) & ~size_t(255);
+  const size_t at = off;
+  off += bytes;
+  return at;
+}
+
+}  // namespace
+
+namespace api {
+
+int exchange_block(b200rt_ctx *c, void **dev_ptr) {
+  if (!c->kry_xchg.p) {
+    B200RT_CUDA(c, c->kry_xchg.ensure(sizeof(KryExchange)));
+    B200RT_CUDA(c, cudaMemsetAsync(c->kry_xchg.p, 0, sizeof(KryExchange), c->stream));
+    B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  if (dev_ptr) *dev_ptr = c->kry_xchg.p;
+  return B200RT_OK;
+}
+
+int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, bool reset_timer) {
+  const int n = c->hg.n_vox;
+  if (world < 1 || world > KRY_MAX_WORLD || rank < 0 || rank >= world || !blocks)
+    return fail(c, B200RT_ERR_ARG, "b200rt_solve_distributed: bad rank / world / blocks");
+  if (n > KRY_MAX_N) return fail(c, B200RT_ERR_CAPACITY, "b200rt_solve_distributed: more than 16384 unknowns");
+  if (c->mult.defined) return fail(c, B200RT_ERR_STATE, "b200rt_solve_distributed: singlet emissions only");
+  if (int rc = exchange_block(c, nullptr)) return rc;
+  if (blocks[rank] != c->kry_xchg.p)
+    return fail(c, B200RT_ERR_ARG, "b200rt_solve_distributed: blocks[rank] is not this context's exchange block");
+  if (reset_timer) PhaseTimer::reset(c);
+
+  // the rows this rank multiplies: what its last influence call built
+  std::vector<int> rows;
+  for (auto &r : c->built_ranges)
+    for (int v = r.first; v < r.second; v++) rows.push_back(v);
+  const int n_rows = (int) rows.size();
+
+  // work area
+  const int ns = (n + 31) & ~31;
+  size_t off = 0;
+  const size_t o_st = carve_bytes(off, sizeof(KryState));
+  const size_t o_V = carve_bytes(off, (size_t) (KRY_MAX_IT + 1) * ns * sizeof(double));
+  const size_t o_w = carve_bytes(off, (size_t) ns * sizeof(double)), o_b = carve_bytes(off, (size_t) ns * sizeof(double)),
+               o_x = carve_bytes(off, (size_t) ns * sizeof(double));
+  const size_t o_p1 = carve_bytes(off, (size_t) (KRY_MAX_IT + 1) * KRY_MAX_B * sizeof(double)),
+               o_p2 = carve_bytes(off, (size_t) (KRY_MAX_IT + 1) * KRY_MAX_B * sizeof(double));
+  const size_t o_np = carve_bytes(off, KRY_MAX_B * sizeof(double));
+  const size_t o_R = carve_bytes(off, (size_t) (KRY_MAX_IT + 1) * KRY_MAX_IT * sizeof(double));
+  const size_t o_cs = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double)), o_sn = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double)),
+               o_g = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double)), o_y = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double));
+  const size_t o_rows = carve_bytes(off, (size_t) std::max(n, 1) * sizeof(int));
+  const bool fresh = c->kry_work.bytes < off;
+  B200RT_CUDA(c, c->kry_work.ensure(off));
+  char *base = static_cast<char *>(c->kry_work.p);
+  if (fresh) {    // the round counter lives with the exchange block's life: it restarts only together with it
+    B200RT_CUDA(c, cudaMemsetAsync(base + o_st, 0, sizeof(KryState), c->stream));
+    if (c->kry_round_base) {
+      B200RT_CUDA(c, cudaMemcpyAsync(base + o_st, &c->kry_round_base, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+      B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+  }
+  KryWork wk;
+  wk.st = reinterpret_cast<KryState *>(base + o_st);
+  wk.V = reinterpret_cast<double *>(base + o_V);
+  wk.wloc = reinterpret_cast<double *>(base + o_w); wk.bvec = reinterpret_cast<double *>(base + o_b);
+  wk.xsol = reinterpret_cast<double *>(base + o_x);
+  wk.part1 = reinterpret_cast<double *>(base + o_p1); wk.part2 = reinterpret_cast<double *>(base + o_p2);
+  wk.npart = reinterpret_cast<double *>(base + o_np);
+  wk.R = reinterpret_cast<double *>(base + o_R);
+  wk.cs = reinterpret_cast<double *>(base + o_cs); wk.sn = reinterpret_cast<double *>(base + o_sn);
+  wk.g = reinterpret_cast<double *>(base + o_g); wk.y = reinterpret_cast<double *>(base + o_y);
+  wk.ns = ns;
+  int *d_rows = reinterpret_cast<int *>(base + o_rows);
+  B200RT_CUDA(c, c->host_stage.ensure((size_t) std::max(n, 1) * sizeof(int)));
+  std::memcpy(c->host_stage.p, rows.data(), (size_t) n_rows * sizeof(int));
+  B200RT_CUDA(c, cudaMemcpyAsync(d_rows, c->host_stage.p, (size_t) n_rows * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  B200RT_CUDA(c, cudaStreamSynchronize(c->stream));
+  KryPeers pe;
+  for (int q = 0; q < KRY_MAX_WORLD; q++) pe.p[q] = q < world ? static_cast<KryExchange *>(blocks[q]) : nullptr;
+  pe.rank = rank; pe.world = world;
+
+  double tol = 1e-13;
+  if (const char *env = getenv("B200RT_KRYLOV_TOL")) tol = atof(env);
+  int max_it = KRY_MAX_IT;
+  if (const char *env = getenv("B200RT_KRYLOV_MAXIT")) max_it = std::max(1, std::min(KRY_MAX_IT, atoi(env)));
+
+  const int post_blocks = std::max(1, std::min(n_rows, NUM_SMS * 8));   // CTAs pull rows from a queue
+  const int orth_blocks = (n + KRY_SLICE - 1) / KRY_SLICE;
+  B200RT_CUDA(c, c->host_scratch.ensure(64 * sizeof(KryState)));
+  KryState *h_st = c->host_scratch.as<KryState>();
+  cudaStream_t s = c->stream;
+  constexpr int CHUNK = 16;
+
+  for (int e = 0; e < c->n_em; e++) {
+    Emission &E = c->em[e];
+    if (!E.have_K) return fail(c, B200RT_ERR_STATE, "b200rt_solve_distributed: influence rows not built");
+    PhaseTimer t(c, PH_SOLVE);
+    int launches = 0;
+    const double *K = E.K.as<double>(), *S0 = E.S0.as<double>();
+    B200RT_CUDA(c, cudaMemsetAsync(reinterpret_cast<char *>(wk.st) + offsetof(KryState, iter), 0, 7 * sizeof(int), s));   // iter, done, error, converged, the tickets, the row queue
+    kry_post<0><<<post_blocks, KRY_THREADS, 0, s>>>(K, n, d_rows, n_rows, E.branching, S0, wk, pe);
+    kry_begin<<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe, tol, max_it);
+    launches += 2;
+    // Arnoldi steps in chunks; the state after chunk k is read back while chunk k + 1 runs, so at most two chunks of
+    // (empty: every kernel returns at once after `done`) launches follow the step that converged
+    // B200RT_KRYLOV_TRACE=1: time the four kernels of the first 48 steps (development aid)
+    static const bool trace = getenv("B200RT_KRYLOV_TRACE") != nullptr;
+    std::vector<cudaEvent_t> marks;
+    auto mark = [&] { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, s); marks.push_back(ev); };
+    const int n_chunks = (max_it + CHUNK - 1) / CHUNK;
+    std::vector<cudaEvent_t> read(n_chunks);
+    int issued = 0;
+    bool stop = false;
+    for (int k = 0; k < n_chunks && !stop; k++) {
+      for (int it = 0; it < CHUNK && k * CHUNK + it < max_it; it++) {
+        const bool tr = trace && k * CHUNK + it < 48;
+        if (tr) mark();
+        kry_post<1><<<post_blocks, KRY_THREADS, 0, s>>>(K, n, d_rows, n_rows, E.branching, S0, wk, pe);
+        if (tr) mark();
+        kry_orth<0><<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe);
+        if (tr) mark();
+        kry_orth<1><<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe);
+        if (tr) mark();
+        kry_orth<2><<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe);
+        if (tr) mark();
+        launches += 4;
+      }
+      B200RT_CUDA(c, cudaMemcpyAsync(h_st + k, wk.st, sizeof(KryState), cudaMemcpyDeviceToHost, s));
+      read[k] = PhaseTimer::take(c);
+      B200RT_CUDA(c, cudaEventRecord(read[k], s));
+      issued = k + 1;
+      if (k >= 1) {
+        B200RT_CUDA(c, cudaEventSynchronize(read[k - 1]));
+        stop = h_st[k - 1].done != 0;
+      }
+    }
+    (void) issued;
+    kry_backsolve<<<1, 32, 0, s>>>(wk);
+    kry_solution<<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, E.S.as<double>());
+    kry_post<2><<<post_blocks, KRY_THREADS, 0, s>>>(K, n, d_rows, n_rows, E.branching, S0, wk, pe);
+    kry_residual<<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe);
+    launches += 4;
+    B200RT_CUDA(c, cudaGetLastError());
+    if (c->precision == B200RT_F64)
+      B200RT_CUDA(c, launch_convert<double>(E.S.as<double>(), E.S_real.as<double>(), n, s));
+    else
+      B200RT_CUDA(c, launch_convert<float>(E.S.as<double>(), E.S_real.as<float>(), n, s));
+    t.stop(launches);
+    B200RT_CUDA(c, cudaMemcpyAsync(h_st + 63, wk.st, sizeof(KryState), cudaMemcpyDeviceToHost, s));
+    B200RT_CUDA(c, cudaStreamSynchronize(s));
+    if (trace && !marks.empty()) {
+      double sum[4] = {0, 0, 0, 0};
+      const int steps_traced = (int) marks.size() / 5;
+      for (int st_ = 0; st_ < steps_traced; st_++)
+        for (int q = 0; q < 4; q++) {
+          float ms = 0;
+          cudaEventElapsedTime(&ms, marks[st_ * 5 + q], marks[st_ * 5 + q + 1]);
+          sum[q] += ms;
+        }
+      fprintf(stderr, "krylov trace (%d steps, us per step): post %.2f  orth0 %.2f  orth1 %.2f  orth2 %.2f\n", steps_traced,
+              sum[0] / steps_traced * 1e3, sum[1] / steps_traced * 1e3, sum[2] / steps_traced * 1e3, sum[3] / steps_traced * 1e3);
+      for (auto ev : marks) cudaEventDestroy(ev);
+    }
+    const KryState fin = h_st[63];
+    c->kry_round_base = fin.round;
+    c->kry_last_iters = fin.iter;
+    if (fin.error == 2)
+      return fail(c, B200RT_ERR_STATE, "b200rt_solve_distributed: the rows the ranks built do not add up to the grid (every voxel must be in exactly one rank's influence call)");
+    if (fin.error)
+      return fail(c, B200RT_ERR_CUDA, "b200rt_solve_distributed: a peer never posted its rows (4 s): all ranks must call it, with the same grid");
+    if (!fin.converged)
+      return fail(c, B200RT_ERR_NOT_DOMINANT, "b200rt_solve_distributed: GMRES residual " + std::to_string(fin.res) + " after " +
+                                                  std::to_string(fin.iter) + " steps (rows missing on some rank, or a matrix the LU path should take)");
+    if (!(fin.true_res <= 1e-8))
+      return fail(c, B200RT_ERR_NOT_DOMINANT, "b200rt_solve_distributed: residual " + std::to_string(fin.true_res));
+    E.residual = fin.true_res;
+    E.have_S = true;
+    E.rec_dirty = true;
+  }
+  PhaseTimer::collect(c);
+  return B200RT_OK;
+}
+
+}  // namespace api
+}  // namespace b200rt

@@ -68,6 +68,20 @@ def connect_row_sink(dist, ctx, rank: int, root: int = 0, n_emissions: int = 1):
     return ptrs
 
 
+def connect_exchange(dist, ctx, rank: int, world: int):
+    """Distributed solve (include/b200rt.h, "distributed solve"): every rank exports a CUDA IPC handle of its exchange
+    block, every rank opens every other one.  Returns blocks[q] = rank q's block as addressable from this process
+    (blocks[rank] is the own device pointer), the argument of ctx.solve_distributed(rank, world, blocks).  After this the
+    ranks never meet on the host again: rows stay where they were built, S ends up resident everywhere.  Close the
+    foreign entries with ctx.ipc_close before the contexts are destroyed."""
+    ptr, handle = ctx.solve_exchange(want_ipc=world > 1)
+    if world == 1:
+        return [ptr]
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    return [ptr if q == rank else ctx.ipc_open(handles[q]) for q in range(world)]
+
+
 def broadcast_vector(dist, v, root: int = 0):
     """the solved source function (n_vox doubles) from the solving rank to every rank"""
     dist.broadcast(v, src=root)

@@ -215,7 +215,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    peer_ptrs = multi.connect_row_sink(dist, ctx, rank, 0, 1) if world > 1 else []
+    # the solve: one GPU factorises K where it was built (block LU); several GPUs leave the rows where they were built and
+    # iterate together (GMRES over peer memory, csrc/solve_krylov.cu) -- no row gather, no barrier, no broadcast of S
+    use_gmres = args.solver == "gmres" or (args.solver == "auto" and world > 1)
+    peer_ptrs, blocks = [], None
+    if use_gmres:
+        blocks = multi.connect_exchange(dist, ctx, rank, world)
+    elif world > 1:
+        peer_ptrs = multi.connect_row_sink(dist, ctx, rank, 0, 1)
 
     def gather_rows():
         """the one exchange on the path: every rank's row block -> rank 0's resident K.  The rows travel INSIDE
@@ -235,22 +242,27 @@ def run_ours(args):
         t["march_launches"] = ctx.kernel_ms(binding.PH_INFLUENCE)[1] - 1      # minus the single-scattering march
         steps = ctx.last_step_count()
         w1 = time.perf_counter()
-        if world > 1:                                           # every rank's rows are in rank 0's K after this
+        if world > 1 and not use_gmres:                         # every rank's rows are in rank 0's K after this
             gather_rows()
         w2 = time.perf_counter()
         # row_exchange = what the exchange adds to the critical path: the un-hidden tail of the row DMA inside
         # ctx.influence (its wall time minus its kernels) + the barrier
-        t["exchange"] = (w2 - w1) + max(0.0, (w1 - w0) - t["traverse"] - t["march"]) if world > 1 else 0.0
+        t["exchange"] = (w2 - w1) + max(0.0, (w1 - w0) - t["traverse"] - t["march"]) if (world > 1 and not use_gmres) else 0.0
         t["influence_tail"] = (w1 - w0) - t["traverse"] - t["march"]      # host launch/sync overhead (+ un-hidden DMA tail)
         t["barrier"] = w2 - w1
         if os.environ.get("B200RT_BENCH_DEBUG"):
             print(f"rank {rank}: influence wall {(w1 - w0) * 1e3:.3f} ms, kernels {(t['traverse'] + t['march']) * 1e3:.3f} ms, "
                   f"barrier {(w2 - w1) * 1e3:.3f} ms", file=sys.stderr, flush=True)
-        if rank == 0:
+        if use_gmres:                                           # every rank; S is resident on every rank afterwards
+            ctx.solve_distributed(rank, world, blocks)
+            t["solve"] = ctx.kernel_ms(binding.PH_SOLVE)[0] * 1e-3
+            t["solve_steps"] = ctx.last_solve_steps()
+            launches += ctx.kernel_ms(binding.PH_SOLVE)[1]
+        elif rank == 0:
             ctx.solve()
             t["solve"] = ctx.kernel_ms(binding.PH_SOLVE)[0] * 1e-3
             launches += ctx.kernel_ms(binding.PH_SOLVE)[1]
-        if world > 1:
+        if world > 1 and not use_gmres:
             S_t = torch.as_tensor(cuda_array(S_ptr.value, (n_vox,)), device=dev)
             dist.broadcast(S_t, src=0)
             torch.cuda.synchronize()
@@ -279,12 +291,15 @@ def run_ours(args):
         ctx.influence_ranges(v_ranges)
         sol = ctx.solution(0, want_S=False)                     # D2H: S0 + optical depths
         w1 = time.perf_counter()
-        if world > 1:
+        if use_gmres:
+            ctx.solve_distributed(rank, world, blocks)
+            S = ctx.solution(0)["S"]                            # D2H: S
+        elif world > 1:
             gather_rows()
-        if rank == 0:
+        if rank == 0 and not use_gmres:
             ctx.solve()
             S = ctx.solution(0)["S"]                            # D2H: S
-        if world > 1:
+        if world > 1 and not use_gmres:
             S_t = torch.as_tensor(cuda_array(S_ptr.value, (n_vox,)), device=dev)
             dist.broadcast(S_t, src=0)
             torch.cuda.synchronize()
@@ -352,9 +367,13 @@ def run_ours(args):
     h2d = 8 * n_vox * 8 + 9 * (l1 - l0) * 8
     d2h = 4 * n_vox * 8 + 4 * (l1 - l0) * 8
 
-    if world > 1:                     # peers let go of rank 0's K before rank 0 frees it
+    if world > 1:                     # peers let go of rank 0's K / of each other's exchange blocks before they are freed
         for p_ in peer_ptrs:
             ctx.ipc_close(p_)
+        if blocks:
+            for q, p_ in enumerate(blocks):
+                if q != rank:
+                    ctx.ipc_close(p_)
         dist.barrier()
     dfma = dmma = None
     if rank == 0:
@@ -408,7 +427,16 @@ def run_ours(args):
                              (l1 - l0) * quad * FLOP_EQ_PER_QUADRATIC, substeps_rank / 9.0 * 12.0,
                              {"rays": l1 - l0, "quadratics_per_ray": quad, "flop_eq_per_quadratic": FLOP_EQ_PER_QUADRATIC}, "traverse_los"),
     }
-    if t_solve > 0:
+    if t_solve > 0 and use_gmres:
+        sv = t_solve / K
+        products = recs[-1]["solve_steps"] + 1                       # Arnoldi steps + the residual check
+        k_bytes = products * n_rows_mine * n_vox * 8.0
+        rooflines["solve"] = {"kernel": "distributed GMRES (kry_post: this rank's rows of K x vector, once per step)", "bound": "hbm",
+                              "achieved": k_bytes / sv / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": k_bytes / sv / 1e9 / hbm_peak,
+                              "peak_kind": peak_kind, "launch_ms": sv * 1e3, "steps": recs[-1]["solve_steps"],
+                              "note": "algorithmic bytes = (steps + 1) x own rows x n_vox x 8; the rest of a step is the "
+                                      "orthogonalisation (3 short launches) and the wait for the peers' pieces"}
+    elif t_solve > 0:
         sv = t_solve / K
         rooflines["solve"] = {"kernel": "block LU (gemm128 DMMA.8x8x4 + cluster Gauss-Jordan)", "bound": "fp64 tensor",
                               "achieved": (2.0 / 3.0 * n_vox ** 3) / sv / 1e12, "peak": dmma, "unit": "TFLOP/s",
@@ -423,7 +451,8 @@ def run_ours(args):
     fp64 = {"dfma_peak_tflops": dfma, "dmma_peak_tflops": dmma,
             "march_flop_eq_tflops": rooflines["march"]["achieved"], "brightness_flop_eq_tflops": rooflines["brightness"]["achieved"],
             "los_substeps": substeps_rank,
-            "solve_tflops": rooflines.get("solve", {}).get("achieved"), "solve_frac_of_dmma": rooflines.get("solve", {}).get("frac")}
+            "solve_tflops": None if use_gmres else rooflines.get("solve", {}).get("achieved"),
+            "solve_frac_of_dmma": None if use_gmres else rooflines.get("solve", {}).get("frac")}
 
     line = {"metric": "influence-matrix ray-voxel steps/s + observation LOS/s", "value": value,
             "unit": "ray-voxel steps/s", "los_per_s": los_per_s, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -433,8 +462,13 @@ def run_ours(args):
                                    f"{n_los} IUVS-like LOS brightness, n_subsamples=10",
                        "grid": GRID, "n_emissions": 1, "n_los": n_los, "ray_voxel_steps": int(steps_total),
                        "l2": "256 MB buffer written between timed iterations (L2 flush); K is 273 MB > L2",
-                       "partition": ("one process per GPU: rows by source voxel (pushed to rank 0 over peer memory while "
-                                     "marching), LOS by index; the in-process form of the same partition (one handle, "
+                       "solver": ("GMRES over the ranks' resident rows (b200rt_solve_distributed), tolerance 1e-13, "
+                                  f"{recs[-1].get('solve_steps')} steps") if use_gmres else "block LU (DMMA) on one GPU",
+                       "partition": ("one process per GPU: rows by source voxel, " +
+                                     ("left where they were built (the ranks solve together over peer memory: no row gather, "
+                                      "no host barrier, no broadcast of S)" if use_gmres else
+                                      "pushed to rank 0 over peer memory while marching") +
+                                     ", LOS by index; the in-process form of the same partition (one handle, "
                                      "b200rt_create_multi, what observation_fit uses) is timed under in_process")
                        if world > 1 else "single GPU"},
             "phases_ms": {"influence_traverse+march": t_infl / K * 1e3, "influence_traverse": mean("traverse") * 1e3,
@@ -553,6 +587,8 @@ def main():
     ap.add_argument("--n-los", type=int, default=1000000)
     ap.add_argument("--ref-stride", type=int, default=8, help="CPU sample: every k-th source-voxel row")
     ap.add_argument("--ref-los", type=int, default=50000, help="CPU sample: lines of sight per step")
+    ap.add_argument("--solver", default="auto", choices=["auto", "lu", "gmres"],
+                    help="auto: block LU on one GPU, distributed GMRES (rows stay on their ranks) on several")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the IPH and sweep measurements")
     ap.add_argument("--no-in-process", action="store_true", help="N > 1: skip the one-handle in-process arm on rank 0")

@@ -206,6 +206,37 @@ int b200rt_ipc_open(b200rt_ctx *ctx, const void *handle64, void **peer_ptr);
 int b200rt_ipc_close(b200rt_ctx *ctx, void *peer_ptr);
 int b200rt_set_row_sink(b200rt_ctx *ctx, int i_emission, void *peer_K_dev);   /* NULL clears */
 
+/* ---- distributed solve: the rows stay where they were built ---------------------------
+ * The N-GPU form of RT_grid::solve_gpu.  Instead of gathering K on one GPU and factorising it there, every rank keeps
+ * the rows its b200rt_influence / b200rt_influence_ranges call built (no row sink) and all ranks solve
+ * (I - w K) S = S0 together by GMRES: one step is one product with K, each rank multiplies its own rows and writes its
+ * piece of the result into every rank's EXCHANGE BLOCK over peer memory (NVLink), then every rank orthogonalises the
+ * assembled vector redundantly -- bit-identical on all ranks -- so S ends up resident on every rank with no row gather,
+ * no broadcast and no host barrier.  K is the kernel of a second-kind integral equation: the step count does not grow
+ * with the grid (~70 for the H Lyman alpha corona at 1e-13; csrc/solve_krylov.cu).
+ *   b200rt_solve_exchange:    this context's exchange block (B200RT_KRYLOV_BLOCK_BYTES of device memory, allocated on
+ *                             first use, alive until destroy): its device pointer (ranks of one process, peer access
+ *                             enabled) and/or a CUDA IPC handle of it (64 bytes; other processes open it with
+ *                             b200rt_ipc_open).  Either output may be NULL.
+ *   b200rt_solve_distributed: blocks[q] = rank q's exchange block as addressable from THIS process, blocks[rank] = the
+ *                             own one.  Every rank calls it, after its influence call on the same grid, the same number
+ *                             of times (the blocks carry monotonic round counters).  On return every emission's S is
+ *                             resident on every rank (b200rt_get_solution, b200rt_brightness*), b200rt_last_residual
+ *                             is the true relative residual |S0 - (I - wK) S| / |S0| and b200rt_last_kernel_ms
+ *                             (B200RT_PHASE_SOLVE) counts the launches.  The union of the ranks' rows must be every
+ *                             voxel; a rank that never arrives is reported (B200RT_ERR_CUDA) after 4 s, no convergence
+ *                             within 160 steps as B200RT_ERR_NOT_DOMINANT.  world = 1 is allowed (one GPU, GMRES
+ *                             instead of the LU).  Singlet emissions, n_vox <= B200RT_KRYLOV_MAX_N.
+ * A device group (b200rt_create_multi) does this behind b200rt_solve / b200rt_generate_S for grids of
+ * B200RT_KRYLOV_MIN_N (default 2048) voxels and more; smaller systems keep the LU on the owning device.
+ * Knobs: B200RT_KRYLOV_TOL (relative residual of the Krylov recurrence, default 1e-13), B200RT_KRYLOV_MAXIT. */
+#define B200RT_KRYLOV_MAX_N 16384
+#define B200RT_KRYLOV_MAX_WORLD 16
+#define B200RT_KRYLOV_BLOCK_BYTES (B200RT_KRYLOV_MAX_WORLD * 128 + 2 * B200RT_KRYLOV_MAX_N * 8)
+int b200rt_solve_exchange(b200rt_ctx *ctx, void **block_dev, void *ipc_handle64);
+int b200rt_solve_distributed(b200rt_ctx *ctx, int rank, int world, void *const *blocks);
+int b200rt_last_solve_steps(b200rt_ctx *ctx, int *n_steps);   /* GMRES steps of the last distributed solve */
+
 /* ---- observations ---------------------------------------------------------------
  * host helper: observation::add_MSO_observation (observation.hpp:46-65) + atmo_point::xyz +
  * atmo_vector::ptxyz (atmo_vec.cpp:51-61,256-290): MSO position / look direction ->

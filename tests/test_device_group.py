@@ -162,3 +162,34 @@ def test_facade_uses_every_device(synth, binding, split_everything, monkeypatch)
         F.generate_source_function(1e5, 300.0)
         out.append(np.asarray(F.brightness()))
     assert rel_err(out[0], out[1]) < 1e-9
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_group_distributed_solve(synth, binding, split_everything, monkeypatch, prec):
+    """grids of B200RT_KRYLOV_MIN_N voxels and more: the rows stay on the members that built them and the members solve
+    together (csrc/solve_krylov.cu); S is resident on every member, and a caller that asks for the assembled influence
+    matrix afterwards still gets every row (gathered on demand)"""
+    monkeypatch.setenv("B200RT_KRYLOV_MIN_N", "50")
+    scn = synth.make_scenario(20, 12, 6, 8, n_em=2, sza_T_contrast=0.1)
+    one = binding.GpuModel(scn, prec, device=0)
+    one.build_rows()
+    one.solve()
+    ids = group_devices(binding)
+    grp = binding.GpuModel(scn, prec, devices=ids)
+    grp.ctx.generate_S()
+    steps = grp.ctx.last_solve_steps()
+    assert 5 < steps < 120                                        # it was the distributed solve
+    tol = 1e-7 if prec == "f64" else 1e-5                          # float tables: K itself differs by float rounding order
+    for e in range(2):
+        assert grp.ctx.residual(e) < 1e-12
+        assert rel_err(one.vectors(e)["S"], grp.vectors(e)["S"], floor=1e-30) < tol
+    locs, dirs = synth.random_los(1003, seed=5)
+    _, bN = grp.brightness(locs, dirs, 10)                         # every member integrates with its resident S
+    for e in range(2):
+        one.set_sourcefn(e, grp.vectors(e)["S"])
+    _, b1 = one.brightness(locs, dirs, 10)
+    assert rel_err(b1, bN, floor=1e-300) < (1e-12 if prec == "f64" else 1e-5)
+    for e in range(2):
+        assert rel_err(one.K(e), grp.K(e)) < (1e-12 if prec == "f64" else 1e-5)     # gathered from the members' shards
+    grp.ctx.solve()                                                # again, on the same rows
+    assert grp.ctx.last_solve_steps() == steps
