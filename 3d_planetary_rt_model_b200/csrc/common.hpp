@@ -420,7 +420,7 @@ int measure_fp64_peaks(b200rt_ctx *c, double *dfma_tflops, double *dmma_tflops);
 // ---- solve_krylov.cu
 namespace api {
 int exchange_block(b200rt_ctx *c, void **dev_ptr);
-int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, bool reset_timer);
+int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, bool reset_timer, int cta_cap = 0);
 }
 // ---- solve.cu
 struct SolveResult { double residual; double min_margin; int launches; };

@@ -255,9 +255,16 @@ int solve_and_share(b200rt_ctx *g) {
       cudaSetDevice(gr->m[i]->device);
       if (int rc = api::exchange_block(gr->m[i], &blocks[i])) { g->err = gr->m[i]->err; return rc; }
     }
+    // members that share a device (an id named several times) share its SMs: each one's resident grid shrinks so that all fit
+    std::vector<int> cap(n_mem, 0);
+    for (int i = 0; i < n_mem; i++) {
+      int share = 0;
+      for (int k = 0; k < n_mem; k++) share += gr->m[k]->device == gr->m[i]->device;
+      cap[i] = share > 1 ? std::max(1, 2 * NUM_SMS / share) : 0;   // (0: the default, three CTAs per SM)
+    }
     const int rc = run_members(g, n_mem, [&](int i) {
       cudaSetDevice(gr->m[i]->device);
-      return api::solve_distributed(gr->m[i], i, n_mem, blocks.data(), true);
+      return api::solve_distributed(gr->m[i], i, n_mem, blocks.data(), true, cap[i]);
     });
     if (rc != B200RT_OK) return rc;
     collect_phases(gr, n_mem);

@@ -54,6 +54,10 @@ struct KryState {
   unsigned int post_tickets, orth_tickets, row_queue;
   int max_it;
   double beta, inv_norm, res, true_res, tol;
+  // the one-launch form (kry_loop): barrier among the CTAs that orthogonalise, and the step sequence CTA 0 publishes
+  unsigned int orth_bar, step_seq;
+  unsigned long long t_phase[10];    // CTA 0's clock over the Arnoldi steps [ns]: product, wait for peers, orthogonalisation,
+                                     // closing; [4..9]: the orthogonalisation's three passes and the barrier after each
 };
 
 struct KryWork {                     // device pointers into one allocation
@@ -486,6 +490,439 @@ kry_residual(int n, KryWork wk, KryPeers pe) {
   }
 }
 
+// =====================================================================================================================
+// The whole solve as ONE cooperative launch per rank (kry_loop).  The four launches per step above cost ~36 us of launch
+// gaps and cold re-reads around ~5 us of work (measured with events: orth0 8.4, orth1 10.5, orth2 17 us per step on the
+// 100x60 grid), which on eight GPUs is six times the product itself.  Here the grid stays resident for the whole
+// iteration: every CTA pulls rows for the product; the first ceil(n / 96) CTAs own a slice of the vector and run the two
+// Gram-Schmidt passes with three counter barriers among themselves; CTA 0 closes the step (Givens, residual, stop?) and
+// publishes the step sequence every CTA waits on.  The same algorithm with the same fixed order of every sum as the launches above
+// (the two forms differ in where 1 / |w| multiplies the product, i.e. by rounding).  Everything one CTA reads that another wrote inside the launch goes through L2
+// (ld.cg / volatile): L1 is not coherent between SMs.  Every spin loop leaves when st->error is raised (CTA 0 raises it
+// when a peer has not posted for 4 s), so a missing rank ends the launch on every rank instead of hanging it.
+struct KryLoopArgs {
+  const double *K;
+  const int *rows;
+  const double *S0;
+  double *S;
+  KryWork wk;
+  KryPeers pe;
+  double branching, tol;
+  int n, n_rows, max_it, orth_blocks;
+};
+
+__device__ __forceinline__ unsigned int ld_vol_u32(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+__device__ __forceinline__ int ld_vol_i32(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+
+// thread 0: wait until *ctr >= target; false when the solve is being abandoned
+__device__ __forceinline__ unsigned int ld_acq_u32(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned int *ctr, unsigned int target, const KryState *st) {
+  unsigned int spins = 0;
+  while (ld_acq_u32(ctr) < target) {
+    __nanosleep(16);
+    if ((++spins & 127u) == 0 && ld_vol_i32(&st->error)) return false;
+  }
+  return true;
+}
+// all threads of every orthogonalising CTA
+__device__ __forceinline__ bool orth_barrier(KryState *st, unsigned int target, int *sh_ok) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->orth_bar) : "memory");
+    *sh_ok = spin_until(&st->orth_bar, target, st) ? 1 : 0;
+  }
+  __syncthreads();
+  return *sh_ok != 0;
+}
+// all threads of every CTA but CTA 0 (which publishes with step_publish)
+// ... and until the orthogonalising CTAs have all arrived `arrivals` times (their slices of w are in place)
+__device__ __forceinline__ bool step_wait(KryState *st, unsigned int target, unsigned int arrivals, int *sh_ok) {
+  if (threadIdx.x == 0)
+    *sh_ok = (spin_until(&st->step_seq, target, st) && spin_until(&st->orth_bar, arrivals, st)) ? 1 : 0;
+  __syncthreads();
+  return *sh_ok != 0;
+}
+// an orthogonalising CTA arrives without waiting (the wait is step_wait's)
+__device__ __forceinline__ void orth_arrive(KryState *st) {
+  __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->orth_bar) : "memory");
+}
+__device__ __forceinline__ void step_publish(KryState *st, unsigned int value) {
+  __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->step_seq), "r"(value) : "memory");
+}
+// thread 0 of an orthogonalising CTA: every rank has posted `round` here.  CTA 0 keeps the clock.
+__device__ __forceinline__ bool peers_posted(KryState *st, const KryPeers &pe, unsigned long long round, int *sh_ok) {
+  if (threadIdx.x == 0) {
+    const KryExchange *mine = pe.p[pe.rank];
+    const unsigned long long t0 = global_ns();
+    int ok = 1;
+    for (int q = 0; q < pe.world && ok; q++) {
+      unsigned int spins = 0;
+      while (ld_flag(&mine->flag[q][0]) < round) {
+        __nanosleep(20);
+        if ((++spins & 127u) == 0) {
+          if (ld_vol_i32(&st->error)) { ok = 0; break; }
+          if (blockIdx.x == 0 && global_ns() - t0 > 4000000000ull) {
+            *reinterpret_cast<volatile int *>(&st->error) = 1;
+            ok = 0;
+            break;
+          }
+        }
+      }
+    }
+    *sh_ok = ok;
+  }
+  __syncthreads();
+  return *sh_ok != 0;
+}
+
+// the product phase of a round: MODE as kry_post.  x was written by other CTAs of this launch, so it comes through L2:
+// STAGE copies it to shared memory once per round (a CTA with many rows, one GPU), otherwise every row reads it with
+// ld.cg beside its row of K (a CTA with one or two rows, eight GPUs: the copy would cost as much as the rows).
+// The next row index is requested from the queue while the current row is being multiplied.
+constexpr int KRY_UNR = 12;          // loads of K in flight per thread: 5841 / 256 = 22.8 columns per thread = two trips
+template <int MODE, bool STAGE>
+__device__ __forceinline__ void loop_post(const KryLoopArgs &a, double *xs, double *red, int *sh_row, unsigned long long round) {
+  KryState *st = a.wk.st;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.n;
+  const int slot = (int) (round & 1);
+  const double *src = MODE == 1 ? a.wk.wloc : a.wk.xsol;
+  const double scale = MODE == 1 ? *reinterpret_cast<const volatile double *>(&st->inv_norm) : 1.0;
+  if (tid == 0) sh_row[0] = (int) atomicAdd(&st->row_queue, 1u);
+  bool staged = false;
+  for (int it = 0;; it++) {
+    __syncthreads();
+    const int slot_row = sh_row[it & 1];
+    if (slot_row >= a.n_rows) break;
+    if (tid == 0) sh_row[(it + 1) & 1] = (int) atomicAdd(&st->row_queue, 1u);   // in flight during this row
+    const int i = a.rows[slot_row];
+    double val = 0;
+    if (MODE == 0) {
+      val = a.S0[i];
+    } else {
+      if (STAGE && !staged) {
+#pragma unroll 8
+        for (int c = tid; c < n; c += KRY_THREADS) xs[c] = __ldcg(src + c) * scale;
+        staged = true;
+        __syncthreads();
+      }
+      const double *Kr = a.K + (size_t) i * n;
+      double acc[KRY_UNR];
+#pragma unroll
+      for (int u = 0; u < KRY_UNR; u++) acc[u] = 0;
+      int col = tid;
+      for (; col + (KRY_UNR - 1) * KRY_THREADS < n; col += KRY_UNR * KRY_THREADS) {
+        double kk[KRY_UNR], xx[KRY_UNR];
+#pragma unroll
+        for (int u = 0; u < KRY_UNR; u++) kk[u] = __ldcs(Kr + col + KRY_THREADS * u);
+#pragma unroll
+        for (int u = 0; u < KRY_UNR; u++) xx[u] = STAGE ? xs[col + KRY_THREADS * u] : __ldcg(src + col + KRY_THREADS * u);
+#pragma unroll
+        for (int u = 0; u < KRY_UNR; u++) acc[u] = fma(kk[u], xx[u], acc[u]);
+      }
+      {
+        double kk[KRY_UNR], xx[KRY_UNR];
+#pragma unroll
+        for (int u = 0; u < KRY_UNR; u++) {
+          const int cc = col + KRY_THREADS * u;
+          kk[u] = cc < n ? __ldcs(Kr + cc) : 0.0;
+          xx[u] = cc < n ? (STAGE ? xs[cc] : __ldcg(src + cc)) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < KRY_UNR; u++) acc[u] = fma(kk[u], xx[u], acc[u]);
+      }
+      double sm = 0;
+#pragma unroll
+      for (int u = 0; u < KRY_UNR; u++) sm += acc[u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      if (lane == 0) red[warp] = sm;
+      __syncthreads();
+      if (tid < 32) {
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < KRY_WARPS; k++) t += red[k];
+        const double xi = STAGE ? xs[i] : __ldcg(src + i);
+        val = STAGE ? xi - a.branching * t : scale * (xi - a.branching * t);
+      }
+    }
+    if (tid < a.pe.world) st_remote(&a.pe.p[tid]->w[slot][i], val);
+  }
+  if (tid < a.pe.world) __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    const unsigned int t = atomicAdd(&st->post_tickets, 1u);
+    if (t == gridDim.x - 1) {
+      __threadfence_system();
+      st->post_tickets = 0;
+      st->row_queue = 0;
+      st->round = round + 1;
+      for (int q = 0; q < a.pe.world; q++) {
+        if (MODE == 0) a.pe.p[q]->flag[a.pe.rank][1] = (unsigned long long) a.n_rows;
+        st_flag(&a.pe.p[q]->flag[a.pe.rank][0], round + 1);
+      }
+    }
+  }
+}
+
+// partial sums another CTA wrote: through L2
+__device__ __forceinline__ void loop_reduce(const double *part, int nv, int n_cta, double *h) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v0 = warp; v0 < nv; v0 += KRY_VPT * KRY_WARPS) {
+    double s[KRY_VPT];
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++) s[k] = 0;
+    for (int c0 = 0; c0 < n_cta; c0 += 64) {           // 2 x KRY_VPT loads in flight per lane: one trip to L2 per 64 CTAs
+      double lo_[KRY_VPT], hi_[KRY_VPT];
+#pragma unroll
+      for (int k = 0; k < KRY_VPT; k++) {
+        const double *p = part + (size_t) min(v0 + k * KRY_WARPS, nv - 1) * KRY_MAX_B + c0;
+        lo_[k] = (c0 + lane < n_cta) ? __ldcg(p + lane) : 0.0;
+        hi_[k] = (c0 + 32 + lane < n_cta) ? __ldcg(p + 32 + lane) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < KRY_VPT; k++) { s[k] += lo_[k]; s[k] += hi_[k]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < KRY_VPT; k++) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+#pragma unroll
+    for (int k = 0; k < KRY_VPT; k++)
+      if (lane == 0 && v0 + k * KRY_WARPS < nv) h[v0 + k * KRY_WARPS] = s[k];
+  }
+}
+__device__ __forceinline__ double loop_sum_partials(const double *p, int n_cta) {   // a warp; as warp_sum_partials, through L2
+  const int lane = threadIdx.x & 31;
+  double s = 0;
+  for (int c = lane; c < n_cta; c += 32) s += __ldcg(p + c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_loop(KryLoopArgs a) {
+  extern __shared__ double xs[];
+  __shared__ double ws[KRY_SLICE];
+  __shared__ double red[KRY_WARPS][KRY_SLICE];
+  __shared__ double h[KRY_MAX_IT + 2], hsum[KRY_MAX_IT + 2];
+  __shared__ double rot[2 * KRY_MAX_IT + 2], gs[KRY_MAX_IT + 2];      // CTA 0: the rotations and the rotated right-hand side
+  __shared__ double scratch[KRY_WARPS];
+  __shared__ double sh_val;
+  __shared__ int sh_flag, sh_row[2];
+  KryState *st = a.wk.st;
+  const KryWork &wk = a.wk;
+  const KryPeers &pe = a.pe;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.n;
+  const int cta = blockIdx.x, n_orth = a.orth_blocks;
+  const bool orth = cta < n_orth;
+  const int lo = cta * KRY_SLICE, len = orth ? min(KRY_SLICE, n - lo) : 0;
+  unsigned long long round = st->round;          // every CTA counts the rounds itself (st->round is for the host)
+  unsigned int bar = 0, seq = 0;
+  const KryExchange *mine = pe.p[pe.rank];
+  const bool stage = a.n_rows > 3 * (int) gridDim.x;   // rows per CTA and round
+  const bool clock = cta == 0 && tid == 0;
+  unsigned long long t_mark = 0, t_sub = 0, t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+  // ---- round 0: the right-hand side, assembled from every rank's own rows
+  loop_post<0, false>(a, xs, &red[0][0], sh_row, round);
+  round++;
+  double beta = 0;
+  ++bar;                                           // (every CTA counts the barriers of the orthogonalising ones)
+  if (orth) {
+    if (!peers_posted(st, pe, round, &sh_flag)) return;
+    const int slot = (int) ((round - 1) & 1);
+    double b = 0;
+    if (tid < len) {
+      b = ld_remote(&mine->w[slot][lo + tid]);
+      wk.bvec[lo + tid] = b;
+      wk.wloc[lo + tid] = b;
+      ws[tid] = b;
+    }
+    const double s2 = slice_sum(b * b, scratch);
+    if (tid == 0) wk.npart[cta] = s2;
+    if (!orth_barrier(st, bar * n_orth, &sh_flag)) return;
+    if (warp == 0) {
+      const double t = loop_sum_partials(wk.npart, n_orth);
+      if (lane == 0) sh_val = t;
+    }
+    __syncthreads();
+    beta = sqrt(sh_val);
+    const double inv = beta > 0 ? 1.0 / beta : 0.0;
+    if (tid < len) wk.V[lo + tid] = ws[tid] * inv;                 // basis vector 0, this CTA's slice (read only by this CTA)
+    if (cta == 0 && tid == 0) {
+      unsigned long long census = 0;
+      for (int q = 0; q < pe.world; q++) census += ld_flag(&mine->flag[q][1]);
+      st->beta = beta;
+      st->inv_norm = inv;
+      gs[0] = beta;
+      st->iter = 0;
+      st->res = 1.0;
+      st->true_res = -1.0;
+      st->converged = beta > 0 ? 0 : 1;
+      int stop = beta > 0 ? 0 : 1;
+      if (census != (unsigned long long) n) { st->error = 2; stop = 1; }
+      st->done = stop;
+    }
+  }
+  ++seq;
+  if (cta == 0) step_publish(st, seq);
+  if (!step_wait(st, seq, bar * n_orth, &sh_flag)) return;
+  if (ld_vol_i32(&st->error)) return;
+  int done = ld_vol_i32(&st->done);
+
+  // ---- Arnoldi steps
+  int j = 0;
+  while (!done) {
+    if (clock) t_mark = global_ns();
+    if (stage) loop_post<1, true>(a, xs, &red[0][0], sh_row, round);
+    else loop_post<1, false>(a, xs, &red[0][0], sh_row, round);
+    round++;
+    bar += 3;
+    if (orth) {
+      const int nv = j + 1;
+      if (clock) { const unsigned long long t = global_ns(); t_acc[0] += t - t_mark; t_mark = t; }
+      if (!peers_posted(st, pe, round, &sh_flag)) return;
+      if (clock) { const unsigned long long t = global_ns(); t_acc[1] += t - t_mark; t_mark = t; t_sub = t; }
+      const int slot = (int) ((round - 1) & 1);
+      if (tid < len) ws[tid] = ld_remote(&mine->w[slot][lo + tid]);
+      __syncthreads();
+      slice_dots(ws, wk, lo, len, nv, wk.part1);
+      if (clock) { const unsigned long long t = global_ns(); t_acc[4] += t - t_sub; t_sub = t; }
+      if (!orth_barrier(st, (bar - 2) * n_orth, &sh_flag)) return;
+      if (clock) { const unsigned long long t = global_ns(); t_acc[5] += t - t_sub; t_sub = t; }
+      loop_reduce(wk.part1, nv, n_orth, h);
+      __syncthreads();
+      for (int v = tid; v < nv; v += KRY_THREADS) hsum[v] = h[v];
+      slice_update(ws, wk, lo, len, nv, h, red, -1.0);
+      slice_dots(ws, wk, lo, len, nv, wk.part2);
+      {   // |w1|^2 of the slice rides with the second pass's partials (row nv): after the second pass
+          // |w|^2 = |w1|^2 - sum h2^2 (h2 is a re-orthogonalisation: tiny against |w1|, no cancellation), so the norm
+          // needs no reduction -- and no barrier -- of its own
+        const double w1 = slice_sum(tid < len ? ws[tid] * ws[tid] : 0.0, scratch);
+        if (tid == 0) wk.part2[(size_t) nv * KRY_MAX_B + cta] = w1;
+      }
+      if (clock) { const unsigned long long t = global_ns(); t_acc[6] += t - t_sub; t_sub = t; }
+      if (!orth_barrier(st, (bar - 1) * n_orth, &sh_flag)) return;
+      if (clock) { const unsigned long long t = global_ns(); t_acc[7] += t - t_sub; t_sub = t; }
+      loop_reduce(wk.part2, nv + 1, n_orth, h);
+      __syncthreads();
+      for (int v = tid; v < nv; v += KRY_THREADS) hsum[v] += h[v];
+      if (warp == 0) {
+        double q = 0;
+        for (int v = lane; v < nv; v += 32) q = fma(h[v], h[v], q);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (lane == 0) sh_val = fmax(h[nv] - q, 0.0);
+      }
+      slice_update(ws, wk, lo, len, nv, h, red, -1.0);       // (its barriers publish sh_val)
+      if (tid < len) wk.wloc[lo + tid] = ws[tid];                  // unnormalised: the product scales by 1 / |w|
+      if (clock) { const unsigned long long t = global_ns(); t_acc[8] += t - t_sub; t_sub = t; }
+      // the slices of w must be in place before the next product reads them: arrive here, wait with everyone at the end
+      // of the step (CTA 0 closes the step meanwhile)
+      orth_arrive(st);
+      const double hn = sqrt(sh_val);
+      const double inv = hn > 0 ? 1.0 / hn : 0.0;
+      if (tid < len) wk.V[(size_t) (j + 1) * wk.ns + lo + tid] = ws[tid] * inv;
+      if (clock) { const unsigned long long t = global_ns(); t_acc[2] += t - t_mark; t_mark = t; }
+      if (cta == 0) {
+        if (tid == 0) {
+          double hi = hsum[0];
+          for (int i = 0; i < j; i++) {
+            const double c_ = rot[2 * i], s_ = rot[2 * i + 1], up = hsum[i + 1];
+            hsum[i] = c_ * hi + s_ * up;
+            hi = -s_ * hi + c_ * up;
+          }
+          const double d = hypot(hi, hn);
+          const double c_ = d > 0 ? hi / d : 1.0, s_ = d > 0 ? hn / d : 0.0;
+          hsum[j] = d;
+          rot[2 * j] = c_; rot[2 * j + 1] = s_;
+          const double gj = gs[j];
+          gs[j + 1] = -s_ * gj;
+          gs[j] = c_ * gj;
+          const double res = fabs(gs[j + 1]) / beta;
+          st->res = res;
+          st->iter = j + 1;
+          st->inv_norm = inv;
+          const bool conv = res <= a.tol || hn == 0.0;
+          st->converged = conv ? 1 : 0;
+          st->done = (conv || j + 1 >= a.max_it) ? 1 : 0;
+        }
+        __syncthreads();
+        for (int i = tid; i <= j; i += KRY_THREADS) wk.R[(size_t) i * KRY_MAX_IT + j] = hsum[i];
+        if (clock) { const unsigned long long t = global_ns(); t_acc[3] += t - t_mark; t_mark = t; }
+      }
+    }
+    ++seq;
+    if (cta == 0) step_publish(st, seq);
+    if (clock) t_sub = global_ns();
+    if (!step_wait(st, seq, bar * n_orth, &sh_flag)) return;
+    if (clock) t_acc[9] += global_ns() - t_sub;
+    done = ld_vol_i32(&st->done);
+    j++;
+  }
+  if (ld_vol_i32(&st->error)) return;
+  if (clock)
+    for (int q = 0; q < 10; q++) st->t_phase[q] = t_acc[q];
+
+  // ---- S = V y, y = R^-1 g: CTA 0 substitutes (row l on thread l), the slices combine
+  const int k = j;                                 // Arnoldi steps taken (0 when S0 = 0)
+  if (cta == 0) {
+    double gl = tid < k ? gs[tid] : 0.0;
+    for (int i = k - 1; i >= 0; i--) {
+      if (tid == i) {
+        const double y = gl / wk.R[(size_t) i * KRY_MAX_IT + i];
+        sh_val = y;
+        wk.y[i] = y;
+      }
+      __syncthreads();
+      if (tid < i) gl -= wk.R[(size_t) tid * KRY_MAX_IT + i] * sh_val;
+      __syncthreads();
+    }
+  }
+  ++seq;
+  if (cta == 0) step_publish(st, seq);
+  if (!step_wait(st, seq, bar * n_orth, &sh_flag)) return;
+  ++bar;
+  if (orth) {
+    for (int v = tid; v < k; v += KRY_THREADS) h[v] = __ldcg(wk.y + v);
+    if (tid < KRY_SLICE) ws[tid] = 0;
+    __syncthreads();
+    slice_update(ws, wk, lo, len, k, h, red, 1.0);
+    if (tid < len) { wk.xsol[lo + tid] = ws[tid]; a.S[lo + tid] = ws[tid]; }
+    orth_arrive(st);
+  }
+  ++seq;
+  if (cta == 0) step_publish(st, seq);
+  if (!step_wait(st, seq, bar * n_orth, &sh_flag)) return;
+
+  // ---- the true residual: one more product, with the solution
+  if (stage) loop_post<2, true>(a, xs, &red[0][0], sh_row, round);
+  else loop_post<2, false>(a, xs, &red[0][0], sh_row, round);
+  round++;
+  if (orth) {
+    if (!peers_posted(st, pe, round, &sh_flag)) return;
+    const int slot = (int) ((round - 1) & 1);
+    double r = 0;
+    if (tid < len) r = wk.bvec[lo + tid] - ld_remote(&mine->w[slot][lo + tid]);
+    const double s2 = slice_sum(r * r, scratch);
+    if (tid == 0) wk.npart[cta] = s2;
+    if (!orth_barrier(st, ++bar * n_orth, &sh_flag)) return;     // (the last barrier: only these CTAs count it)
+    if (cta == 0 && warp == 0) {
+      const double t = loop_sum_partials(wk.npart, n_orth);
+      if (lane == 0) st->true_res = beta > 0 ? sqrt(t) / beta : 0.0;
+    }
+  }
+}
+
 size_t carve_bytes(size_t &off, size_t bytes) {
   off = (off + 255) & ~size_t(255);
   const size_t at = off;
@@ -507,7 +944,7 @@ int exchange_block(b200rt_ctx *c, void **dev_ptr) {
   return B200RT_OK;
 }
 
-int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, bool reset_timer) {
+int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, bool reset_timer, int cta_cap) {
   const int n = c->hg.n_vox;
   if (world < 1 || world > KRY_MAX_WORLD || rank < 0 || rank >= world || !blocks)
     return fail(c, B200RT_ERR_ARG, "b200rt_solve_distributed: bad rank / world / blocks");
@@ -586,16 +1023,43 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
     PhaseTimer t(c, PH_SOLVE);
     int launches = 0;
     const double *K = E.K.as<double>(), *S0 = E.S0.as<double>();
-    B200RT_CUDA(c, cudaMemsetAsync(reinterpret_cast<char *>(wk.st) + offsetof(KryState, iter), 0, 7 * sizeof(int), s));   // iter, done, error, converged, the tickets, the row queue
+    // everything but the round counter starts from zero (no kernel of this context is in flight here)
+    B200RT_CUDA(c, cudaMemsetAsync(reinterpret_cast<char *>(wk.st) + offsetof(KryState, iter), 0,
+                                   sizeof(KryState) - offsetof(KryState, iter), s));
+    // B200RT_KRYLOV_TRACE=1: time the four kernels of the first 48 steps (development aid)
+    static const bool trace = getenv("B200RT_KRYLOV_TRACE") != nullptr;
+    std::vector<cudaEvent_t> marks;
+    auto mark = [&] { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, s); marks.push_back(ev); };
+    // ---- the one-launch form: the grid stays resident for the whole iteration (cooperative launch, so that it is)
+    bool fused = true;
+    if (const char *env = getenv("B200RT_KRYLOV_FUSED")) fused = atoi(env) != 0;
+    if (fused) {
+      const size_t smem = (size_t) n * sizeof(double);
+      int per_sm = 0;
+      cudaError_t e_occ = cudaFuncSetAttribute(kry_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+      if (e_occ == cudaSuccess) e_occ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kry_loop, KRY_THREADS, smem);
+      int cap = cta_cap > 0 ? cta_cap : 3 * NUM_SMS;
+      if (const char *env = getenv("B200RT_KRYLOV_CTAS")) cap = std::max(1, atoi(env));
+      const int grid = std::min(cap, per_sm * NUM_SMS);
+      if (e_occ != cudaSuccess || grid < orth_blocks) {
+        cudaGetLastError();
+        fused = false;                             // (a vector too long for the shared-memory staging: the launches below)
+      } else {
+        KryLoopArgs a;
+        a.K = K; a.rows = d_rows; a.S0 = S0; a.S = E.S.as<double>(); a.wk = wk; a.pe = pe;
+        a.branching = E.branching; a.tol = tol; a.n = n; a.n_rows = n_rows; a.max_it = max_it; a.orth_blocks = orth_blocks;
+        void *kargs[] = {&a};
+        const cudaError_t e_l = cudaLaunchCooperativeKernel((void *) kry_loop, dim3(grid), dim3(KRY_THREADS), kargs, smem, s);
+        if (e_l == cudaSuccess) launches += 1;
+        else { cudaGetLastError(); fused = false; }
+      }
+    }
+    if (!fused) {
     kry_post<0><<<post_blocks, KRY_THREADS, 0, s>>>(K, n, d_rows, n_rows, E.branching, S0, wk, pe);
     kry_begin<<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe, tol, max_it);
     launches += 2;
     // Arnoldi steps in chunks; the state after chunk k is read back while chunk k + 1 runs, so at most two chunks of
     // (empty: every kernel returns at once after `done`) launches follow the step that converged
-    // B200RT_KRYLOV_TRACE=1: time the four kernels of the first 48 steps (development aid)
-    static const bool trace = getenv("B200RT_KRYLOV_TRACE") != nullptr;
-    std::vector<cudaEvent_t> marks;
-    auto mark = [&] { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, s); marks.push_back(ev); };
     const int n_chunks = (max_it + CHUNK - 1) / CHUNK;
     std::vector<cudaEvent_t> read(n_chunks);
     int issued = 0;
@@ -629,6 +1093,7 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
     kry_post<2><<<post_blocks, KRY_THREADS, 0, s>>>(K, n, d_rows, n_rows, E.branching, S0, wk, pe);
     kry_residual<<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe);
     launches += 4;
+    }   // !fused
     B200RT_CUDA(c, cudaGetLastError());
     if (c->precision == B200RT_F64)
       B200RT_CUDA(c, launch_convert<double>(E.S.as<double>(), E.S_real.as<double>(), n, s));
@@ -651,6 +1116,13 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
       for (auto ev : marks) cudaEventDestroy(ev);
     }
     const KryState fin = h_st[63];
+    if (trace && fused && fin.iter > 0)
+      fprintf(stderr, "krylov trace (one launch, %d steps, CTA 0's clock, us per step): product %.2f  wait for peers %.2f  "
+              "orthogonalisation %.2f (pass / barrier: %.2f / %.2f, %.2f / %.2f, %.2f / %.2f)  closing %.2f\n", fin.iter,
+              fin.t_phase[0] * 1e-3 / fin.iter, fin.t_phase[1] * 1e-3 / fin.iter, fin.t_phase[2] * 1e-3 / fin.iter,
+              fin.t_phase[4] * 1e-3 / fin.iter, fin.t_phase[5] * 1e-3 / fin.iter, fin.t_phase[6] * 1e-3 / fin.iter,
+              fin.t_phase[7] * 1e-3 / fin.iter, fin.t_phase[8] * 1e-3 / fin.iter, fin.t_phase[9] * 1e-3 / fin.iter,
+              fin.t_phase[3] * 1e-3 / fin.iter);
     c->kry_round_base = fin.round;
     c->kry_last_iters = fin.iter;
     if (fin.error == 2)

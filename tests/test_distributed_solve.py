@@ -52,8 +52,16 @@ def run_ranks(binding, scn, devices, chunks=3, prec="f64"):
     return models
 
 
+@pytest.fixture(params=["one launch", "four launches per step"])
+def form(request, monkeypatch):
+    """the solve as one cooperative launch (kry_loop, the default) and as the per-step launches it falls back to"""
+    monkeypatch.setenv("B200RT_KRYLOV_FUSED", "1" if request.param == "one launch" else "0")
+    monkeypatch.setenv("B200RT_KRYLOV_CTAS", "64")     # several ranks share device 0 here: every resident grid has to fit
+    return request.param
+
+
 @pytest.mark.parametrize("shape", [(12, 8, 5, 6), (40, 20, 7, 12)])
-def test_one_rank_gmres_equals_lu_and_oracle(synth, binding, oraclebind, shape):
+def test_one_rank_gmres_equals_lu_and_oracle(synth, binding, oraclebind, shape, form):
     scn = synth.make_scenario(*shape, n_em=2, sza_T_contrast=0.1)
     G, S_lu, _ = lu_solution(binding, scn)
     block, _ = G.ctx.solve_exchange()
@@ -77,7 +85,7 @@ def test_one_rank_gmres_equals_lu_and_oracle(synth, binding, oraclebind, shape):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_ranks_sharing_one_device(synth, binding, world):
+def test_ranks_sharing_one_device(synth, binding, world, form):
     """the exchange protocol itself: `world` contexts on device 0, each with its own rows only"""
     scn = synth.make_scenario(20, 12, 6, 8, n_em=2, sza_T_contrast=0.1)
     _, S_lu, _ = lu_solution(binding, scn)
@@ -97,7 +105,7 @@ def test_ranks_sharing_one_device(synth, binding, world):
     assert np.isfinite(a["brightness"]).all()
 
 
-def test_missing_rows_are_reported(synth, binding):
+def test_missing_rows_are_reported(synth, binding, form):
     """a rank that built fewer rows than its share: the iteration cannot converge, and says so instead of hanging"""
     scn = synth.make_scenario(12, 8, 5, 6, n_em=1)
     G = binding.GpuModel(scn, "f64")
@@ -105,6 +113,24 @@ def test_missing_rows_are_reported(synth, binding):
     block, _ = G.ctx.solve_exchange()
     with pytest.raises(binding.B200RTError):
         G.ctx.solve_distributed(0, 1, [block])
+
+
+def test_both_forms_agree(synth, binding, monkeypatch):
+    """one cooperative launch against four launches per step: same algorithm and order of sums (they differ in where
+    1 / |w| multiplies the product, i.e. by rounding)"""
+    scn = synth.make_scenario(20, 12, 6, 8, n_em=1)
+    G = binding.GpuModel(scn, "f64")
+    G.build_rows()
+    block, _ = G.ctx.solve_exchange()
+    out = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("B200RT_KRYLOV_FUSED", fused)
+        G.ctx.solve_distributed(0, 1, [block])
+        out.append((G.vectors(0)["S"].copy(), G.ctx.last_solve_steps(), G.ctx.residual(0), G.ctx.kernel_ms(binding.PH_SOLVE)[1]))
+    assert out[0][3] == 1 and out[1][3] > 20                        # launches: one, against four per step
+    assert out[0][1] == out[1][1]
+    assert rel_err(out[0][0], out[1][0], floor=1e-30) < 1e-9
+    assert out[0][2] < 1e-12 and out[1][2] < 1e-12
 
 
 def test_two_devices(synth, binding):
