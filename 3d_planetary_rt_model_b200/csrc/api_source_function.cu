@@ -137,6 +137,27 @@ int influence_impl(b200rt_ctx *c, const std::vector<std::pair<int, int>> &ranges
 // only_e >= 0: that emission alone (a device group solves emission e on the device that gathered its rows)
 int solve_impl(b200rt_ctx *c, bool reset_timer, int only_e = -1) {
   const int n = c->hg.n_vox;
+  // Large systems whose rows were all built here: preconditioned GMRES (solve_krylov.cu with one rank: 4.0 ms against the
+  // LU's 5.8 ms at n = 5841, S within 1e-11 of the LU's element by element).  The LU below stays the solve of small
+  // systems (a 741-unknown LU is 0.4 ms, shorter than the iteration's set-up), of matrices assembled from peers' row
+  // pushes, and the fallback when the iteration does not converge.  B200RT_SOLVER = lu | gmres overrides the size rule.
+  if (only_e < 0) {
+    long long min_n = 2048;
+    if (const char *env = getenv("B200RT_KRYLOV_MIN_N")) min_n = atoll(env);
+    bool iterate = n >= min_n;
+    if (const char *env = getenv("B200RT_SOLVER")) iterate = std::strcmp(env, "gmres") == 0 || (iterate && std::strcmp(env, "lu") != 0);
+    long long own = 0;
+    for (auto &r : c->built_ranges) own += r.second - r.first;
+    bool have_all = own == n;
+    for (int e = 0; e < c->n_em; e++) have_all = have_all && c->em[e].have_K;
+    if (iterate && have_all && n <= B200RT_KRYLOV_MAX_N) {
+      void *block = nullptr;
+      if (int rc = exchange_block(c, &block)) return rc;
+      const int rc = solve_distributed(c, 0, 1, &block, reset_timer);
+      if (rc != B200RT_ERR_NOT_DOMINANT) return rc;
+      // not converged: the direct solve decides (and reports a matrix it cannot take)
+    }
+  }
   if (reset_timer) PhaseTimer::reset(c);
   for (int e = 0; e < c->n_em; e++) {
     if (only_e >= 0 && e != only_e) continue;

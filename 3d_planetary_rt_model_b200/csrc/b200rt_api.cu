@@ -44,7 +44,7 @@ int b200rt_destroy(b200rt_ctx *c) {
   cudaStreamSynchronize(c->stream);
   DevBuf *bufs[] = {&c->grid_tables, &c->sun_rays, &c->list_dist, &c->list_ent, &c->list_len, &c->list_flag,
                     &c->work_counter, &c->step_counter, &c->los_in, &c->los_out, &c->los_order, &c->lu, &c->lu_dinv, &c->lu_flag,
-                    &c->iph.dev, &c->iph.io, &c->vox_map, &c->sph_table, &c->kry_xchg, &c->kry_work};
+                    &c->iph.dev, &c->iph.io, &c->vox_map, &c->sph_table, &c->kry_xchg, &c->kry_work, &c->kry_bp};
   for (DevBuf *b : bufs) b->release();
   c->host_scratch.release();
   c->host_words.release();

@@ -241,7 +241,7 @@ struct b200rt_ctx {
   size_t timer_used = 0;
   // distributed solve (solve_krylov.cu): this context's exchange block (peers write into it), the work area, the source
   // voxel ranges the last influence call built (= the rows this rank multiplies), the round counter's last value
-  b200rt::DevBuf kry_xchg, kry_work;
+  b200rt::DevBuf kry_xchg, kry_work, kry_bp;   // kry_bp: the own rows of A M^-1 (right-preconditioned iteration)
   std::vector<std::pair<int, int>> built_ranges;
   unsigned long long kry_round_base = 0;
   int kry_last_iters = 0;

@@ -37,9 +37,12 @@ constexpr int KRY_MAX_N = B200RT_KRYLOV_MAX_N;       // 16384 unknowns: the exch
 constexpr int KRY_MAX_WORLD = B200RT_KRYLOV_MAX_WORLD;
 constexpr int KRY_MAX_B = (KRY_MAX_N + KRY_SLICE - 1) / KRY_SLICE;
 
+constexpr int KRY_MAX_NR = B200RT_KRYLOV_MAX_NR;     // radial voxels per SZA column the preconditioner handles (128)
 struct KryExchange {                                 // one per rank, written by every rank
   unsigned long long flag[KRY_MAX_WORLD][16];        // flag[q][0]: rounds rank q has completed into THIS block (own 128-byte line)
   double w[2][KRY_MAX_N];
+  double pre[(size_t) KRY_MAX_N * KRY_MAX_NR];       // pre[v][i']: A[v][(i', column of v)], the diagonal blocks of the
+                                                     // preconditioner, every row written by the rank that built it
 };
 static_assert(sizeof(KryExchange) == B200RT_KRYLOV_BLOCK_BYTES, "include/b200rt.h states the size of the exchange block");
 
@@ -69,6 +72,12 @@ struct KryWork {                     // device pointers into one allocation
   double *R;                         // [KRY_MAX_IT + 1][KRY_MAX_IT], upper triangular after the rotations
   double *cs, *sn, *g, *y;           // [KRY_MAX_IT + 1]
   int ns;
+  // right preconditioner M = the diagonal blocks of A over the SZA columns of the grid (voxel = i_r * n_col + i_col):
+  double *Minv;                      // [n_col][nr][nr] the inverted blocks (every rank inverts all of them, identically)
+  double *Bp;                        // [own rows][n] rows of A M^-1, columns in column-major voxel order c' = i_col * nr + i_r
+  double *usol;                      // [ns] V y before M^-1 is applied
+  double *wperm;                     // [ns] the current vector in the column order of Bp (what the product reads)
+  int nr, n_col;                     // 0: no preconditioner
 };
 
 __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p) {
@@ -499,6 +508,169 @@ kry_residual(int n, KryWork wk, KryPeers pe) {
 }
 
 // =====================================================================================================================
+// Right preconditioner: M = the diagonal blocks of A = I - wK over the SZA columns of the grid (all radial voxels of one
+// SZA index: the strongest coupling in this atmosphere is vertical).  GMRES on A M^-1 u = S0, S = M^-1 u: 39 steps
+// instead of 71 on the 100x60 grid, 24 instead of 69 on the 40x20 grid (tools/dev/krylov_probe.py); residuals are those
+// of the original system.  Three launches before the iteration:
+//   kry_pre_post    every rank writes the block entries of ITS rows into every rank's exchange block (one more round);
+//   kry_pre_invert  every rank inverts all n_col blocks (nr x nr, Gauss-Jordan in shared memory, no exchanges: the blocks
+//                   are diagonally dominant like A) -- redundantly, so that the inverses are bit-identical everywhere;
+//   kry_pre_permute, kry_pre_rows   the own rows of A M^-1, columns regrouped by SZA column, so that the iteration's
+//                   product is the same row-times-vector as before with nothing added per step.
+__device__ __forceinline__ void post_round_tail(KryState *st, const KryPeers &pe, unsigned long long round, int *sh) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&st->post_tickets, 1u);
+    *sh = (t == gridDim.x - 1);
+    if (*sh) {
+      __threadfence();
+      st->post_tickets = 0;
+      st->row_queue = 0;
+      st->round = round + 1;
+    }
+  }
+  __syncthreads();
+  if (*sh && tid < pe.world) st_flag_relaxed(&pe.p[tid]->flag[pe.rank][0], round + 1);
+}
+
+__global__ void __launch_bounds__(128)
+kry_pre_post(const double *__restrict__ K, int n, const int *__restrict__ rows, int n_rows, double branching, KryWork wk,
+             KryPeers pe) {
+  __shared__ int sh;
+  KryState *st = wk.st;
+  const int tid = threadIdx.x, nr = wk.nr, n_col = wk.n_col;
+  const unsigned long long round = st->round;
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const int v = rows[r], iv = v / n_col, jv = v - iv * n_col;
+    if (tid < nr) {
+      const double val = (tid == iv ? 1.0 : 0.0) - branching * K[(size_t) v * n + (size_t) tid * n_col + jv];
+      for (int q = 0; q < pe.world; q++) st_remote(&pe.p[q]->pre[(size_t) v * KRY_MAX_NR + tid], val);
+    }
+  }
+  __threadfence_system();
+  post_round_tail(st, pe, round, &sh);
+}
+
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_pre_invert(KryWork wk, KryPeers pe) {
+  extern __shared__ double Mb[];                   // [nr][nr + 1]
+  __shared__ int sh_flag;
+  __shared__ double sh_inv;
+  KryState *st = wk.st;
+  const int tid = threadIdx.x, nr = wk.nr, n_col = wk.n_col, ld = nr + 1, j = blockIdx.x;
+  if (!wait_round(st, pe, st->round, &sh_flag)) return;
+  const KryExchange *mine = pe.p[pe.rank];
+  for (int e = tid; e < nr * nr; e += KRY_THREADS) {
+    const int i = e / nr, c = e - i * nr;
+    Mb[i * ld + c] = ld_remote(&mine->pre[(size_t) (i * n_col + j) * KRY_MAX_NR + c]);
+  }
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;           // thread: columns tx, tx + 32, ...; rows ty, ty + 8, ...
+  for (int p = 0; p < nr; p++) {                   // in-place Gauss-Jordan inversion, pivot p
+    if (tid == 0) sh_inv = 1.0 / Mb[p * ld + p];
+    __syncthreads();
+    const double inv = sh_inv;
+    for (int c = tid; c < nr; c += KRY_THREADS) Mb[p * ld + c] = (c == p) ? inv : Mb[p * ld + c] * inv;
+    __syncthreads();
+    double prow[4];                                // this thread's four columns of the pivot row (0 where it must not touch)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int c = tx + 32 * k;
+      prow[k] = (c < nr && c != p) ? Mb[p * ld + c] : 0.0;
+    }
+#pragma unroll 4
+    for (int i = ty; i < nr; i += KRY_WARPS) {
+      const double f = (i == p) ? 0.0 : Mb[i * ld + p];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int c = tx + 32 * k;
+        if (c < nr) Mb[i * ld + c] = fma(-f, prow[k], Mb[i * ld + c]);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < nr; i += KRY_THREADS)
+      if (i != p) Mb[i * ld + p] = -Mb[i * ld + p] * inv;
+    __syncthreads();
+  }
+  double *out = wk.Minv + (size_t) j * nr * nr;
+  for (int e = tid; e < nr * nr; e += KRY_THREADS) out[e] = Mb[(e / nr) * ld + (e % nr)];
+}
+
+// own rows of A with the columns regrouped by SZA column: Bp[r][j * nr + i] = A[row r][i * n_col + j]  (a row is read
+// once, coalesced, and written once, coalesced; gathering the strided entries inside kry_pre_rows fetched every 64-byte
+// line of K eight times: 1.45 ms for the rows of one GPU)
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_pre_permute(const double *__restrict__ K, int n, const int *__restrict__ rows, int n_rows, double branching, KryWork wk) {
+  extern __shared__ double rowbuf[];               // [n]
+  const int tid = threadIdx.x, nr = wk.nr, n_col = wk.n_col;
+  for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    const int v = rows[r];
+    const double *Kr = K + (size_t) v * n;
+    for (int c = tid; c < n; c += KRY_THREADS) rowbuf[c] = (c == v ? 1.0 : 0.0) - branching * __ldcs(Kr + c);
+    __syncthreads();
+    double *out = wk.Bp + (size_t) r * n;
+    for (int c = tid; c < n; c += KRY_THREADS) {
+      const int j = c / nr, i = c - j * nr;
+      out[c] = rowbuf[i * n_col + j];
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int KRY_PRE_RT = 32;                       // rows of a tile of kry_pre_rows
+// Bp[tile rows][block j] <- Bp[tile rows][block j] x Minv_j, in place (a tile is read and written by one CTA only)
+__global__ void __launch_bounds__(KRY_THREADS)
+kry_pre_rows(int n, int n_rows, KryWork wk) {
+  extern __shared__ double sm[];                   // Minv_j [nr][nr] | At [RT][nr]
+  const int tid = threadIdx.x, nr = wk.nr, j = blockIdx.x;
+  double *Mj = sm, *At = sm + nr * nr;
+  const double *src = wk.Minv + (size_t) j * nr * nr;
+  for (int e = tid; e < nr * nr; e += KRY_THREADS) Mj[e] = src[e];
+  const int cg = tid & 31, rg = tid >> 5;
+  // 4 x 4 register tiles: thread (rg, cg) = rows 4 rg .. 4 rg + 3 of the tile, outputs cg, cg + 32, cg + 64, cg + 96 (8 loads
+  // from shared memory per 16 FMAs; consecutive threads read consecutive words of Minv: with outputs 4 cg .. 4 cg + 3 the
+  // 32-byte stride between threads was an 8-way bank conflict, 28 us per tile instead of 7).  A CTA keeps Minv_j for
+  // several row tiles.
+  for (int r0 = blockIdx.y * KRY_PRE_RT; r0 < n_rows; r0 += gridDim.y * KRY_PRE_RT) {
+    const int rt = min(KRY_PRE_RT, n_rows - r0);
+    __syncthreads();                               // (Minv_j in place; the previous tile's At no longer read)
+    for (int r = tid >> 5; r < rt; r += KRY_WARPS) {
+      const double *in = wk.Bp + (size_t) (r0 + r) * n + (size_t) j * nr;
+      for (int i = tid & 31; i < nr; i += 32) At[r * nr + i] = in[i];
+    }
+    __syncthreads();
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int w = 0; w < 4; w++) acc[u][w] = 0;
+    const double *a0 = At + (4 * rg) * nr;
+    for (int i = 0; i < nr; i++) {
+      double av[4], mv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) av[u] = (4 * rg + u < rt) ? a0[u * nr + i] : 0.0;
+#pragma unroll
+      for (int w = 0; w < 4; w++) mv[w] = (cg + 32 * w < nr) ? Mj[i * nr + cg + 32 * w] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int w = 0; w < 4; w++) acc[u][w] = fma(av[u], mv[w], acc[u][w]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = 4 * rg + u;
+      if (r >= rt) continue;
+      double *out = wk.Bp + (size_t) (r0 + r) * n + (size_t) j * nr;
+#pragma unroll
+      for (int w = 0; w < 4; w++)
+        if (cg + 32 * w < nr) out[cg + 32 * w] = acc[u][w];
+    }
+  }
+}
+
+// =====================================================================================================================
 // The whole solve as ONE cooperative launch per rank (kry_loop).  The four launches per step above cost ~36 us of launch
 // gaps and cold re-reads around ~5 us of work (measured with events: orth0 8.4, orth1 10.5, orth2 17 us per step on the
 // 100x60 grid), which on eight GPUs is six times the product itself.  Here the grid stays resident for the whole
@@ -595,12 +767,14 @@ __device__ __forceinline__ bool peers_posted(KryState *st, const KryPeers &pe, u
 // ld.cg beside its row of K (a CTA with one or two rows, eight GPUs: the copy would cost as much as the rows).
 // The next row index is requested from the queue while the current row is being multiplied.
 constexpr int KRY_UNR = 12;          // loads of K in flight per thread: 5841 / 256 = 22.8 columns per thread = two trips
-template <int MODE, bool STAGE>
+// PC: the rows are those of A M^-1 (wk.Bp, one per own row slot, columns in the order c' = i_col * nr + i_r), so the
+// vector is gathered in that order and the row sum IS the element of the product.
+template <int MODE, bool STAGE, bool PC>
 __device__ __forceinline__ void loop_post(const KryLoopArgs &a, double *xs, double *red, int *sh_row, unsigned long long round) {
   KryState *st = a.wk.st;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.n;
   const int slot = (int) (round & 1);
-  const double *src = MODE == 1 ? a.wk.wloc : a.wk.xsol;
+  const double *src = MODE == 1 ? (PC ? a.wk.wperm : a.wk.wloc) : a.wk.xsol;
   const double scale = MODE == 1 ? *reinterpret_cast<const volatile double *>(&st->inv_norm) : 1.0;
   if (tid == 0) sh_row[0] = (int) atomicAdd(&st->row_queue, 1u);
   bool staged = false;
@@ -620,7 +794,7 @@ __device__ __forceinline__ void loop_post(const KryLoopArgs &a, double *xs, doub
         staged = true;
         __syncthreads();
       }
-      const double *Kr = a.K + (size_t) i * n;
+      const double *Kr = PC ? a.wk.Bp + (size_t) slot_row * n : a.K + (size_t) i * n;
       double acc[KRY_UNR];
 #pragma unroll
       for (int u = 0; u < KRY_UNR; u++) acc[u] = 0;
@@ -656,8 +830,12 @@ __device__ __forceinline__ void loop_post(const KryLoopArgs &a, double *xs, doub
         double t = 0;
 #pragma unroll
         for (int k = 0; k < KRY_WARPS; k++) t += red[k];
-        const double xi = STAGE ? xs[i] : __ldcg(src + i);
-        val = STAGE ? xi - a.branching * t : scale * (xi - a.branching * t);
+        if (PC) {
+          val = STAGE ? t : scale * t;
+        } else {
+          const double xi = STAGE ? xs[i] : __ldcg(src + i);
+          val = STAGE ? xi - a.branching * t : scale * (xi - a.branching * t);
+        }
       }
     }
     if (tid < a.pe.world) st_remote(&a.pe.p[tid]->w[slot][i], val);
@@ -747,11 +925,14 @@ kry_loop(KryLoopArgs a) {
   unsigned int bar = 0, seq = 0;
   const KryExchange *mine = pe.p[pe.rank];
   const bool stage = a.n_rows > 3 * (int) gridDim.x;   // rows per CTA and round
+  const bool pc = wk.nr > 0;                           // right-preconditioned: the iteration is on u, S = M^-1 u
+  int pos_perm = 0;                                    // where this thread's element of the slice sits in the column order of Bp
+  if (pc && tid < len) { const int v = lo + tid, iv = v / wk.n_col; pos_perm = (v - iv * wk.n_col) * wk.nr + iv; }
   const bool clock = cta == 0 && tid == 0;
   unsigned long long t_mark = 0, t_sub = 0, t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   // ---- round 0: the right-hand side, assembled from every rank's own rows
-  loop_post<0, false>(a, xs, &red[0][0], sh_row, round);
+  loop_post<0, false, false>(a, xs, &red[0][0], sh_row, round);
   round++;
   double beta = 0;
   ++bar;                                           // (every CTA counts the barriers of the orthogonalising ones)
@@ -763,6 +944,7 @@ kry_loop(KryLoopArgs a) {
       b = ld_remote(&mine->w[slot][lo + tid]);
       wk.bvec[lo + tid] = b;
       wk.wloc[lo + tid] = b;
+      if (pc) wk.wperm[pos_perm] = b;
       ws[tid] = b;
     }
     const double s2 = slice_sum(b * b, scratch);
@@ -801,8 +983,13 @@ kry_loop(KryLoopArgs a) {
   int j = 0;
   while (!done) {
     if (clock) t_mark = global_ns();
-    if (stage) loop_post<1, true>(a, xs, &red[0][0], sh_row, round);
-    else loop_post<1, false>(a, xs, &red[0][0], sh_row, round);
+    if (pc) {
+      if (stage) loop_post<1, true, true>(a, xs, &red[0][0], sh_row, round);
+      else loop_post<1, false, true>(a, xs, &red[0][0], sh_row, round);
+    } else {
+      if (stage) loop_post<1, true, false>(a, xs, &red[0][0], sh_row, round);
+      else loop_post<1, false, false>(a, xs, &red[0][0], sh_row, round);
+    }
     round++;
     bar += 3;
     if (orth) {
@@ -842,7 +1029,10 @@ kry_loop(KryLoopArgs a) {
         if (lane == 0) sh_val = fmax(h[nv] - q, 0.0);
       }
       slice_update(ws, wk, lo, len, nv, h, red, -1.0);       // (its barriers publish sh_val)
-      if (tid < len) wk.wloc[lo + tid] = ws[tid];                  // unnormalised: the product scales by 1 / |w|
+      if (tid < len) {                                             // unnormalised: the product scales by 1 / |w|
+        if (pc) wk.wperm[pos_perm] = ws[tid];
+        else wk.wloc[lo + tid] = ws[tid];
+      }
       if (clock) { const unsigned long long t = global_ns(); t_acc[8] += t - t_sub; t_sub = t; }
       // the slices of w must be in place before the next product reads them: arrive here, wait with everyone at the end
       // of the step (CTA 0 closes the step meanwhile)
@@ -915,16 +1105,39 @@ kry_loop(KryLoopArgs a) {
     if (tid < KRY_SLICE) ws[tid] = 0;
     __syncthreads();
     slice_update(ws, wk, lo, len, k, h, red, 1.0);
-    if (tid < len) { wk.xsol[lo + tid] = ws[tid]; a.S[lo + tid] = ws[tid]; }
+    if (!pc) {
+      if (tid < len) { wk.xsol[lo + tid] = ws[tid]; a.S[lo + tid] = ws[tid]; }
+    } else if (tid < len) {
+      wk.usol[lo + tid] = ws[tid];
+    }
     orth_arrive(st);
   }
   ++seq;
   if (cta == 0) step_publish(st, seq);
   if (!step_wait(st, seq, bar * n_orth, &sh_flag)) return;
+  if (pc) {                                        // S = M^-1 u, block by block: element (i, j) = row i of Minv_j . u[(., j)]
+    ++bar;
+    if (orth) {
+      const int nr = wk.nr, n_col = wk.n_col;
+      for (int e = warp; e < len; e += KRY_WARPS) {
+        const int v = lo + e, iv = v / n_col, jv = v - iv * n_col;
+        const double *mrow = wk.Minv + ((size_t) jv * nr + iv) * nr;
+        double sum = 0;
+        for (int i = lane; i < nr; i += 32) sum = fma(mrow[i], __ldcg(wk.usol + (size_t) i * n_col + jv), sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) { wk.xsol[v] = sum; a.S[v] = sum; }
+      }
+      orth_arrive(st);
+    }
+    ++seq;
+    if (cta == 0) step_publish(st, seq);
+    if (!step_wait(st, seq, bar * n_orth, &sh_flag)) return;
+  }
 
   // ---- the true residual: one more product, with the solution
-  if (stage) loop_post<2, true>(a, xs, &red[0][0], sh_row, round);
-  else loop_post<2, false>(a, xs, &red[0][0], sh_row, round);
+  if (stage) loop_post<2, true, false>(a, xs, &red[0][0], sh_row, round);
+  else loop_post<2, false, false>(a, xs, &red[0][0], sh_row, round);
   round++;
   if (orth) {
     if (!peers_posted(st, pe, round, &sh_flag)) return;
@@ -993,6 +1206,13 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
   const size_t o_cs = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double)), o_sn = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double)),
                o_g = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double)), o_y = carve_bytes(off, (KRY_MAX_IT + 1) * sizeof(double));
   const size_t o_rows = carve_bytes(off, (size_t) std::max(n, 1) * sizeof(int));
+  // right preconditioner over the SZA columns (spherical grids; B200RT_KRYLOV_PC=0 switches it off)
+  int pc_nr = c->hg.n_rb - 1, pc_nc = c->hg.n_sb - 1;
+  bool pc = !c->hg.pp && pc_nr >= 2 && pc_nr <= KRY_MAX_NR && pc_nc >= 2 && pc_nr * pc_nc == n;
+  if (const char *env = getenv("B200RT_KRYLOV_PC")) pc = pc && atoi(env) != 0;
+  if (const char *env = getenv("B200RT_KRYLOV_FUSED")) pc = pc && atoi(env) != 0;     // the per-step launches iterate on A itself
+  const size_t o_usol = carve_bytes(off, (size_t) ns * sizeof(double)), o_wperm = carve_bytes(off, (size_t) ns * sizeof(double));
+  const size_t o_minv = carve_bytes(off, pc ? (size_t) pc_nc * pc_nr * pc_nr * sizeof(double) : 16);
   const bool fresh = c->kry_work.bytes < off;
   B200RT_CUDA(c, c->kry_work.ensure(off));
   char *base = static_cast<char *>(c->kry_work.p);
@@ -1014,6 +1234,15 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
   wk.cs = reinterpret_cast<double *>(base + o_cs); wk.sn = reinterpret_cast<double *>(base + o_sn);
   wk.g = reinterpret_cast<double *>(base + o_g); wk.y = reinterpret_cast<double *>(base + o_y);
   wk.ns = ns;
+  wk.usol = reinterpret_cast<double *>(base + o_usol);
+  wk.wperm = reinterpret_cast<double *>(base + o_wperm);
+  wk.Minv = reinterpret_cast<double *>(base + o_minv);
+  wk.Bp = nullptr;
+  wk.nr = 0; wk.n_col = 0;
+  if (pc) {
+    B200RT_CUDA(c, c->kry_bp.ensure((size_t) std::max(n_rows, 1) * n * sizeof(double)));
+    wk.Bp = c->kry_bp.as<double>();
+  }
   int *d_rows = reinterpret_cast<int *>(base + o_rows);
   B200RT_CUDA(c, c->host_stage.ensure((size_t) std::max(n, 1) * sizeof(int)));
   std::memcpy(c->host_stage.p, rows.data(), (size_t) n_rows * sizeof(int));
@@ -1051,6 +1280,25 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
     // ---- the one-launch form: the grid stays resident for the whole iteration (cooperative launch, so that it is)
     bool fused = true;
     if (const char *env = getenv("B200RT_KRYLOV_FUSED")) fused = atoi(env) != 0;
+    if (fused && pc) {                             // the preconditioner: block entries to all ranks, inverses, rows of A M^-1
+      wk.nr = pc_nr; wk.n_col = pc_nc;
+      const size_t sm_inv = (size_t) pc_nr * (pc_nr + 1) * sizeof(double);
+      const size_t sm_rows = ((size_t) pc_nr * pc_nr + (size_t) KRY_PRE_RT * pc_nr) * sizeof(double);
+      B200RT_CUDA(c, cudaFuncSetAttribute(kry_pre_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_inv));
+      B200RT_CUDA(c, cudaFuncSetAttribute(kry_pre_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm_rows));
+      B200RT_CUDA(c, cudaFuncSetAttribute(kry_pre_permute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ((size_t) n * sizeof(double))));
+      if (trace) mark();
+      kry_pre_post<<<std::max(1, std::min(n_rows, 4 * NUM_SMS)), 128, 0, s>>>(K, n, d_rows, n_rows, E.branching, wk, pe);
+      if (trace) mark();
+      kry_pre_invert<<<pc_nc, KRY_THREADS, sm_inv, s>>>(wk, pe);
+      if (trace) mark();
+      if (n_rows > 0) {
+        kry_pre_permute<<<std::min(n_rows, 4 * NUM_SMS), KRY_THREADS, (size_t) n * sizeof(double), s>>>(K, n, d_rows, n_rows, E.branching, wk);
+        kry_pre_rows<<<dim3(pc_nc, std::max(1, std::min((n_rows + KRY_PRE_RT - 1) / KRY_PRE_RT, 2 * NUM_SMS / pc_nc))), KRY_THREADS, sm_rows, s>>>(n, n_rows, wk);
+      }
+      if (trace) mark();
+      launches += 4;
+    }
     if (fused) {
       const size_t smem = (size_t) n * sizeof(double);
       int per_sm = 0;
@@ -1072,6 +1320,7 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
         else { cudaGetLastError(); fused = false; }
       }
     }
+    if (!fused) wk.nr = wk.n_col = 0;               // (the launches below iterate on A itself)
     if (!fused) {
     kry_post<0><<<post_blocks, KRY_THREADS, 0, s>>>(K, n, d_rows, n_rows, E.branching, S0, wk, pe);
     kry_begin<<<orth_blocks, KRY_THREADS, 0, s>>>(n, wk, pe, tol, max_it);
@@ -1120,6 +1369,14 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
     t.stop(launches);
     B200RT_CUDA(c, cudaMemcpyAsync(h_st + 63, wk.st, sizeof(KryState), cudaMemcpyDeviceToHost, s));
     B200RT_CUDA(c, cudaStreamSynchronize(s));
+    if (trace && fused && marks.size() == 4) {
+      float ms[3];
+      for (int q = 0; q < 3; q++) cudaEventElapsedTime(&ms[q], marks[q], marks[q + 1]);
+      fprintf(stderr, "krylov trace: preconditioner set-up [us]: block entries to all ranks %.1f  inverses %.1f  rows of A M^-1 %.1f\n",
+              ms[0] * 1e3, ms[1] * 1e3, ms[2] * 1e3);
+      for (auto ev : marks) cudaEventDestroy(ev);
+      marks.clear();
+    }
     if (trace && !marks.empty()) {
       double sum[4] = {0, 0, 0, 0};
       const int steps_traced = (int) marks.size() / 5;

@@ -215,9 +215,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the solve: one GPU factorises K where it was built (block LU); several GPUs leave the rows where they were built and
-    # iterate together (GMRES over peer memory, csrc/solve_krylov.cu) -- no row gather, no barrier, no broadcast of S
-    use_gmres = args.solver == "gmres" or (args.solver == "auto" and world > 1)
+    # the solve: right-preconditioned GMRES over the rows where they were built (csrc/solve_krylov.cu; what the library
+    # itself picks for this grid size) -- on several GPUs the ranks iterate together over peer memory: no row gather, no
+    # barrier, no broadcast of S.  --solver lu: the block LU on rank 0 (rows pushed there over peer memory).
+    use_gmres = args.solver in ("gmres", "auto")
+    if not use_gmres:
+        os.environ["B200RT_SOLVER"] = "lu"
     peer_ptrs, blocks = [], None
     if use_gmres:
         blocks = multi.connect_exchange(dist, ctx, rank, world)
@@ -430,12 +433,13 @@ def run_ours(args):
     if t_solve > 0 and use_gmres:
         sv = t_solve / K
         products = recs[-1]["solve_steps"] + 1                       # Arnoldi steps + the residual check
-        k_bytes = products * n_rows_mine * n_vox * 8.0
+        k_bytes = (products + 4) * n_rows_mine * n_vox * 8.0         # + the set-up: rows read and written twice
         rooflines["solve"] = {"kernel": "distributed GMRES (kry_post: this rank's rows of K x vector, once per step)", "bound": "hbm",
                               "achieved": k_bytes / sv / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": k_bytes / sv / 1e9 / hbm_peak,
                               "peak_kind": peak_kind, "launch_ms": sv * 1e3, "steps": recs[-1]["solve_steps"],
-                              "note": "algorithmic bytes = (steps + 1) x own rows x n_vox x 8; the rest of a step is the "
-                                      "orthogonalisation (3 short launches) and the wait for the peers' pieces"}
+                              "note": "algorithmic bytes = (steps + 1 + 4) x own rows x n_vox x 8 (one product per step, the "
+                                      "residual check, the preconditioner set-up's two passes over the rows); the rest of a "
+                                      "step is the orthogonalisation (~13 us) and the wait for the peers' pieces"}
     elif t_solve > 0:
         sv = t_solve / K
         rooflines["solve"] = {"kernel": "block LU (gemm128 DMMA.8x8x4 + cluster Gauss-Jordan)", "bound": "fp64 tensor",
@@ -462,7 +466,8 @@ def run_ours(args):
                                    f"{n_los} IUVS-like LOS brightness, n_subsamples=10",
                        "grid": GRID, "n_emissions": 1, "n_los": n_los, "ray_voxel_steps": int(steps_total),
                        "l2": "256 MB buffer written between timed iterations (L2 flush); K is 273 MB > L2",
-                       "solver": ("GMRES over the ranks' resident rows (b200rt_solve_distributed), tolerance 1e-13, "
+                       "solver": ("GMRES over the ranks' resident rows (b200rt_solve_distributed), right-preconditioned with the "
+                                  "inverted diagonal blocks of the SZA columns, tolerance 1e-13, "
                                   f"{recs[-1].get('solve_steps')} steps") if use_gmres else "block LU (DMMA) on one GPU",
                        "partition": ("one process per GPU: rows by source voxel, " +
                                      ("left where they were built (the ranks solve together over peer memory: no row gather, "
@@ -588,7 +593,7 @@ def main():
     ap.add_argument("--ref-stride", type=int, default=8, help="CPU sample: every k-th source-voxel row")
     ap.add_argument("--ref-los", type=int, default=50000, help="CPU sample: lines of sight per step")
     ap.add_argument("--solver", default="auto", choices=["auto", "lu", "gmres"],
-                    help="auto: block LU on one GPU, distributed GMRES (rows stay on their ranks) on several")
+                    help="auto / gmres: preconditioned GMRES over the rows where they were built; lu: block LU on rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the IPH and sweep measurements")
     ap.add_argument("--no-in-process", action="store_true", help="N > 1: skip the one-handle in-process arm on rank 0")

@@ -232,7 +232,8 @@ int b200rt_set_row_sink(b200rt_ctx *ctx, int i_emission, void *peer_K_dev);   /*
  * Knobs: B200RT_KRYLOV_TOL (relative residual of the Krylov recurrence, default 1e-13), B200RT_KRYLOV_MAXIT. */
 #define B200RT_KRYLOV_MAX_N 16384
 #define B200RT_KRYLOV_MAX_WORLD 16
-#define B200RT_KRYLOV_BLOCK_BYTES (B200RT_KRYLOV_MAX_WORLD * 128 + 2 * B200RT_KRYLOV_MAX_N * 8)
+#define B200RT_KRYLOV_MAX_NR 128
+#define B200RT_KRYLOV_BLOCK_BYTES (B200RT_KRYLOV_MAX_WORLD * 128 + 2 * B200RT_KRYLOV_MAX_N * 8 + (unsigned long long) B200RT_KRYLOV_MAX_N * B200RT_KRYLOV_MAX_NR * 8)
 int b200rt_solve_exchange(b200rt_ctx *ctx, void **block_dev, void *ipc_handle64);
 int b200rt_solve_distributed(b200rt_ctx *ctx, int rank, int world, void *const *blocks);
 int b200rt_last_solve_steps(b200rt_ctx *ctx, int *n_steps);   /* GMRES steps of the last distributed solve */

