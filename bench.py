@@ -437,6 +437,7 @@ def run_ours(args):
         rooflines["solve"] = {"kernel": "distributed GMRES (kry_post: this rank's rows of K x vector, once per step)", "bound": "hbm",
                               "achieved": k_bytes / sv / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": k_bytes / sv / 1e9 / hbm_peak,
                               "peak_kind": peak_kind, "launch_ms": sv * 1e3, "steps": recs[-1]["solve_steps"],
+                              "traffic": traffic.get("kry_loop"),
                               "note": "algorithmic bytes = (steps + 1 + 4) x own rows x n_vox x 8 (one product per step, the "
                                       "residual check, the preconditioner set-up's two passes over the rows); the rest of a "
                                       "step is the orthogonalisation (~13 us) and the wait for the peers' pieces"}

@@ -166,7 +166,14 @@ int b200rt_influence(b200rt_ctx *ctx, int v_begin, int v_end);
 /* the same for several ascending, disjoint source-voxel ranges in one call (singlet emissions): the interleaved shards
  * that balance the cost of low-altitude (long rays through many voxels) and high-altitude rows across GPUs */
 int b200rt_influence_ranges(b200rt_ctx *ctx, int n_ranges, const int *v_begin, const int *v_end);
-int b200rt_solve(b200rt_ctx *ctx);                      /* RT_grid::solve_gpu, emission_voxels::solve_gpu */
+/* RT_grid::solve_gpu, emission_voxels::solve_gpu: (I - w K) S = S0 per emission.  Two solvers behind it, both FP64 whatever
+ * the context's Real: a block LU without row exchanges (FP64 tensor-core DMMA; the matrix is checked to be diagonally
+ * dominant or an M-matrix first, B200RT_ERR_NOT_DOMINANT otherwise) and a right-preconditioned GMRES (see "distributed
+ * solve" below; with one rank it is simply the faster solve of a large system: 4.0 ms against 5.8 ms at 5841 unknowns).
+ * Systems of B200RT_KRYLOV_MIN_N (2048) unknowns and more whose rows were all built by this context take the GMRES and fall
+ * back to the LU if it does not converge; everything else takes the LU.  B200RT_SOLVER = lu | gmres overrides the size rule.
+ * Either way b200rt_last_residual reports the true relative residual afterwards. */
+int b200rt_solve(b200rt_ctx *ctx);
 /* ray-voxel steps executed by the last b200rt_influence call (one step = one
  * RT_grid::influence_update, RT_grid.hpp:90-105, covering all emissions) */
 int b200rt_last_step_count(b200rt_ctx *ctx, long long *n_steps);
@@ -213,7 +220,9 @@ int b200rt_set_row_sink(b200rt_ctx *ctx, int i_emission, void *peer_K_dev);   /*
  * piece of the result into every rank's EXCHANGE BLOCK over peer memory (NVLink), then every rank orthogonalises the
  * assembled vector redundantly -- bit-identical on all ranks -- so S ends up resident on every rank with no row gather,
  * no broadcast and no host barrier.  K is the kernel of a second-kind integral equation: the step count does not grow
- * with the grid (~70 for the H Lyman alpha corona at 1e-13; csrc/solve_krylov.cu).
+ * with the grid (csrc/solve_krylov.cu).  Right preconditioner on spherical grids: the inverted diagonal blocks of I - wK
+ * over the SZA columns (all radial voxels of one SZA index), whose entries every rank contributes for its rows in one more
+ * exchange round and which every rank inverts redundantly; 38 steps instead of 71 on the 100x60 grid at 1e-13.
  *   b200rt_solve_exchange:    this context's exchange block (B200RT_KRYLOV_BLOCK_BYTES of device memory, allocated on
  *                             first use, alive until destroy): its device pointer (ranks of one process, peer access
  *                             enabled) and/or a CUDA IPC handle of it (64 bytes; other processes open it with
@@ -229,7 +238,8 @@ int b200rt_set_row_sink(b200rt_ctx *ctx, int i_emission, void *peer_K_dev);   /*
  *                             instead of the LU).  Singlet emissions, n_vox <= B200RT_KRYLOV_MAX_N.
  * A device group (b200rt_create_multi) does this behind b200rt_solve / b200rt_generate_S for grids of
  * B200RT_KRYLOV_MIN_N (default 2048) voxels and more; smaller systems keep the LU on the owning device.
- * Knobs: B200RT_KRYLOV_TOL (relative residual of the Krylov recurrence, default 1e-13), B200RT_KRYLOV_MAXIT. */
+ * Knobs: B200RT_KRYLOV_TOL (relative residual of the Krylov recurrence, default 1e-13), B200RT_KRYLOV_MAXIT,
+ * B200RT_KRYLOV_PC=0 (no preconditioner). */
 #define B200RT_KRYLOV_MAX_N 16384
 #define B200RT_KRYLOV_MAX_WORLD 16
 #define B200RT_KRYLOV_MAX_NR 128

@@ -25,7 +25,7 @@ open(os.path.join(P, f"{tag}_launches_summary.txt"), "w").write(
 full, traffic = "", {}
 if os.path.exists(os.path.join(P, "roofline_traffic.json")):
     traffic = json.load(open(os.path.join(P, "roofline_traffic.json")))
-for k in ("brightness_kernel", "march_kernel", "traverse_kernel", "traverse_los", "gemm128_kernel"):
+for k in ("brightness_kernel", "march_kernel", "traverse_kernel", "traverse_los", "gemm128_kernel", "kry_loop"):
     rep = os.path.join(G, f"prof_{k}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue

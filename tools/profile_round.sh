@@ -13,11 +13,11 @@ echo "launch list rc=$?"
 # name -> kernel regex (the voxel-ray and the line-of-sight instantiations of the traversal are captured separately)
 # ncu matches -k against the function name without template arguments unless --kernel-name-base demangled is given
 declare -A RX=( [brightness_kernel]="brightness_kernel" [march_kernel]="march_kernel" [traverse_kernel]="traverse_fast_kernel<double, .bool.1"
-                [traverse_los]="traverse_fast_kernel<double, .bool.0" [gemm128_kernel]="gemm128_kernel<.int.1, " )
+                [traverse_los]="traverse_fast_kernel<double, .bool.0" [gemm128_kernel]="gemm128_kernel<.int.1, " [kry_loop]="kry_loop" )
 # launches of the matched kernel to skip: the first <double, false> traversal of a step is the sun-ward rays of the single
 # scattering (n_vox rays), the second the lines of sight
 declare -A SKIP=( [traverse_los]=1 )
-for K in ${KERNELS:-brightness_kernel march_kernel traverse_kernel traverse_los gemm128_kernel}; do
+for K in ${KERNELS:-brightness_kernel march_kernel traverse_kernel traverse_los kry_loop}; do
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:${RX[$K]}" -s ${SKIP[$K]:-0} -c 1 -f -o $OUT/prof_${K}_$TAG $CMD > $OUT/ncu_${K}_$TAG.log 2>&1
   echo "$K rc=$?"
 done
