@@ -304,7 +304,7 @@ __device__ __forceinline__ double slice_sum(double f, double *scratch) {
   __syncthreads();
   return s;
 }
-// thread 0 waits until every rank has posted `round` into this rank's block; false (and st->error) after 4 s
+// thread 0 waits until every rank has posted `round` into this rank's block; false (and st->error) after 20 s
 __device__ __forceinline__ bool wait_round(KryState *st, const KryPeers &pe, unsigned long long round, int *sh_ok) {
   if (threadIdx.x == 0) {
     const KryExchange *mine = pe.p[pe.rank];
@@ -314,7 +314,7 @@ __device__ __forceinline__ bool wait_round(KryState *st, const KryPeers &pe, uns
       unsigned int spins = 0;
       while (ld_flag(&mine->flag[q][0]) < round) {
         __nanosleep(64);
-        if ((++spins & 1023u) == 0 && global_ns() - t0 > 4000000000ull) { ok = 0; break; }
+        if ((++spins & 1023u) == 0 && global_ns() - t0 > 20000000000ull) { ok = 0; break; }
       }
     }
     if (!ok) { st->error = 1; st->done = 1; }
@@ -679,7 +679,7 @@ kry_pre_rows(int n, int n_rows, KryWork wk) {
 // publishes the step sequence every CTA waits on.  The same algorithm with the same fixed order of every sum as the launches above
 // (the two forms differ in where 1 / |w| multiplies the product, i.e. by rounding).  Everything one CTA reads that another wrote inside the launch goes through L2
 // (ld.cg / volatile): L1 is not coherent between SMs.  Every spin loop leaves when st->error is raised (CTA 0 raises it
-// when a peer has not posted for 4 s), so a missing rank ends the launch on every rank instead of hanging it.
+// when a peer has not posted for 20 s), so a missing rank ends the launch on every rank instead of hanging it.
 struct KryLoopArgs {
   const double *K;
   const int *rows;
@@ -748,7 +748,7 @@ __device__ __forceinline__ bool peers_posted(KryState *st, const KryPeers &pe, u
         __nanosleep(20);
         if ((++spins & 127u) == 0) {
           if (ld_vol_i32(&st->error)) { ok = 0; break; }
-          if (blockIdx.x == 0 && global_ns() - t0 > 4000000000ull) {
+          if (blockIdx.x == 0 && global_ns() - t0 > 20000000000ull) {
             *reinterpret_cast<volatile int *>(&st->error) = 1;
             ok = 0;
             break;
@@ -1444,7 +1444,7 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
     if (fin.error == 2)
       return fail(c, B200RT_ERR_STATE, "b200rt_solve_distributed: the rows the ranks built do not add up to the grid (every voxel must be in exactly one rank's influence call)");
     if (fin.error)
-      return fail(c, B200RT_ERR_CUDA, "b200rt_solve_distributed: a peer never posted its rows (4 s): all ranks must call it, with the same grid");
+      return fail(c, B200RT_ERR_CUDA, "b200rt_solve_distributed: a peer never posted its rows (20 s): all ranks must call it, with the same grid");
     if (!fin.converged)
       return fail(c, B200RT_ERR_NOT_DOMINANT, "b200rt_solve_distributed: GMRES residual " + std::to_string(fin.res) + " after " +
                                                   std::to_string(fin.iter) + " steps (rows missing on some rank, or a matrix the LU path should take)");

@@ -233,7 +233,7 @@ int b200rt_set_row_sink(b200rt_ctx *ctx, int i_emission, void *peer_K_dev);   /*
  *                             resident on every rank (b200rt_get_solution, b200rt_brightness*), b200rt_last_residual
  *                             is the true relative residual |S0 - (I - wK) S| / |S0| and b200rt_last_kernel_ms
  *                             (B200RT_PHASE_SOLVE) counts the launches.  The union of the ranks' rows must be every
- *                             voxel; a rank that never arrives is reported (B200RT_ERR_CUDA) after 4 s, no convergence
+ *                             voxel; a rank that never arrives is reported (B200RT_ERR_CUDA) after 20 s, no convergence
  *                             within 160 steps as B200RT_ERR_NOT_DOMINANT.  world = 1 is allowed (one GPU, GMRES
  *                             instead of the LU).  Singlet emissions, n_vox <= B200RT_KRYLOV_MAX_N.
  * A device group (b200rt_create_multi) does this behind b200rt_solve / b200rt_generate_S for grids of
