@@ -22,6 +22,7 @@
 // resetting; the vector slots alternate with the round (a rank can be at most one round ahead of a peer that still reads).
 #include <cstddef>
 #include <cstdio>
+#include <mutex>
 #include "api_internal.hpp"
 
 namespace b200rt {
@@ -700,11 +701,19 @@ __device__ __forceinline__ unsigned int ld_acq_u32(const unsigned int *p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ bool spin_until(const unsigned int *ctr, unsigned int target, const KryState *st) {
+__device__ __forceinline__ bool spin_until(const unsigned int *ctr, unsigned int target, KryState *st) {
   unsigned int spins = 0;
+  unsigned long long t0 = 0;
   while (ld_acq_u32(ctr) < target) {
     __nanosleep(16);
-    if ((++spins & 127u) == 0 && ld_vol_i32(&st->error)) return false;
+    if ((++spins & 127u) == 0) {
+      if (ld_vol_i32(&st->error)) return false;
+      // a barrier of this launch that does not open for 30 s: part of the grid never became resident (another resident
+      // grid of another context holds the SMs): give up on every CTA instead of hanging the device
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 30000000000ull) { *reinterpret_cast<volatile int *>(&st->error) = 3; return false; }
+    }
   }
   return true;
 }
@@ -1206,6 +1215,11 @@ size_t carve_bytes(size_t &off, size_t bytes) {
 
 namespace api {
 
+// Single-rank solves of different contexts on ONE device take turns: each is a cooperative launch that waits on its own
+// barriers, and two such grids that each got part of the SMs would wait for each other's slots.  (Ranks of ONE solve that
+// share a device -- the tests, a device group naming a device twice -- must run side by side and size their grids to fit.)
+static std::mutex g_single_rank_solve[64];
+
 int exchange_block(b200rt_ctx *c, void **dev_ptr) {
   if (!c->kry_xchg.p) {
     B200RT_CUDA(c, c->kry_xchg.ensure(sizeof(KryExchange)));
@@ -1226,6 +1240,8 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
   if (blocks[rank] != c->kry_xchg.p)
     return fail(c, B200RT_ERR_ARG, "b200rt_solve_distributed: blocks[rank] is not this context's exchange block");
   if (reset_timer) PhaseTimer::reset(c);
+  std::unique_lock<std::mutex> turn;
+  if (world == 1) turn = std::unique_lock<std::mutex>(g_single_rank_solve[c->device & 63]);
 
   // the rows this rank multiplies: what its last influence call built
   std::vector<int> rows;
@@ -1441,6 +1457,9 @@ int solve_distributed(b200rt_ctx *c, int rank, int world, void *const *blocks, b
               fin.t_phase[3] * 1e-3 / fin.iter);
     c->kry_round_base = fin.round;
     c->kry_last_iters = fin.iter;
+    if (fin.error == 3)
+      return fail(c, B200RT_ERR_CUDA, "b200rt_solve_distributed: the resident grid of the solve never became complete (30 s): another resident "
+                                      "grid on this device holds its SMs (B200RT_KRYLOV_CTAS limits the grid; B200RT_KRYLOV_FUSED=0 avoids it)");
     if (fin.error == 2)
       return fail(c, B200RT_ERR_STATE, "b200rt_solve_distributed: the rows the ranks built do not add up to the grid (every voxel must be in exactly one rank's influence call)");
     if (fin.error)
