@@ -13,10 +13,14 @@
 // iteration stops -- are bit-identical on all ranks and nothing else is ever exchanged.  No row gather, no broadcast of
 // S, no host barrier: the only synchronisation is a kernel of rank r waiting for the round counters of its peers.
 //
-// Per step (4 launches): kry_post<1>  x = w / |w| -> V[j];  (x - w K x)[own rows] -> every block;  post round
-//                        kry_orth<0>  wait for the round;  w = assembled vector;  partial V^T w per slice
-//                        kry_orth<1>  h1 = sum of partials;  w -= V h1;  partial V^T w          (classical Gram-Schmidt, twice)
-//                        kry_orth<2>  h2;  w -= V h2;  |w|^2 partials;  last CTA: Hessenberg column, Givens, residual, stop?
+// Three parts below.  (1) The algorithm as separate launches, four per step -- the first form built, kept as the fallback
+// when a cooperative launch does not fit (B200RT_KRYLOV_FUSED=0 selects it; it iterates on A itself):
+//     kry_post<1>  x = w / |w| -> V[j];  (x - w K x)[own rows] -> every block;  post round
+//     kry_orth<0>  wait for the round;  w = assembled vector;  partial V^T w per slice
+//     kry_orth<1>  h1 = sum of partials;  w -= V h1;  partial V^T w          (classical Gram-Schmidt, twice)
+//     kry_orth<2>  h2;  w -= V h2;  |w|^2 partials;  last CTA: Hessenberg column, Givens, residual, stop?
+// (2) The right preconditioner's set-up (kry_pre_*): diagonal blocks of A over the SZA columns, inverted on every rank, and
+// the own rows of A M^-1.  (3) kry_loop: the whole iteration as ONE cooperative launch per rank -- the default.
 // All sums run in a fixed order (no floating-point atomics): deterministic, and identical on every rank.
 // The round counters are monotonic over the life of a block and every rank runs the same rounds, so they never need
 // resetting; the vector slots alternate with the round (a rank can be at most one round ahead of a peer that still reads).
@@ -85,9 +89,6 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_flag_relaxed(unsigned long long *p, unsigned long long v) {   // after a system-wide fence
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
