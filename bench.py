@@ -294,7 +294,10 @@ def run_ours(args):
         ctx.influence_ranges(v_ranges)
         sol = ctx.solution(0, want_S=False)                     # D2H: S0 + optical depths
         w1 = time.perf_counter()
-        if use_gmres:
+        if use_gmres and world == 1:
+            ctx.solve()                                         # the reference-facing call: the library picks the GMRES itself at this size
+            S = ctx.solution(0)["S"]                            # D2H: S
+        elif use_gmres:
             ctx.solve_distributed(rank, world, blocks)
             S = ctx.solution(0)["S"]                            # D2H: S
         elif world > 1:
