@@ -90,8 +90,14 @@ __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_flag_relaxed(unsigned long long *p, unsigned long long v) {   // after a system-wide fence
+__device__ __forceinline__ void st_flag_relaxed(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// the round flag: a system-scope release by the posting thread (one thread per peer, all at once), so that everything this
+// CTA has observed -- every CTA's pieces, already fenced system-wide by their authors -- is ordered before the flag for
+// the peer that acquires it
+__device__ __forceinline__ void st_flag_release(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ double ld_remote(const double *p) {       // written by a peer: never through L1
   double v;
@@ -191,11 +197,8 @@ kry_post(const double *__restrict__ K, int n, const int *__restrict__ rows, int 
   }
   __syncthreads();
   if (sh_row && tid < pe.world) {                  // post the round on every rank, one thread per peer
-    if (MODE == 0) {                               // row census, read by the peer after it has seen the round
-      st_flag_relaxed(&pe.p[tid]->flag[pe.rank][1], (unsigned long long) n_rows);
-      __threadfence_system();
-    }
-    st_flag_relaxed(&pe.p[tid]->flag[pe.rank][0], round + 1);
+    if (MODE == 0) st_flag_relaxed(&pe.p[tid]->flag[pe.rank][1], (unsigned long long) n_rows);   // row census, read after the round
+    st_flag_release(&pe.p[tid]->flag[pe.rank][0], round + 1);
   }
 }
 
@@ -534,7 +537,7 @@ __device__ __forceinline__ void post_round_tail(KryState *st, const KryPeers &pe
     }
   }
   __syncthreads();
-  if (*sh && tid < pe.world) st_flag_relaxed(&pe.p[tid]->flag[pe.rank][0], round + 1);
+  if (*sh && tid < pe.world) st_flag_release(&pe.p[tid]->flag[pe.rank][0], round + 1);
 }
 
 __global__ void __launch_bounds__(128)
@@ -893,8 +896,8 @@ __device__ __forceinline__ void loop_post(const KryLoopArgs &a, double *xs, doub
   }
   // The threads that stored pieces fence them system-wide (in parallel, once per CTA); when that fence returns the pieces
   // are in the peers' memory, so everything after it -- the ticket, the last CTA's flags -- only has to come later in
-  // time.  The last CTA posts the round on all ranks at once, one thread per peer: posting them one after the other with
-  // release stores cost a round trip over NVLink per peer (measured on eight GPUs: 20 us of a 55 us step).
+  // time.  The last CTA posts the round on all ranks at once, one thread per peer (a release store each): posting them
+  // one after the other from one thread cost a round trip over NVLink per peer (measured on eight GPUs: 20 us of a 55 us step).
   if ((WARP_ROWS ? lane : tid) < a.pe.world) __threadfence_system();
   __syncthreads();
   if (tid == 0) {
@@ -910,11 +913,8 @@ __device__ __forceinline__ void loop_post(const KryLoopArgs &a, double *xs, doub
   }
   __syncthreads();
   if (sh_row[0] && tid < a.pe.world) {
-    if (MODE == 0) {                               // row census, read by the peer after it has seen the round
-      st_flag_relaxed(&a.pe.p[tid]->flag[a.pe.rank][1], (unsigned long long) a.n_rows);
-      __threadfence_system();
-    }
-    st_flag_relaxed(&a.pe.p[tid]->flag[a.pe.rank][0], round + 1);
+    if (MODE == 0) st_flag_relaxed(&a.pe.p[tid]->flag[a.pe.rank][1], (unsigned long long) a.n_rows);   // row census, read after the round
+    st_flag_release(&a.pe.p[tid]->flag[a.pe.rank][0], round + 1);
   }
   __syncthreads();
 }
