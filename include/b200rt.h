@@ -51,12 +51,16 @@ int b200rt_device_count(void);
  * observation_fit::generate_source_function + brightness, observation_fit.cpp:122-169,491-516), so the handle fans
  * each call out itself and every other entry point of this header takes it unchanged:
  *   geometry, emission tables, source function: replicated on every device;
- *   b200rt_generate_S / b200rt_influence*:      source-voxel rows split into interleaved shards; the devices write
- *                                               their finished row batches into the resident K of the device that
- *                                               solves that emission (emission e: device e mod n; one emission: the
- *                                               first device) over peer memory (copy engines, NVLink) while marching
- *                                               the next batch;
- *   b200rt_solve:                               each emission on its device, side by side; S handed to the others;
+ *   b200rt_generate_S / b200rt_influence*:      source-voxel rows split into interleaved shards.  Grids of
+ *                                               B200RT_KRYLOV_MIN_N (2048) voxels and more: the rows STAY on the devices
+ *                                               that built them.  Smaller grids: the devices write their finished row
+ *                                               batches into the resident K of the device that solves that emission
+ *                                               (emission e: device e mod n; one emission: the first device) over peer
+ *                                               memory (copy engines, NVLink) while marching the next batch;
+ *   b200rt_solve:                               large grids: all devices together, each multiplying its own rows
+ *                                               ("distributed solve" below), S resident everywhere afterwards; small
+ *                                               grids: each emission's LU on its device, side by side, S handed over;
+ *   b200rt_get_influence, b200rt_influence_dev: the assembled matrix on the first device (rows gathered on demand);
  *   b200rt_brightness*, b200rt_iph_*:           lines of sight split by index, results at their offsets in the
  *                                               caller's arrays; counters add up, b200rt_last_kernel_ms is the
  *                                               slowest device's time.
@@ -207,7 +211,8 @@ int b200rt_sourcefn_dev(b200rt_ctx *ctx, int i_emission, void **S_dev);
  * (b200rt_ipc_open -> a device pointer valid in their process) and name it as their row sink; from then on
  * b200rt_influence(v_begin, v_end) marches its range in >= 4 batches and DMAs each finished batch into the sink with
  * the copy engines over NVLink WHILE the next batch is marched (no SMs, no collective kernel), and returns when the
- * rows have landed.  A host barrier across ranks then releases the solve.  Singlet emissions only. */
+ * rows have landed.  A host barrier across ranks then releases the solve.  Singlet emissions only.
+ * (This is the form for a solve by factorisation on one GPU; the distributed solve below needs no row exchange at all.) */
 int b200rt_ipc_export_influence(b200rt_ctx *ctx, int i_emission, void *handle64);
 int b200rt_ipc_open(b200rt_ctx *ctx, const void *handle64, void **peer_ptr);
 int b200rt_ipc_close(b200rt_ctx *ctx, void *peer_ptr);
