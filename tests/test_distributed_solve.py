@@ -144,3 +144,26 @@ def test_two_devices(synth, binding):
     for m in models:
         assert rel_err(S_lu[0], m.vectors(0)["S"], floor=1e-30) < 1e-7
     assert np.array_equal(models[0].vectors(0)["S"], models[1].vectors(0)["S"])
+
+
+def test_b200rt_solve_picks_by_size_and_falls_back(synth, binding, monkeypatch):
+    """b200rt_solve on a context that built every row: GMRES from B200RT_KRYLOV_MIN_N unknowns, the LU below -- and the LU
+    again when the iteration is cut short before it converges"""
+    scn = synth.make_scenario(20, 12, 6, 8, n_em=1)
+    G = binding.GpuModel(scn, "f64")
+    G.build_rows()
+    G.solve()                                                        # 209 unknowns: the LU
+    S_lu = G.vectors(0)["S"].copy()
+    assert G.ctx.kernel_ms(binding.PH_SOLVE)[1] > 5                  # its launches
+    monkeypatch.setenv("B200RT_KRYLOV_MIN_N", "50")
+    G.solve()                                                        # now the iteration (one launch + the set-up)
+    assert G.ctx.kernel_ms(binding.PH_SOLVE)[1] <= 5 and 3 < G.ctx.last_solve_steps() < 100
+    assert rel_err(S_lu, G.vectors(0)["S"], floor=1e-30) < 1e-9 and G.ctx.residual(0) < 1e-12
+    monkeypatch.setenv("B200RT_KRYLOV_MAXIT", "3")
+    G.solve()                                                        # cut short -> not converged -> the LU decides
+    assert G.ctx.last_solve_steps() == 3
+    assert np.array_equal(G.vectors(0)["S"], S_lu) and G.ctx.residual(0) < 1e-12
+    monkeypatch.setenv("B200RT_SOLVER", "lu")
+    monkeypatch.delenv("B200RT_KRYLOV_MAXIT")
+    G.solve()
+    assert np.array_equal(G.vectors(0)["S"], S_lu)
